@@ -1,0 +1,108 @@
+/* kocr.h - C ABI of the B200-native text-line recogniser (libkocr_b200.so).
+ *
+ * Drop-in boundary for the recognition forward path of netra-ai-lab/Khmer-OCR-CNN-Transformer.
+ * The reference has no FFI layer (pure Python on torch); these entry points are what a binding
+ * for the path's stages would call.  Each one names the reference code it replaces
+ * (paths relative to netra_ocr/recognition/).
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every function returns 0 on success and
+ * a non-zero status on failure; kocr_last_error() then returns a thread-local message.  Nothing
+ * throws across the boundary.  A handle owns its device weights and workspace, is bound to one
+ * GPU, and must be used from one host thread at a time.  `stream` is a cudaStream_t passed as
+ * void* (NULL = the legacy default stream).  There is NO CPU fallback: without a CUDA device every
+ * compute entry fails with an error.
+ */
+#ifndef KOCR_H_
+#define KOCR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KOCR_ABI_VERSION 1
+#define KOCR_TOKENS_LD 257          /* 1 <sos> + up to 256 generated ids per line */
+
+typedef struct kocr_handle kocr_handle;
+
+/* ABI version of the loaded library (== KOCR_ABI_VERSION). */
+int kocr_abi_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* kocr_last_error(void);
+
+/* Build a recogniser from a packed weight blob (see khmer_ocr_cnn_transformer_b200/weights.py:
+ * reference state_dict -> BN-folded, K-major bf16 GEMM operands + fp32 vectors).
+ * Replaces OCRPredictor.__init__/_load_weights (predictor.py:13-46).
+ * max_lines / max_chunks bound one batch; the workspace is allocated here, once. */
+int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_lines, int max_chunks,
+                kocr_handle** out);
+int kocr_destroy(kocr_handle* h);
+
+/* Bytes of device memory held by the handle (weights + workspace). */
+size_t kocr_workspace_bytes(const kocr_handle* h);
+
+/* Model facts read from the blob: variant (0 = SE-VGG + BiLSTM, 1 = VGG baseline), emb_dim,
+ * max_seq_len (global_pos rows), decode_max_len, vocab size.  (utils.py:14-43 autodetect_config) */
+int kocr_model_info(const kocr_handle* h, int* variant, int* emb_dim, int* max_seq_len, int* decode_max_len,
+                    int* vocab_size);
+
+/* Stage 1 - ImagePreprocessor.process for a batch of grey lines (preprocessor.py:35-58) including
+ * Pillow's BILINEAR resize to height 48, 48x100/overlap-16 chunking, white padding, normalisation.
+ * pixels: concatenated uint8 (h_i x w_i) images, on the host (pixels_on_device = 0; copied with
+ * cudaMemcpyAsync) or already on the device (1).  offsets[i] = byte offset of line i.
+ * chunk_counts_out[i] (host, may be NULL) receives the chunks kept for line i
+ * (= min(ceil(W'/84), ceil(max_seq_len/32))).  Leaves fp32 (n,1,48,100) chunks in the workspace. */
+int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes, int pixels_on_device,
+                       const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n_lines,
+                       int32_t* chunk_counts_out, void* stream);
+
+/* Stages 2-4 - model.cnn -> model.patch -> model.enc on all chunks of the batch
+ * (predictor.py:166-170; se_model.py:63-79,104-117,119-126), then merge + global_pos
+ * (predictor.py:174-183).  Consumes the chunks left by kocr_gather_chunks. */
+int kocr_sevgg_encoder_forward(kocr_handle* h, void* stream);
+
+/* Stage 5a - context_bilstm over each line's merged sequence (predictor.py:185-186;
+ * se_model.py:228-234) and the decoder's cross-attention K/V precompute.  For the VGG baseline
+ * (no BiLSTM) the merged sequence is the memory. */
+int kocr_merge_bilstm_forward(kocr_handle* h, void* stream);
+
+/* Stage 5b - OCRPredictor._greedy_decode for every line of the batch (predictor.py:85-99) with a
+ * KV cache.  tokens_out: host int32 [n_lines, KOCR_TOKENS_LD], row = <sos> then generated ids;
+ * lengths_out: host int32 [n_lines] = number of valid entries in the row (eos is not stored).
+ * max_steps <= decode_max_len (0 = decode_max_len).  Synchronises the stream before returning. */
+int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream);
+
+/* Whole path, host in / host out: gather_chunks -> sevgg_encoder_forward -> merge_bilstm_forward ->
+ * decode_greedy.  This is what OCRPredictor.predict_batch (predictor.py:138-199) calls per batch. */
+int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes, int pixels_on_device,
+                         const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n_lines,
+                         int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream);
+
+/* Options (tests / parity tooling):
+ *   "trace_logits"  1 -> decode_greedy records the last-position logits of every step
+ *   "force_tokens"  1 -> decode_greedy feeds the ids set with kocr_set_forced_tokens instead of its argmax */
+int kocr_set_option(kocr_handle* h, const char* name, int value);
+int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens /* [n_lines, KOCR_TOKENS_LD] */, int n_lines);
+
+/* Copy an intermediate of the last batch to the host (tests only).  Names: "chunks" f32 (n,1,48,100);
+ * "pool1" "pool2" "conv3" "conv4" "pool3" "conv5" "conv6" "pool4" "conv7" bf16 padded-linear activations;
+ * "patch_in" bf16 [n*32,1024]; "enc" f32 [n*32,384] (encoder output + global_pos); "memory" f32 [tokens,384];
+ * "logits_trace" f32 [n_lines, steps, 128].  Returns the byte size through *bytes_out when dst is NULL. */
+int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t kocr_launch_count(void);
+
+/* Unit-test hook for the tcgen05 GEMM: D = A[rowsA,cin] (x taps, row-shifted) * W[N, taps*cin]^T + bias,
+ * device pointers, bf16 operands.  impl 0 = tcgen05 kernel, 1 = CUDA-core check kernel. */
+int kocr_test_gemm(int impl, const void* a_bf16, int64_t rows_a, const void* w_bf16, int m, int n, int taps, int cin,
+                   const int32_t* tap_off, const float* bias, int relu, int pl_h, int pl_w, float* out_f32,
+                   void* out_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOCR_H_ */

@@ -1,0 +1,185 @@
+"""ctypes binding of libkocr_b200.so (include/kocr.h).  No CPU fallback: a missing library or a
+missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libkocr_b200.so"
+TOKENS_LD = 257
+
+EXPORTS = [
+    "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
+    "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
+    "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm",
+]
+
+_lib = None
+
+
+class KocrError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the in-tree library (building it with nvcc first if it is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+        if _build.needs_build():
+            _build.build()
+    if not LIB_PATH.exists():
+        raise KocrError(f"{LIB_PATH} is missing: run `python -m khmer_ocr_cnn_transformer_b200.build` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    lib.kocr_abi_version.restype = i32
+    lib.kocr_last_error.restype = C.c_char_p
+    lib.kocr_create.argtypes = [vp, sz, i32, i32, i32, C.POINTER(vp)]
+    lib.kocr_destroy.argtypes = [vp]
+    lib.kocr_workspace_bytes.argtypes = [vp]
+    lib.kocr_workspace_bytes.restype = sz
+    lib.kocr_model_info.argtypes = [vp] + [C.POINTER(i32)] * 5
+    lib.kocr_gather_chunks.argtypes = [vp, vp, sz, i32, vp, vp, vp, i32, vp, vp]
+    lib.kocr_sevgg_encoder_forward.argtypes = [vp, vp]
+    lib.kocr_merge_bilstm_forward.argtypes = [vp, vp]
+    lib.kocr_decode_greedy.argtypes = [vp, i32, vp, vp, vp]
+    lib.kocr_recognize_lines.argtypes = [vp, vp, sz, i32, vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.kocr_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.kocr_set_forced_tokens.argtypes = [vp, vp, i32]
+    lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.kocr_launch_count.restype = i64
+    lib.kocr_test_gemm.argtypes = [i32, vp, i64, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp]
+    for f in ("kocr_create", "kocr_destroy", "kocr_model_info", "kocr_gather_chunks",
+              "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward", "kocr_decode_greedy",
+              "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens", "kocr_debug_read",
+              "kocr_test_gemm"):
+        getattr(lib, f).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load_library().kocr_last_error().decode("utf-8", "replace")
+        raise KocrError(f"libkocr_b200 error {rc}: {msg}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+class LineBatch:
+    """Concatenated grey uint8 line images + the offset/height/width tables the C ABI takes."""
+
+    def __init__(self, images):
+        hs, ws, offs, total = [], [], [], 0
+        for im in images:
+            if im.ndim != 2 or im.dtype != np.uint8:
+                raise ValueError("line images must be 2-D uint8 (grey) arrays")
+            hs.append(im.shape[0]); ws.append(im.shape[1]); offs.append(total)
+            total += im.size
+        self.n = len(images)
+        self.pixels = np.empty(max(total, 1), np.uint8)
+        for im, o in zip(images, offs):
+            self.pixels[o:o + im.size] = im.reshape(-1)
+        self.pixel_bytes = total
+        self.offsets = np.asarray(offs, np.int64)
+        self.heights = np.asarray(hs, np.int32)
+        self.widths = np.asarray(ws, np.int32)
+
+
+class Recognizer:
+    """Thin owner of a `kocr_handle` (one per GPU, one host thread)."""
+
+    DEBUG_DTYPES = {"chunks": np.float32, "enc": np.float32, "memory": np.float32, "logits_trace": np.float32}
+
+    def __init__(self, weight_blob: bytes, device: int = 0, max_lines: int = 256, max_chunks: int = 4096):
+        self.lib = load_library()
+        if self.lib.kocr_abi_version() != 1:
+            raise KocrError("ABI version mismatch between _native.py and libkocr_b200.so")
+        self._h = C.c_void_p()
+        buf = (C.c_char * len(weight_blob)).from_buffer_copy(weight_blob)
+        check(self.lib.kocr_create(buf, len(weight_blob), device, max_lines, max_chunks, C.byref(self._h)))
+        self.max_lines, self.max_chunks, self.device = max_lines, max_chunks, device
+        v = [C.c_int() for _ in range(5)]
+        check(self.lib.kocr_model_info(self._h, *[C.byref(x) for x in v]))
+        self.variant, self.emb_dim, self.max_seq_len, self.decode_max_len, self.vocab_size = [x.value for x in v]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.kocr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stages ---------------------------------------------------------------------------
+    def gather_chunks(self, batch: LineBatch, stream=None, pixels_dev_ptr=None):
+        counts = np.zeros(max(batch.n, 1), np.int32)
+        pix = _ptr(pixels_dev_ptr) if pixels_dev_ptr is not None else _ptr(batch.pixels)
+        check(self.lib.kocr_gather_chunks(self._h, pix, batch.pixel_bytes, 1 if pixels_dev_ptr is not None else 0,
+                                          _ptr(batch.offsets), _ptr(batch.heights), _ptr(batch.widths), batch.n,
+                                          _ptr(counts), _ptr(stream)))
+        return counts[:batch.n]
+
+    def sevgg_encoder_forward(self, stream=None):
+        check(self.lib.kocr_sevgg_encoder_forward(self._h, _ptr(stream)))
+
+    def merge_bilstm_forward(self, stream=None):
+        check(self.lib.kocr_merge_bilstm_forward(self._h, _ptr(stream)))
+
+    def decode_greedy(self, n_lines: int, max_steps: int = 0, stream=None):
+        tokens = np.zeros((max(n_lines, 1), TOKENS_LD), np.int32)
+        lengths = np.zeros(max(n_lines, 1), np.int32)
+        check(self.lib.kocr_decode_greedy(self._h, max_steps, _ptr(tokens), _ptr(lengths), _ptr(stream)))
+        return tokens[:n_lines], lengths[:n_lines]
+
+    def recognize_lines(self, batch: LineBatch, max_steps: int = 0, stream=None, pixels_dev_ptr=None,
+                        tokens_out=None, lengths_out=None):
+        tokens = tokens_out if tokens_out is not None else np.zeros((max(batch.n, 1), TOKENS_LD), np.int32)
+        lengths = lengths_out if lengths_out is not None else np.zeros(max(batch.n, 1), np.int32)
+        pix = _ptr(pixels_dev_ptr) if pixels_dev_ptr is not None else _ptr(batch.pixels)
+        check(self.lib.kocr_recognize_lines(self._h, pix, batch.pixel_bytes, 1 if pixels_dev_ptr is not None else 0,
+                                            _ptr(batch.offsets), _ptr(batch.heights), _ptr(batch.widths), batch.n,
+                                            max_steps, _ptr(tokens), _ptr(lengths), _ptr(stream)))
+        return tokens[:batch.n], lengths[:batch.n]
+
+    # ---- test hooks -----------------------------------------------------------------------
+    def set_option(self, name: str, value: int):
+        check(self.lib.kocr_set_option(self._h, name.encode(), int(value)))
+
+    def set_forced_tokens(self, tokens: np.ndarray):
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        assert tokens.ndim == 2 and tokens.shape[1] == TOKENS_LD
+        check(self.lib.kocr_set_forced_tokens(self._h, _ptr(tokens), tokens.shape[0]))
+
+    def debug_read(self, name: str) -> np.ndarray:
+        n = C.c_size_t()
+        check(self.lib.kocr_debug_read(self._h, name.encode(), None, 0, C.byref(n)))
+        if name == "last_steps":
+            return np.asarray(n.value)
+        dtype = self.DEBUG_DTYPES.get(name, np.uint16)       # bf16 buffers come back as raw uint16
+        out = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
+        check(self.lib.kocr_debug_read(self._h, name.encode(), _ptr(out), out.nbytes, C.byref(n)))
+        return out
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.kocr_workspace_bytes(self._h))
+
+
+def launch_count() -> int:
+    return int(load_library().kocr_launch_count())

@@ -1,0 +1,346 @@
+// Persistent, warp-specialised tcgen05 GEMM (see gemm_tc.cuh for the contract).
+//
+// CTA = 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Tile = 128 (M) x BN (N, 128 or 256), K step 64 bf16 = one 128-byte swizzle atom per row.
+// Accumulators: 2 stages x BN fp32 columns in TMEM so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Operands: NSTAGE-deep ring of {A 16 KB, B BN*128 B} in shared memory.
+#include "gemm_tc.cuh"
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace kocr {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;
+
+template <int BN> struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NSTAGE = (BN == 256) ? 4 : 6;          // 192 KB of operands
+    static constexpr int TMEM_COLS = 2 * BN;                    // 256 / 512
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmKernelParams {
+    int M, N, taps, cin_blocks;      // cin_blocks = cin / 64
+    int tap_off[9];
+    int num_m_tiles, num_n_tiles;
+    GemmEpilogue ep;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmKernelParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                          // [NSTAGE]
+    uint64_t* empty_bar = bars + Cfg::NSTAGE;           // [NSTAGE]
+    uint64_t* tmem_full = bars + 2 * Cfg::NSTAGE;       // [2]
+    uint64_t* tmem_empty = bars + 2 * Cfg::NSTAGE + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = p.taps * p.cin_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.num_n_tiles) * BM;
+                const int n0 = (tile % p.num_n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / p.cin_blocks;
+                    const int cb = kb - tap * p.cin_blocks;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(&tmap_a, &full_bar[stage], sa, cb * BK, m0 + p.tap_off[tap]);
+                    tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+                    if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem slot
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator ready
+                }
+                __syncwarp();
+                if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        const GemmEpilogue& ep = p.ep;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / p.num_n_tiles) * BM;
+            const int n0 = (tile % p.num_n_tiles) * BN;
+            const long row = (long)m0 + row_in_tile;
+            const bool in_range = row < p.M;
+            bool valid = in_range;
+            if (ep.pl_S > 0) {
+                const int r = (int)(row % ep.pl_S);
+                const int h = r / ep.pl_P, w = r - h * ep.pl_P;
+                valid = valid && (h < ep.pl_H) && (w < ep.pl_W);
+            }
+            const float* add_row = nullptr;
+            if (ep.addend != nullptr && in_range) {
+                const long ar = ep.add_period > 0 ? (row % ep.add_period) : row;
+                add_row = ep.addend + ar * ep.ld_add + n0;
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c * 32, v);
+                tmem_ld_wait();
+                if (c == BN / 32 - 1) {
+                    // all TMEM reads of this accumulator stage are done -> release it to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!in_range) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (ep.bias) x += __ldg(ep.bias + n0 + c * 32 + j);
+                    f[j] = x;
+                }
+                if (add_row) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(add_row + c * 32 + j));
+                        f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (ep.relu) f[j] = fmaxf(f[j], 0.f);
+                    if (!valid) f[j] = 0.f;
+                }
+                if (ep.out_f32) {
+                    float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + n0 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+                if (ep.out_bf16) {
+                    uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + row * ep.ld_bf16 + n0 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    if (ep.out_bf16_lo) {
+                        uint4* ol = reinterpret_cast<uint4*>(ep.out_bf16_lo + row * ep.ld_bf16 + n0 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            ol[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core check kernel (tests only): one thread per output element, fp32 accumulation.
+// ------------------------------------------------------------------------------------------
+__global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ a, long rowsA,
+                                       const __nv_bfloat16* __restrict__ w, GemmKernelParams p) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)p.M * p.N) return;
+    const long row = idx / p.N;
+    const int n = (int)(idx - row * p.N);
+    const int cin = p.cin_blocks * BK;
+    const GemmEpilogue& ep = p.ep;
+    float acc = 0.f;
+    for (int t = 0; t < p.taps; ++t) {
+        const long ar = row + p.tap_off[t];
+        if (ar < 0 || ar >= rowsA) continue;
+        const __nv_bfloat16* ap = a + ar * cin;
+        const __nv_bfloat16* wp = w + (long)n * p.taps * cin + (long)t * cin;
+        for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(ap[c]), __bfloat162float(wp[c]), acc);
+    }
+    if (ep.bias) acc += ep.bias[n];
+    if (ep.addend) {
+        const long ar = ep.add_period > 0 ? (row % ep.add_period) : row;
+        acc += ep.addend[ar * ep.ld_add + n];
+    }
+    if (ep.relu) acc = fmaxf(acc, 0.f);
+    if (ep.pl_S > 0) {
+        const int r = (int)(row % ep.pl_S);
+        const int h = r / ep.pl_P, ww = r - h * ep.pl_P;
+        if (!(h < ep.pl_H && ww < ep.pl_W)) acc = 0.f;
+    }
+    if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + n] = acc;
+    if (ep.out_bf16) {
+        ep.out_bf16[row * ep.ld_bf16 + n] = __float2bfloat16_rn(acc);
+        if (ep.out_bf16_lo)
+            ep.out_bf16_lo[row * ep.ld_bf16 + n] =
+                __float2bfloat16_rn(acc - __bfloat162float(__float2bfloat16_rn(acc)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// bf16 row-major [rows, cols] matrix, box = {64 cols, box_rows}, 128-byte swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    typedef std::tuple<const void*, uint64_t, uint64_t, uint32_t> Key;
+    static std::map<Key, CUtensorMap> cache;
+    static std::mutex mu;
+    Key key(ptr, rows, cols, box_rows);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    PFN_encodeTiled enc = get_encode_fn();
+    KOCR_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KOCR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu box_rows=%u", (int)r,
+               ptr, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return 0;
+}
+
+static long g_gemm_launches = 0;
+long gemm_tc_launch_count() { return g_gemm_launches; }
+
+static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
+    KOCR_CHECK(p.cin % BK == 0, "gemm: cin %d not a multiple of %d", p.cin, BK);
+    KOCR_CHECK(p.N % BN == 0, "gemm: N %d not a multiple of the N tile %d", p.N, BN);
+    KOCR_CHECK(p.taps == 1 || p.taps == 9, "gemm: taps must be 1 or 9");
+    KOCR_CHECK(p.M > 0, "gemm: empty M");
+    kp.M = p.M; kp.N = p.N; kp.taps = p.taps; kp.cin_blocks = p.cin / BK;
+    for (int i = 0; i < 9; ++i) kp.tap_off[i] = i < p.taps ? p.tap_off[i] : 0;
+    kp.num_m_tiles = (p.M + BM - 1) / BM;
+    kp.num_n_tiles = p.N / BN;
+    kp.ep = p.ep;
+    return 0;
+}
+
+template <int BN>
+static int launch_impl(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p, int num_sms,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    GemmKernelParams kp;
+    KOCR_TRY(fill_params(kp, p, BN));
+    CUtensorMap ta, tb;
+    KOCR_TRY(make_tmap(&ta, a, (uint64_t)rowsA, (uint64_t)p.cin, BM));
+    KOCR_TRY(make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.taps * p.cin, BN));
+    static bool attr_set = false;
+    if (!attr_set) {
+        KOCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = kp.num_m_tiles * kp.num_n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
+    KOCR_CUDA(cudaGetLastError());
+    ++g_gemm_launches;
+    return 0;
+}
+
+int launch_gemm_tc(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p, int num_sms,
+                   cudaStream_t stream) {
+    if (p.N % 256 == 0) return launch_impl<256>(a, rowsA, w, p, num_sms, stream);
+    return launch_impl<128>(a, rowsA, w, p, num_sms, stream);
+}
+
+int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p,
+                           cudaStream_t stream) {
+    GemmKernelParams kp;
+    KOCR_TRY(fill_params(kp, p, 128));
+    const long total = (long)p.M * p.N;
+    gemm_simt_check_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, rowsA, w, kp);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace kocr

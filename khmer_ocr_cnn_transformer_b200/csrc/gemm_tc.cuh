@@ -1,0 +1,49 @@
+// tcgen05 / TMEM / TMA GEMM used for every dense contraction on the path:
+//   * conv2..conv7 as implicit GEMM over the padded-linear NHWC layout (9 row-shifted taps),
+//   * patch projection, encoder/decoder projections and FFNs, BiLSTM input projection,
+//     cross-attention K/V precompute, output projection.
+// D[M,N] = sum_taps A[rows + tap_off, cin-block] * W[N, tap*cin + cin-block]^T  (+ epilogue)
+//
+// Reference ops replaced: nn.Conv2d / nn.Linear / in_proj / out_proj GEMMs dispatched to
+// cuDNN/cuBLAS by the reference (se_model.py:39-61,92-97,121-125,167-173,228-234).
+#pragma once
+#include "common.cuh"
+
+namespace kocr {
+
+struct GemmEpilogue {
+    const float* bias;        // [N] or nullptr
+    int relu;                 // apply max(x, 0)
+    // row-validity mask for padded-linear outputs: rows whose (h, w) is a pad position get 0.
+    int pl_S, pl_P, pl_H, pl_W;   // pl_S == 0 -> no mask
+    // optional fp32 addend: out += addend[(period ? row % period : row) * ld_add + n]
+    const float* addend;
+    int ld_add;
+    int add_period;
+    // outputs (either may be null)
+    __nv_bfloat16* out_bf16;
+    int ld_bf16;
+    float* out_f32;
+    int ld_f32;
+    // optional second bf16 copy holding the rounding residual (x - bf16(x)) for split-precision
+    // ("bf16x3") consumers; written at out_bf16_lo with the same leading dimension.
+    __nv_bfloat16* out_bf16_lo;
+};
+
+struct GemmProblem {
+    int M, N;                 // output rows / cols (N multiple of the N tile)
+    int taps;                 // 1 (linear) or 9 (3x3 conv)
+    int cin;                  // K per tap (multiple of 64)
+    int tap_off[9];           // row shift per tap
+    GemmEpilogue ep;
+};
+
+// Host launchers (defined in gemm_tc.cu).  a: bf16 [rowsA, cin] row-major, w: bf16 [N, taps*cin].
+int launch_gemm_tc(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w,
+                   const GemmProblem& p, int num_sms, cudaStream_t stream);
+// CUDA-core restatement of the same contract; used ONLY by tests to localise tcgen05 bugs.
+int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w,
+                           const GemmProblem& p, cudaStream_t stream);
+long gemm_tc_launch_count();
+
+}  // namespace kocr

@@ -1,0 +1,77 @@
+// Launchers of the non-GEMM kernels (CUDA-core / HBM-bound parts of the path).
+#pragma once
+#include "common.cuh"
+
+namespace kocr {
+
+static constexpr int IMG_H = 48;          // config.py:7
+static constexpr int CHUNK_W = 100;       // config.py:8
+static constexpr int CHUNK_STRIDE = 84;   // chunk_width - chunk_overlap (preprocessor.py:31)
+static constexpr int TOK_PER_CHUNK = 32;  // AdaptiveAvgPool2d((2,32)) -> 32 patches (se_model.py:61)
+static constexpr int D_MODEL = 384;
+static constexpr int N_HEAD = 8;
+static constexpr int HEAD_DIM = 48;
+static constexpr int LSTM_H = 192;
+static constexpr int VOCAB = 124;
+static constexpr int VOCAB_PAD = 128;
+static constexpr int DEC_MAX = 256;       // dec.pos_emb rows (se_model.py:171)
+
+struct LineDesc {
+    long long src_off;    // byte offset of the (h, w) grey image in the pixel buffer
+    long long mid_off;    // byte offset of the (h, new_w) horizontally-resized intermediate
+    int h, w, new_w;
+    int first_chunk, n_chunks;
+    int pad_;
+};
+
+// ---- stage 1 ---------------------------------------------------------------------------
+int launch_preprocess(const uint8_t* d_pixels, uint8_t* d_mid, const LineDesc* d_lines, const int* d_chunk_line,
+                      int* d_vtab, float* d_chunks, int n_lines, int n_chunks, int max_new_w, cudaStream_t stream);
+int preprocess_vtab_ints_per_line();
+int preprocess_kmax();
+
+// ---- stage 2 helpers -------------------------------------------------------------------
+// conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool: f32 chunks -> bf16 padded-linear (24x50, 64).
+int launch_conv1_pool(const float* d_chunks, const float* w /*[64][9]*/, const float* b /*[64]*/,
+                      __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
+// 2x2 max-pool between padded-linear layouts (C multiple of 8).
+int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
+// 1D-SE gate (optional) + (2,1) max-pool: padded-linear (H, W, C) -> padded-linear (H/2, W, C).
+struct SEWeights { const float* w0; const float* b0; const float* w2; const float* b2; int R; };
+int launch_se_pool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+                   const SEWeights* se /*null -> plain pool*/, cudaStream_t stream);
+// 1D-SE gate (optional) + AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n_chunks*32, 2*C] (k = kh*C + c).
+int launch_se_finalpool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+                        const SEWeights* se, cudaStream_t stream);
+
+// ---- stage 4/5 helpers -----------------------------------------------------------------
+// per-chunk 32-token, 8-head attention: qkv bf16 [M, 1152] -> out bf16 [M, 384].
+int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
+// LayerNorm over 384: y = LN(x)*g + b (+ pos[row_pos[row]]); writes f32 and/or bf16 (+ residual lo part).
+int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
+                     float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
+                     cudaStream_t stream);
+// f32 [rows, 384] (+ pos[row_pos[row]]) -> f32 + bf16 copies (VGG merge path without LN).
+int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
+                   __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream);
+
+// BiLSTM recurrence (input projection already in gin): persistent 2-CTA cluster kernel.
+struct LstmGroup { int line[8]; };   // lines handled together by one cluster (-1 = unused)
+int launch_bilstm(const float* gin /*[Mtok,1536]*/, const __nv_bfloat16* whh_packed, const int* line_tok_off,
+                  const int* line_T, const LstmGroup* groups, int n_groups, float* mem_f32,
+                  __nv_bfloat16* mem_bf16, __nv_bfloat16* mem_bf16_lo, cudaStream_t stream);
+size_t bilstm_whh_packed_elems();
+
+// ---- decoder step kernels ---------------------------------------------------------------
+int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, int t, const float* tok_emb, const float* pos_emb,
+                     float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines, cudaStream_t stream);
+int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache, float* vcache /*[L, DEC_MAX, 384]*/,
+                         const int* tokens, int t, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
+                         cudaStream_t stream);
+int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,
+                          const int* line_tok_off, const int* line_T, int max_T, __nv_bfloat16* out,
+                          __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
+int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,
+                      int t, int n_lines, cudaStream_t stream);
+
+}  // namespace kocr

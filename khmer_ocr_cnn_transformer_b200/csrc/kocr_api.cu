@@ -1,0 +1,707 @@
+// C-ABI of libkocr_b200.so (include/kocr.h): handle, packed-weight lookup, workspace carving and the
+// orchestration of the five stages of the recognition forward path on one CUDA stream.
+#include "../../include/kocr.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace kocr {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static int64_t g_launches = 0;     // non-GEMM kernel launches (GEMM launches are counted in gemm_tc.cu)
+
+// ---- packed weight blob ---------------------------------------------------------------
+struct BlobHeader { char magic[8]; uint32_t n_entries; uint32_t reserved; };
+struct BlobEntry { char name[48]; uint32_t dtype; uint32_t pad; uint64_t offset; uint64_t nbytes; };
+
+struct EncLayerW {
+    const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;
+    const float *in_b, *out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b;
+};
+struct DecLayerW {
+    const __nv_bfloat16 *sa_in_w, *sa_out_w, *ca_q_w, *ca_out_w, *l1_w, *l2_w;
+    const float *sa_in_b, *sa_out_b, *ca_q_b, *ca_out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+};
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace kocr
+
+using namespace kocr;
+
+struct kocr_handle {
+    int device = 0;
+    int num_sms = 148;
+    int variant = 0, emb_dim = 384, max_seq_len = 4096, dec_max_len = 256, vocab = 124;
+    int max_lines = 0, max_chunks = 0;
+    // weights
+    uint8_t* d_blob = nullptr;
+    size_t blob_bytes = 0;
+    std::map<std::string, std::pair<const void*, size_t>> w;
+    const float *conv1_w, *conv1_b;
+    const __nv_bfloat16* conv_w[8];
+    const float* conv_b[8];
+    SEWeights se[3];
+    const __nv_bfloat16* patch_w; const float *patch_b, *patch_pos;
+    EncLayerW enc[2];
+    const float* global_pos;
+    const __nv_bfloat16 *lstm_w_ih, *lstm_w_hh; const float* lstm_b;
+    const float *dec_tok_emb, *dec_pos;
+    DecLayerW dec[2];
+    const __nv_bfloat16 *dec_kv_w, *dec_out_w; const float *dec_kv_b, *dec_out_b;
+    // workspace
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    std::map<std::string, Buf> named;
+    Buf pixels_dev, mid_dev, trace;
+    uint8_t* staging_host = nullptr;   // pinned
+    uint8_t* staging_dev = nullptr;
+    size_t staging_bytes = 0;
+    cudaEvent_t staging_done = nullptr;
+    int32_t* pinned_flag = nullptr;    // pinned int for early-exit polling
+    // batch state
+    int n_lines = 0, n_chunks = 0, n_tok = 0, max_T = 0, n_groups = 0, max_new_w = 0;
+    std::vector<int> line_T, line_first_chunk, line_n_chunks;
+    int last_steps = 0;
+    // options
+    int trace_logits = 0, force_tokens = 0;
+    bool have_forced = false;
+    // device arrays inside staging_dev
+    LineDesc* d_lines = nullptr; int* d_chunk_line = nullptr; int* d_row_pos = nullptr;
+    int* d_line_tok_off = nullptr; int* d_line_T = nullptr; LstmGroup* d_groups = nullptr;
+};
+
+namespace {
+
+template <typename T> T* buf(kocr_handle* h, const char* name) { return reinterpret_cast<T*>(h->named[name].p); }
+
+int lookup(kocr_handle* h, const char* name, const void** out, size_t min_bytes) {
+    auto it = h->w.find(name);
+    KOCR_CHECK(it != h->w.end(), "weight blob lacks entry '%s'", name);
+    KOCR_CHECK(it->second.second >= min_bytes, "weight blob entry '%s' has %zu bytes, expected >= %zu", name,
+               it->second.second, min_bytes);
+    *out = it->second.first;
+    return 0;
+}
+#define W_F32(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 4))
+#define W_BF16(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 2))
+
+int resolve_weights(kocr_handle* h) {
+    const int D = D_MODEL;
+    static const int cin[8] = {0, 1, 64, 128, 256, 256, 512, 512};
+    static const int cout[8] = {0, 64, 128, 256, 256, 512, 512, 512};
+    W_F32(h->conv1_w, "conv1.w", 64 * 9);
+    W_F32(h->conv1_b, "conv1.b", 64);
+    char nm[64];
+    for (int i = 2; i <= 7; ++i) {
+        snprintf(nm, sizeof nm, "conv%d.w", i); W_BF16(h->conv_w[i], nm, (size_t)cout[i] * 9 * cin[i]);
+        snprintf(nm, sizeof nm, "conv%d.b", i); W_F32(h->conv_b[i], nm, cout[i]);
+    }
+    if (h->variant == 0) {
+        static const int sc[3] = {256, 512, 512};
+        for (int i = 0; i < 3; ++i) {
+            const int C = sc[i], R = C / 16;
+            h->se[i].R = R;
+            snprintf(nm, sizeof nm, "se%d.w0", i + 3); W_F32(h->se[i].w0, nm, R * C);
+            snprintf(nm, sizeof nm, "se%d.b0", i + 3); W_F32(h->se[i].b0, nm, R);
+            snprintf(nm, sizeof nm, "se%d.w2", i + 3); W_F32(h->se[i].w2, nm, C * R);
+            snprintf(nm, sizeof nm, "se%d.b2", i + 3); W_F32(h->se[i].b2, nm, C);
+        }
+        W_BF16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
+        W_F32(h->lstm_b, "lstm.b", 8 * LSTM_H);
+        W_BF16(h->lstm_w_hh, "lstm.w_hh", bilstm_whh_packed_elems());
+    }
+    W_BF16(h->patch_w, "patch.w", D * 1024);
+    W_F32(h->patch_b, "patch.b", D);
+    W_F32(h->patch_pos, "patch.pos", 32 * D);
+    for (int l = 0; l < 2; ++l) {
+        EncLayerW& e = h->enc[l];
+        snprintf(nm, sizeof nm, "enc%d.in_w", l); W_BF16(e.in_w, nm, 3 * D * D);
+        snprintf(nm, sizeof nm, "enc%d.in_b", l); W_F32(e.in_b, nm, 3 * D);
+        snprintf(nm, sizeof nm, "enc%d.out_w", l); W_BF16(e.out_w, nm, D * D);
+        snprintf(nm, sizeof nm, "enc%d.out_b", l); W_F32(e.out_b, nm, D);
+        snprintf(nm, sizeof nm, "enc%d.l1_w", l); W_BF16(e.l1_w, nm, 1024 * D);
+        snprintf(nm, sizeof nm, "enc%d.l1_b", l); W_F32(e.l1_b, nm, 1024);
+        snprintf(nm, sizeof nm, "enc%d.l2_w", l); W_BF16(e.l2_w, nm, D * 1024);
+        snprintf(nm, sizeof nm, "enc%d.l2_b", l); W_F32(e.l2_b, nm, D);
+        snprintf(nm, sizeof nm, "enc%d.n1_g", l); W_F32(e.n1_g, nm, D);
+        snprintf(nm, sizeof nm, "enc%d.n1_b", l); W_F32(e.n1_b, nm, D);
+        snprintf(nm, sizeof nm, "enc%d.n2_g", l); W_F32(e.n2_g, nm, D);
+        snprintf(nm, sizeof nm, "enc%d.n2_b", l); W_F32(e.n2_b, nm, D);
+    }
+    W_F32(h->global_pos, "global_pos", (size_t)h->max_seq_len * D);
+    W_F32(h->dec_tok_emb, "dec.tok_emb", (size_t)h->vocab * D);
+    W_F32(h->dec_pos, "dec.pos", (size_t)h->dec_max_len * D);
+    for (int l = 0; l < 2; ++l) {
+        DecLayerW& d = h->dec[l];
+        snprintf(nm, sizeof nm, "dec%d.sa_in_w", l); W_BF16(d.sa_in_w, nm, 3 * D * D);
+        snprintf(nm, sizeof nm, "dec%d.sa_in_b", l); W_F32(d.sa_in_b, nm, 3 * D);
+        snprintf(nm, sizeof nm, "dec%d.sa_out_w", l); W_BF16(d.sa_out_w, nm, D * D);
+        snprintf(nm, sizeof nm, "dec%d.sa_out_b", l); W_F32(d.sa_out_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.ca_q_w", l); W_BF16(d.ca_q_w, nm, D * D);
+        snprintf(nm, sizeof nm, "dec%d.ca_q_b", l); W_F32(d.ca_q_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.ca_out_w", l); W_BF16(d.ca_out_w, nm, D * D);
+        snprintf(nm, sizeof nm, "dec%d.ca_out_b", l); W_F32(d.ca_out_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.l1_w", l); W_BF16(d.l1_w, nm, 4 * D * D);
+        snprintf(nm, sizeof nm, "dec%d.l1_b", l); W_F32(d.l1_b, nm, 4 * D);
+        snprintf(nm, sizeof nm, "dec%d.l2_w", l); W_BF16(d.l2_w, nm, 4 * D * D);
+        snprintf(nm, sizeof nm, "dec%d.l2_b", l); W_F32(d.l2_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n1_g", l); W_F32(d.n1_g, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n1_b", l); W_F32(d.n1_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n2_g", l); W_F32(d.n2_g, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n2_b", l); W_F32(d.n2_b, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n3_g", l); W_F32(d.n3_g, nm, D);
+        snprintf(nm, sizeof nm, "dec%d.n3_b", l); W_F32(d.n3_b, nm, D);
+    }
+    W_BF16(h->dec_kv_w, "dec.ca_kv_w", 4 * D * D);
+    W_F32(h->dec_kv_b, "dec.ca_kv_b", 4 * D);
+    W_BF16(h->dec_out_w, "dec.out_w", VOCAB_PAD * D);
+    W_F32(h->dec_out_b, "dec.out_b", VOCAB_PAD);
+    return 0;
+}
+
+// activation geometry per stage of the backbone
+const PLGeom G1 = make_pl(24, 50), G2 = make_pl(12, 25), G3 = make_pl(6, 25), G4 = make_pl(3, 25);
+
+struct WsItem { const char* name; size_t bytes; };
+
+int carve_workspace(kocr_handle* h) {
+    const size_t NC = h->max_chunks, L = h->max_lines, M = NC * TOK_PER_CHUNK;
+    const size_t D = D_MODEL;
+    std::vector<WsItem> items = {
+        {"chunks", NC * IMG_H * CHUNK_W * 4},
+        {"pool1", NC * G1.S * 64 * 2},   {"conv2", NC * G1.S * 128 * 2}, {"pool2", NC * G2.S * 128 * 2},
+        {"conv3", NC * G2.S * 256 * 2},  {"conv4", NC * G2.S * 256 * 2}, {"pool3", NC * G3.S * 256 * 2},
+        {"conv5", NC * G3.S * 512 * 2},  {"conv6", NC * G3.S * 512 * 2}, {"pool4", NC * G4.S * 512 * 2},
+        {"conv7", NC * G4.S * 512 * 2},  {"patch_in", M * 1024 * 2},
+        {"x", M * D * 4},   {"xb", M * D * 2},  {"qkv", M * 3 * D * 2}, {"ao", M * D * 2}, {"y", M * D * 4},
+        {"hff", M * 1024 * 2},
+        {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2},
+        {"vtab", L * (size_t)preprocess_vtab_ints_per_line() * 4},
+        {"tokens", L * KOCR_TOKENS_LD * 4}, {"forced", L * KOCR_TOKENS_LD * 4}, {"lengths", L * 4},
+        {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4},
+        {"dx", L * D * 4}, {"dxb", L * D * 2}, {"dqkv", L * 3 * D * 4}, {"dao", L * D * 2}, {"dy", L * D * 4},
+        {"dq", L * D * 4}, {"dh", L * 4 * D * 2}, {"logits", L * VOCAB_PAD * 4},
+        {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
+    };
+    size_t total = 0;
+    for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
+    KOCR_CUDA(cudaMalloc(&h->ws, total));
+    KOCR_CUDA(cudaMemset(h->ws, 0, total));
+    h->ws_bytes = total;
+    size_t off = 0;
+    for (auto& it : items) {
+        Buf b; b.p = h->ws + off; b.bytes = it.bytes;
+        h->named[it.name] = b;
+        off += (it.bytes + 1023) / 1024 * 1024;
+    }
+    // staging for the small per-batch integer tables
+    h->staging_bytes = L * sizeof(LineDesc) + NC * 4 + M * 4 + L * 4 * 2 + (L / 8 + 2) * sizeof(LstmGroup) + 4096;
+    KOCR_CUDA(cudaMallocHost(&h->staging_host, h->staging_bytes));
+    KOCR_CUDA(cudaMalloc(&h->staging_dev, h->staging_bytes));
+    KOCR_CUDA(cudaMallocHost(&h->pinned_flag, 64));
+    KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming));
+    return 0;
+}
+
+int ensure(Buf& b, size_t bytes) {
+    if (b.bytes >= bytes) return 0;
+    if (b.p) KOCR_CUDA(cudaFree(b.p));
+    b.p = nullptr; b.bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    KOCR_CUDA(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return 0;
+}
+
+// ---- GEMM convenience wrappers -------------------------------------------------------------
+GemmEpilogue ep_none() {
+    GemmEpilogue e;
+    memset(&e, 0, sizeof e);
+    return e;
+}
+
+int gemm_linear(kocr_handle* h, const __nv_bfloat16* a, long rows, const __nv_bfloat16* w, int N, int K,
+                const GemmEpilogue& ep, cudaStream_t s) {
+    GemmProblem p;
+    memset(&p, 0, sizeof p);
+    p.M = (int)rows; p.N = N; p.taps = 1; p.cin = K; p.ep = ep;
+    return launch_gemm_tc(a, rows, w, p, h->num_sms, s);
+}
+
+int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, const PLGeom& g, int Cin,
+              int Cout, const __nv_bfloat16* w, const float* b, int relu, cudaStream_t s) {
+    GemmProblem p;
+    memset(&p, 0, sizeof p);
+    p.M = n_chunks * g.S; p.N = Cout; p.taps = 9; p.cin = Cin;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) p.tap_off[r * 3 + c] = (r - 1) * g.P + (c - 1);
+    p.ep = ep_none();
+    p.ep.bias = b; p.ep.relu = relu;
+    p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W;
+    p.ep.out_bf16 = out; p.ep.ld_bf16 = Cout;
+    return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, h->num_sms, s);
+}
+
+int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
+    const int NC = h->n_chunks;
+    if (NC == 0) return 0;
+    const bool se = h->variant == 0;
+    auto B = [&](const char* n) { return buf<__nv_bfloat16>(h, n); };
+    KOCR_TRY(launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s)); ++g_launches;
+    KOCR_TRY(gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
+    KOCR_TRY(launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
+    KOCR_TRY(gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
+    KOCR_TRY(gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
+    KOCR_TRY(launch_se_pool(B("conv4"), B("pool3"), NC, 12, 25, 256, se ? &h->se[0] : nullptr, s)); ++g_launches;
+    KOCR_TRY(gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
+    KOCR_TRY(gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
+    KOCR_TRY(launch_se_pool(B("conv6"), B("pool4"), NC, 6, 25, 512, se ? &h->se[1] : nullptr, s)); ++g_launches;
+    // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
+    KOCR_TRY(gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
+    KOCR_TRY(launch_se_finalpool(B("conv7"), B("patch_in"), NC, 3, 25, 512, se ? &h->se[2] : nullptr, s)); ++g_launches;
+
+    const long M = (long)NC * TOK_PER_CHUNK;
+    float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");
+    __nv_bfloat16* xb = B("xb");
+    {   // patch projection + bias + local positional encoding (se_model.py:108-115)
+        GemmEpilogue e = ep_none();
+        e.bias = h->patch_b; e.addend = h->patch_pos; e.ld_add = D_MODEL; e.add_period = TOK_PER_CHUNK;
+        e.out_f32 = x; e.ld_f32 = D_MODEL; e.out_bf16 = xb; e.ld_bf16 = D_MODEL;
+        KOCR_TRY(gemm_linear(h, B("patch_in"), M, h->patch_w, D_MODEL, 1024, e, s));
+    }
+    for (int l = 0; l < 2; ++l) {
+        const EncLayerW& w = h->enc[l];
+        GemmEpilogue e = ep_none();
+        e.bias = w.in_b; e.out_bf16 = B("qkv"); e.ld_bf16 = 3 * D_MODEL;
+        KOCR_TRY(gemm_linear(h, xb, M, w.in_w, 3 * D_MODEL, D_MODEL, e, s));
+        KOCR_TRY(launch_chunk_attention(B("qkv"), B("ao"), NC, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.out_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
+        KOCR_TRY(gemm_linear(h, B("ao"), M, w.out_w, D_MODEL, D_MODEL, e, s));
+        KOCR_TRY(launch_layernorm(y, w.n1_g, w.n1_b, nullptr, nullptr, x, xb, nullptr, (int)M, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.l1_b; e.relu = 1; e.out_bf16 = B("hff"); e.ld_bf16 = 1024;
+        KOCR_TRY(gemm_linear(h, xb, M, w.l1_w, 1024, D_MODEL, e, s));
+        e = ep_none();
+        e.bias = w.l2_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
+        KOCR_TRY(gemm_linear(h, B("hff"), M, w.l2_w, D_MODEL, 1024, e, s));
+        // last layer: fuse the merge's "+ global_pos[t]" (predictor.py:178-183) into the LayerNorm
+        const bool last = l == 1;
+        KOCR_TRY(launch_layernorm(y, w.n2_g, w.n2_b, last ? h->global_pos : nullptr, last ? h->d_row_pos : nullptr, x,
+                                  xb, nullptr, (int)M, s)); ++g_launches;
+    }
+    return 0;
+}
+
+int stage_memory(kocr_handle* h, cudaStream_t s) {
+    const long M = h->n_tok;
+    if (M == 0) return 0;
+    const __nv_bfloat16* memb = buf<__nv_bfloat16>(h, "xb");
+    if (h->variant == 0) {
+        GemmEpilogue e = ep_none();
+        e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
+        KOCR_TRY(gemm_linear(h, buf<__nv_bfloat16>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
+        KOCR_TRY(launch_bilstm(buf<float>(h, "gin"), h->lstm_w_hh, h->d_line_tok_off, h->d_line_T, h->d_groups,
+                               h->n_groups, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
+        ++g_launches;
+        memb = buf<__nv_bfloat16>(h, "memb");
+    }
+    // cross-attention K/V of both decoder layers, once per line (depends only on the memory)
+    GemmEpilogue e = ep_none();
+    e.bias = h->dec_kv_b; e.out_bf16 = buf<__nv_bfloat16>(h, "kv"); e.ld_bf16 = 4 * D_MODEL;
+    KOCR_TRY(gemm_linear(h, memb, M, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
+    return 0;
+}
+
+int decode_step(kocr_handle* h, int t, cudaStream_t s) {
+    const int L = h->n_lines;
+    const int D = D_MODEL;
+    int* tokens = buf<int>(h, "tokens");
+    float* dx = buf<float>(h, "dx"); float* dy = buf<float>(h, "dy");
+    __nv_bfloat16* dxb = buf<__nv_bfloat16>(h, "dxb");
+    __nv_bfloat16* dao = buf<__nv_bfloat16>(h, "dao");
+    KOCR_TRY(launch_dec_embed(tokens, t, h->dec_tok_emb, h->dec_pos, dx, dxb, nullptr, L, s)); ++g_launches;
+    for (int l = 0; l < 2; ++l) {
+        const DecLayerW& w = h->dec[l];
+        float* kc = buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        float* vc = buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        GemmEpilogue e = ep_none();
+        e.bias = w.sa_in_b; e.out_f32 = buf<float>(h, "dqkv"); e.ld_f32 = 3 * D;
+        KOCR_TRY(gemm_linear(h, dxb, L, w.sa_in_w, 3 * D, D, e, s));
+        KOCR_TRY(launch_dec_self_attn(buf<float>(h, "dqkv"), kc, vc, tokens, t, dao, nullptr, L, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.sa_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
+        KOCR_TRY(gemm_linear(h, dao, L, w.sa_out_w, D, D, e, s));
+        KOCR_TRY(launch_layernorm(dy, w.n1_g, w.n1_b, nullptr, nullptr, dx, dxb, nullptr, L, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.ca_q_b; e.out_f32 = buf<float>(h, "dq"); e.ld_f32 = D;
+        KOCR_TRY(gemm_linear(h, dxb, L, w.ca_q_w, D, D, e, s));
+        KOCR_TRY(launch_dec_cross_attn(buf<float>(h, "dq"), buf<__nv_bfloat16>(h, "kv"), l, h->d_line_tok_off,
+                                       h->d_line_T, h->max_T, dao, nullptr, L, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.ca_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
+        KOCR_TRY(gemm_linear(h, dao, L, w.ca_out_w, D, D, e, s));
+        KOCR_TRY(launch_layernorm(dy, w.n2_g, w.n2_b, nullptr, nullptr, dx, dxb, nullptr, L, s)); ++g_launches;
+        e = ep_none();
+        e.bias = w.l1_b; e.relu = 1; e.out_bf16 = buf<__nv_bfloat16>(h, "dh"); e.ld_bf16 = 4 * D;
+        KOCR_TRY(gemm_linear(h, dxb, L, w.l1_w, 4 * D, D, e, s));
+        e = ep_none();
+        e.bias = w.l2_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
+        KOCR_TRY(gemm_linear(h, buf<__nv_bfloat16>(h, "dh"), L, w.l2_w, D, 4 * D, e, s));
+        KOCR_TRY(launch_layernorm(dy, w.n3_g, w.n3_b, nullptr, nullptr, dx, dxb, nullptr, L, s)); ++g_launches;
+    }
+    GemmEpilogue e = ep_none();
+    e.bias = h->dec_out_b; e.out_f32 = buf<float>(h, "logits"); e.ld_f32 = VOCAB_PAD;
+    KOCR_TRY(gemm_linear(h, dxb, L, h->dec_out_w, VOCAB_PAD, D, e, s));
+    if (h->trace_logits) {
+        KOCR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
+                                    (size_t)DEC_MAX * VOCAB_PAD * 4, buf<float>(h, "logits"), VOCAB_PAD * 4,
+                                    VOCAB_PAD * 4, L, cudaMemcpyDeviceToDevice, s));
+    }
+    KOCR_TRY(launch_dec_argmax(buf<float>(h, "logits"), tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"),
+                               buf<int>(h, "n_active"), t, L, s)); ++g_launches;
+    if (h->force_tokens && h->have_forced && t + 1 < KOCR_TOKENS_LD) {
+        // teacher forcing: overwrite the freshly chosen ids of column t+1 with the caller's
+        KOCR_CUDA(cudaMemcpy2DAsync(tokens + t + 1, KOCR_TOKENS_LD * 4, buf<int>(h, "forced") + t + 1,
+                                    KOCR_TOKENS_LD * 4, 4, L, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ===========================================================================================
+// C ABI
+// ===========================================================================================
+extern "C" {
+
+int kocr_abi_version(void) { return KOCR_ABI_VERSION; }
+const char* kocr_last_error(void) { return get_error(); }
+int64_t kocr_launch_count(void) { return g_launches + gemm_tc_launch_count(); }
+
+int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_lines, int max_chunks,
+                kocr_handle** out) {
+    KOCR_CHECK(out != nullptr && weight_blob != nullptr, "kocr_create: null argument");
+    *out = nullptr;
+    KOCR_CHECK(max_lines > 0 && max_chunks > 0, "kocr_create: max_lines/max_chunks must be positive");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    KOCR_CHECK(ce == cudaSuccess && ndev > 0, "kocr_create: no CUDA device (%s); this library has no CPU path",
+               cudaGetErrorString(ce));
+    KOCR_CHECK(device >= 0 && device < ndev, "kocr_create: device %d out of range (%d devices)", device, ndev);
+    KOCR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KOCR_CUDA(cudaGetDeviceProperties(&prop, device));
+    KOCR_CHECK(prop.major == 10, "kocr_create: device is sm_%d%d; this library is built for sm_100a only", prop.major,
+               prop.minor);
+    const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(weight_blob);
+    KOCR_CHECK(blob_bytes >= sizeof(BlobHeader) && memcmp(hd->magic, "KOCRW001", 8) == 0, "kocr_create: bad blob magic");
+    const BlobEntry* ents = reinterpret_cast<const BlobEntry*>(hd + 1);
+    KOCR_CHECK(blob_bytes >= sizeof(BlobHeader) + (size_t)hd->n_entries * sizeof(BlobEntry), "kocr_create: truncated blob");
+
+    kocr_handle* h = new kocr_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_lines = max_lines;
+    h->max_chunks = max_chunks;
+    auto fail = [&](int rc) { kocr_destroy(h); return rc; };
+    if (cudaMalloc(&h->d_blob, blob_bytes) != cudaSuccess) { set_error("kocr_create: cudaMalloc(%zu) failed", blob_bytes); return fail(1); }
+    h->blob_bytes = blob_bytes;
+    if (cudaMemcpy(h->d_blob, weight_blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("kocr_create: H2D weight copy failed"); return fail(1); }
+    const int32_t* meta = nullptr;
+    for (uint32_t i = 0; i < hd->n_entries; ++i) {
+        const BlobEntry& e = ents[i];
+        if (e.offset + e.nbytes > blob_bytes) { set_error("kocr_create: entry %u out of bounds", i); return fail(2); }
+        char nm[49]; memcpy(nm, e.name, 48); nm[48] = 0;
+        h->w[nm] = std::make_pair((const void*)(h->d_blob + e.offset), (size_t)e.nbytes);
+        if (strcmp(nm, "meta") == 0) meta = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(weight_blob) + e.offset);
+    }
+    if (!meta) { set_error("kocr_create: blob lacks 'meta'"); return fail(2); }
+    h->variant = meta[0]; h->emb_dim = meta[1]; h->max_seq_len = meta[2]; h->dec_max_len = meta[3]; h->vocab = meta[4];
+    if (h->emb_dim != D_MODEL || h->dec_max_len != DEC_MAX || h->vocab != VOCAB) {
+        set_error("kocr_create: unsupported dims emb=%d dec_max=%d vocab=%d (kernels are specialised for 384/256/124)",
+                  h->emb_dim, h->dec_max_len, h->vocab);
+        return fail(2);
+    }
+    int rc = resolve_weights(h);
+    if (rc) return fail(rc);
+    rc = carve_workspace(h);
+    if (rc) return fail(rc);
+    *out = h;
+    return 0;
+}
+
+int kocr_destroy(kocr_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->d_blob) cudaFree(h->d_blob);
+    if (h->ws) cudaFree(h->ws);
+    if (h->pixels_dev.p) cudaFree(h->pixels_dev.p);
+    if (h->mid_dev.p) cudaFree(h->mid_dev.p);
+    if (h->trace.p) cudaFree(h->trace.p);
+    if (h->staging_host) cudaFreeHost(h->staging_host);
+    if (h->staging_dev) cudaFree(h->staging_dev);
+    if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
+    if (h->staging_done) cudaEventDestroy(h->staging_done);
+    delete h;
+    return 0;
+}
+
+size_t kocr_workspace_bytes(const kocr_handle* h) {
+    return h ? h->ws_bytes + h->blob_bytes + h->pixels_dev.bytes + h->mid_dev.bytes + h->trace.bytes + h->staging_bytes : 0;
+}
+
+int kocr_model_info(const kocr_handle* h, int* variant, int* emb_dim, int* max_seq_len, int* decode_max_len,
+                    int* vocab_size) {
+    KOCR_CHECK(h != nullptr, "kocr_model_info: null handle");
+    if (variant) *variant = h->variant;
+    if (emb_dim) *emb_dim = h->emb_dim;
+    if (max_seq_len) *max_seq_len = h->max_seq_len;
+    if (decode_max_len) *decode_max_len = h->dec_max_len;
+    if (vocab_size) *vocab_size = h->vocab;
+    return 0;
+}
+
+int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes, int pixels_on_device,
+                       const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n_lines,
+                       int32_t* chunk_counts_out, void* stream) {
+    KOCR_CHECK(h != nullptr, "kocr_gather_chunks: null handle");
+    KOCR_CHECK(n_lines >= 0 && n_lines <= h->max_lines, "kocr_gather_chunks: %d lines exceed capacity %d", n_lines,
+               h->max_lines);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    h->n_lines = n_lines; h->n_chunks = 0; h->n_tok = 0; h->max_T = 0; h->n_groups = 0; h->max_new_w = 0;
+    h->line_T.assign(n_lines, 0); h->line_first_chunk.assign(n_lines, 0); h->line_n_chunks.assign(n_lines, 0);
+    if (n_lines == 0) return 0;
+    KOCR_CHECK(pixels && offsets && heights && widths, "kocr_gather_chunks: null argument");
+    KOCR_CUDA(cudaEventSynchronize(h->staging_done));      // previous batch's table upload has been consumed
+
+    // carve the staging buffer
+    uint8_t* sp = h->staging_host;
+    LineDesc* lines = reinterpret_cast<LineDesc*>(sp); sp += (size_t)h->max_lines * sizeof(LineDesc);
+    int* chunk_line = reinterpret_cast<int*>(sp); sp += (size_t)h->max_chunks * 4;
+    int* row_pos = reinterpret_cast<int*>(sp); sp += (size_t)h->max_chunks * TOK_PER_CHUNK * 4;
+    int* tok_off = reinterpret_cast<int*>(sp); sp += (size_t)h->max_lines * 4;
+    int* lineT = reinterpret_cast<int*>(sp); sp += (size_t)h->max_lines * 4;
+    sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
+    LstmGroup* groups = reinterpret_cast<LstmGroup*>(sp);
+    auto dev_of = [&](void* hp) { return h->staging_dev + (reinterpret_cast<uint8_t*>(hp) - h->staging_host); };
+    h->d_lines = reinterpret_cast<LineDesc*>(dev_of(lines));
+    h->d_chunk_line = reinterpret_cast<int*>(dev_of(chunk_line));
+    h->d_row_pos = reinterpret_cast<int*>(dev_of(row_pos));
+    h->d_line_tok_off = reinterpret_cast<int*>(dev_of(tok_off));
+    h->d_line_T = reinterpret_cast<int*>(dev_of(lineT));
+    h->d_groups = reinterpret_cast<LstmGroup*>(dev_of(groups));
+
+    const int max_line_chunks = (h->max_seq_len + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
+    const int kmax = preprocess_kmax();
+    long long mid_total = 0;
+    int nc = 0;
+    for (int i = 0; i < n_lines; ++i) {
+        const int hh = heights[i], ww = widths[i];
+        KOCR_CHECK(hh > 0 && ww > 0, "kocr_gather_chunks: line %d has empty size %dx%d", i, hh, ww);
+        KOCR_CHECK(offsets[i] >= 0 && (size_t)offsets[i] + (size_t)hh * ww <= pixel_bytes,
+                   "kocr_gather_chunks: line %d exceeds the pixel buffer", i);
+        // preprocessor.py:45-47: aspect = w / h (float division); new_w = max(50, int(48 * aspect))
+        const double aspect = (double)ww / (double)hh;
+        int new_w = (int)((double)IMG_H * aspect);
+        if (new_w < CHUNK_W / 2) new_w = CHUNK_W / 2;
+        const double sh = std::max((double)ww / new_w, 1.0), sv = std::max((double)hh / IMG_H, 1.0);
+        KOCR_CHECK((int)std::ceil(sh) * 2 + 1 <= kmax && (int)std::ceil(sv) * 2 + 1 <= kmax,
+                   "kocr_gather_chunks: line %d (%dx%d) needs a down-scale beyond the supported %dx", i, hh, ww,
+                   (kmax - 1) / 2);
+        int n = (new_w + CHUNK_STRIDE - 1) / CHUNK_STRIDE;          // preprocessor.py:21-31
+        if (n > max_line_chunks) n = max_line_chunks;               // tokens beyond max_seq_len are dropped (predictor.py:181-183)
+        KOCR_CHECK(nc + n <= h->max_chunks, "kocr_gather_chunks: batch needs more than %d chunks", h->max_chunks);
+        LineDesc& L = lines[i];
+        L.src_off = offsets[i]; L.mid_off = mid_total; L.h = hh; L.w = ww; L.new_w = new_w;
+        L.first_chunk = nc; L.n_chunks = n; L.pad_ = 0;
+        mid_total += (long long)hh * new_w;
+        const int T = std::min(n * TOK_PER_CHUNK, h->max_seq_len);
+        for (int k = 0; k < n; ++k) chunk_line[nc + k] = i;
+        for (int r = 0; r < n * TOK_PER_CHUNK; ++r) row_pos[(size_t)nc * TOK_PER_CHUNK + r] = std::min(r, h->max_seq_len - 1);
+        tok_off[i] = nc * TOK_PER_CHUNK; lineT[i] = T;
+        h->line_T[i] = T; h->line_first_chunk[i] = nc; h->line_n_chunks[i] = n;
+        h->max_T = std::max(h->max_T, T);
+        h->max_new_w = std::max(h->max_new_w, new_w);
+        if (chunk_counts_out) chunk_counts_out[i] = n;
+        nc += n;
+    }
+    h->n_chunks = nc; h->n_tok = nc * TOK_PER_CHUNK;
+    // LSTM groups: lines sorted by length (descending) so that a cluster's 8 lines finish together
+    std::vector<int> order(n_lines);
+    for (int i = 0; i < n_lines; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->line_T[a] > h->line_T[b]; });
+    h->n_groups = (n_lines + 7) / 8;
+    for (int g = 0; g < h->n_groups; ++g)
+        for (int j = 0; j < 8; ++j) groups[g].line[j] = (g * 8 + j < n_lines) ? order[g * 8 + j] : -1;
+    const size_t used = reinterpret_cast<uint8_t*>(groups + h->n_groups) - h->staging_host;
+    KOCR_CHECK(used <= h->staging_bytes, "internal: staging overflow");
+    KOCR_CUDA(cudaMemcpyAsync(h->staging_dev, h->staging_host, used, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaEventRecord(h->staging_done, s));
+
+    const uint8_t* d_pix = pixels;
+    if (!pixels_on_device) {
+        KOCR_TRY(ensure(h->pixels_dev, pixel_bytes));
+        KOCR_CUDA(cudaMemcpyAsync(h->pixels_dev.p, pixels, pixel_bytes, cudaMemcpyHostToDevice, s));
+        d_pix = reinterpret_cast<const uint8_t*>(h->pixels_dev.p);
+    }
+    KOCR_TRY(ensure(h->mid_dev, (size_t)mid_total));
+    KOCR_TRY(launch_preprocess(d_pix, reinterpret_cast<uint8_t*>(h->mid_dev.p), h->d_lines, h->d_chunk_line,
+                               buf<int>(h, "vtab"), buf<float>(h, "chunks"), n_lines, nc, h->max_new_w, s));
+    g_launches += 3;
+    return 0;
+}
+
+int kocr_sevgg_encoder_forward(kocr_handle* h, void* stream) {
+    KOCR_CHECK(h != nullptr, "kocr_sevgg_encoder_forward: null handle");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    return stage_cnn_encoder(h, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kocr_merge_bilstm_forward(kocr_handle* h, void* stream) {
+    KOCR_CHECK(h != nullptr, "kocr_merge_bilstm_forward: null handle");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    return stage_memory(h, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream) {
+    KOCR_CHECK(h != nullptr, "kocr_decode_greedy: null handle");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int L = h->n_lines;
+    if (L == 0) return 0;
+    if (max_steps <= 0 || max_steps > h->dec_max_len) max_steps = h->dec_max_len;
+    int* tokens = buf<int>(h, "tokens");
+    KOCR_CUDA(cudaMemsetAsync(tokens, 0, (size_t)L * KOCR_TOKENS_LD * 4, s));
+    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "finished"), 0, (size_t)L * 4, s));
+    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "n_active"), 0, (DEC_MAX + 1) * 4, s));
+    {   // tokens[:, 0] = <sos> (2), lengths = 1
+        std::vector<int32_t> init((size_t)L, 2), ones((size_t)L, 1);
+        KOCR_CUDA(cudaMemcpy2DAsync(tokens, KOCR_TOKENS_LD * 4, init.data(), 4, 4, L, cudaMemcpyHostToDevice, s));
+        KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "lengths"), ones.data(), (size_t)L * 4, cudaMemcpyHostToDevice, s));
+        KOCR_CUDA(cudaStreamSynchronize(s));   // the two host vectors die at scope end
+    }
+    if (h->trace_logits) {
+        KOCR_TRY(ensure(h->trace, (size_t)h->max_lines * DEC_MAX * VOCAB_PAD * 4));
+        KOCR_CUDA(cudaMemsetAsync(h->trace.p, 0, (size_t)L * DEC_MAX * VOCAB_PAD * 4, s));
+    }
+    int t = 0;
+    const int check_every = 8;
+    for (; t < max_steps; ++t) {
+        KOCR_TRY(decode_step(h, t, s));
+        if (!h->force_tokens && (t + 1) % check_every == 0 && t + 1 < max_steps) {
+            KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + t, 4, cudaMemcpyDeviceToHost, s));
+            KOCR_CUDA(cudaStreamSynchronize(s));
+            if (*h->pinned_flag == 0) { ++t; break; }
+        }
+    }
+    h->last_steps = t;
+    if (tokens_out) KOCR_CUDA(cudaMemcpyAsync(tokens_out, tokens, (size_t)L * KOCR_TOKENS_LD * 4, cudaMemcpyDeviceToHost, s));
+    if (lengths_out) KOCR_CUDA(cudaMemcpyAsync(lengths_out, buf<int>(h, "lengths"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes, int pixels_on_device,
+                         const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n_lines,
+                         int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream) {
+    KOCR_TRY(kocr_gather_chunks(h, pixels, pixel_bytes, pixels_on_device, offsets, heights, widths, n_lines, nullptr,
+                                stream));
+    KOCR_TRY(kocr_sevgg_encoder_forward(h, stream));
+    KOCR_TRY(kocr_merge_bilstm_forward(h, stream));
+    return kocr_decode_greedy(h, max_steps, tokens_out, lengths_out, stream);
+}
+
+int kocr_set_option(kocr_handle* h, const char* name, int value) {
+    KOCR_CHECK(h != nullptr && name != nullptr, "kocr_set_option: null argument");
+    if (strcmp(name, "trace_logits") == 0) { h->trace_logits = value; return 0; }
+    if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
+    KOCR_CHECK(false, "kocr_set_option: unknown option '%s'", name);
+    return 0;
+}
+
+int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens, int n_lines) {
+    KOCR_CHECK(h != nullptr && tokens != nullptr, "kocr_set_forced_tokens: null argument");
+    KOCR_CHECK(n_lines > 0 && n_lines <= h->max_lines, "kocr_set_forced_tokens: bad n_lines %d", n_lines);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    KOCR_CUDA(cudaMemcpy(buf<int>(h, "forced"), tokens, (size_t)n_lines * KOCR_TOKENS_LD * 4, cudaMemcpyHostToDevice));
+    h->have_forced = true;
+    return 0;
+}
+
+int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out) {
+    KOCR_CHECK(h != nullptr && name != nullptr, "kocr_debug_read: null argument");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    const size_t NC = h->n_chunks, M = h->n_tok;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    std::string n(name);
+    auto plb = [&](const char* b, const PLGeom& g, int C) { src = h->named[b].p; bytes = NC * g.S * C * 2; };
+    if (n == "chunks") { src = h->named["chunks"].p; bytes = NC * IMG_H * CHUNK_W * 4; }
+    else if (n == "pool1") plb("pool1", G1, 64);
+    else if (n == "conv2") plb("conv2", G1, 128);
+    else if (n == "pool2") plb("pool2", G2, 128);
+    else if (n == "conv3") plb("conv3", G2, 256);
+    else if (n == "conv4") plb("conv4", G2, 256);
+    else if (n == "pool3") plb("pool3", G3, 256);
+    else if (n == "conv5") plb("conv5", G3, 512);
+    else if (n == "conv6") plb("conv6", G3, 512);
+    else if (n == "pool4") plb("pool4", G4, 512);
+    else if (n == "conv7") plb("conv7", G4, 512);
+    else if (n == "patch_in") { src = h->named["patch_in"].p; bytes = M * 1024 * 2; }
+    else if (n == "enc") { src = h->named["x"].p; bytes = M * D_MODEL * 4; }
+    else if (n == "memory") { src = h->named[h->variant == 0 ? "mem" : "x"].p; bytes = M * D_MODEL * 4; }
+    else if (n == "logits_trace") { src = h->trace.p; bytes = (size_t)h->n_lines * DEC_MAX * VOCAB_PAD * 4; }
+    else if (n == "last_steps") { if (bytes_out) *bytes_out = (size_t)h->last_steps; return 0; }
+    KOCR_CHECK(src != nullptr, "kocr_debug_read: unknown or empty buffer '%s'", name);
+    if (bytes_out) *bytes_out = bytes;
+    if (dst == nullptr) return 0;
+    KOCR_CHECK(dst_bytes >= bytes, "kocr_debug_read: '%s' needs %zu bytes, got %zu", name, bytes, dst_bytes);
+    KOCR_CUDA(cudaDeviceSynchronize());
+    KOCR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int kocr_test_gemm(int impl, const void* a_bf16, int64_t rows_a, const void* w_bf16, int m, int n, int taps, int cin,
+                   const int32_t* tap_off, const float* bias, int relu, int pl_h, int pl_w, float* out_f32,
+                   void* out_bf16, void* stream) {
+    GemmProblem p;
+    memset(&p, 0, sizeof p);
+    p.M = m; p.N = n; p.taps = taps; p.cin = cin;
+    for (int i = 0; i < taps && i < 9; ++i) p.tap_off[i] = tap_off ? tap_off[i] : 0;
+    p.ep.bias = bias; p.ep.relu = relu;
+    if (pl_h > 0) { const PLGeom g = make_pl(pl_h, pl_w); p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W; }
+    p.ep.out_f32 = out_f32; p.ep.ld_f32 = n;
+    p.ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ep.ld_bf16 = n;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (impl == 1)
+        return launch_gemm_simt_check(reinterpret_cast<const __nv_bfloat16*>(a_bf16), rows_a,
+                                      reinterpret_cast<const __nv_bfloat16*>(w_bf16), p, s);
+    int dev = 0, sms = 148;
+    KOCR_CUDA(cudaGetDevice(&dev));
+    KOCR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(a_bf16), rows_a,
+                          reinterpret_cast<const __nv_bfloat16*>(w_bf16), p, sms, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// Sequence-side CUDA-core kernels: per-chunk attention, LayerNorm, BiLSTM recurrence, and the
+// KV-cached greedy decoder step kernels.  All softmax / LayerNorm / LSTM state math is fp32.
+//
+// Reference ops replaced:
+//   nn.TransformerEncoderLayer self-attention over 32 tokens            se_model.py:119-126
+//   nn.LayerNorm(384, eps 1e-5)                                          (inside enc / dec layers)
+//   nn.LSTM(384 -> 192, bidirectional) recurrence                        se_model.py:228-234
+//   TransformerDecoderWrapper + OCRPredictor._greedy_decode              se_model.py:182-208, predictor.py:85-99
+#include "kernels.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace kocr {
+
+// ------------------------------------------------------------------------------------------
+// Per-chunk attention: one CTA per chunk, warp = head, lane = query token.
+// K/V of the head live in shared memory (fp32), scores/softmax in registers.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                              __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float s_kv[];                 // [8 warps][2][32][48]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sk = s_kv + warp * (2 * 32 * HEAD_DIM);
+    float* sv = sk + 32 * HEAD_DIM;
+    const long row = (long)blockIdx.x * TOK_PER_CHUNK + lane;
+    const __nv_bfloat16* base = qkv + row * (3 * D_MODEL) + warp * HEAD_DIM;
+    float q[HEAD_DIM];
+    const float scale = rsqrtf((float)HEAD_DIM);
+#pragma unroll
+    for (int i = 0; i < HEAD_DIM / 8; ++i) {
+        const uint4 a = reinterpret_cast<const uint4*>(base)[i];
+        const uint4 b = reinterpret_cast<const uint4*>(base + D_MODEL)[i];
+        const uint4 c = reinterpret_cast<const uint4*>(base + 2 * D_MODEL)[i];
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q[i * 8 + 2 * j] = bf16_lo(av[j]) * scale;
+            q[i * 8 + 2 * j + 1] = bf16_hi(av[j]) * scale;
+            sk[lane * HEAD_DIM + i * 8 + 2 * j] = bf16_lo(bv[j]);
+            sk[lane * HEAD_DIM + i * 8 + 2 * j + 1] = bf16_hi(bv[j]);
+            sv[lane * HEAD_DIM + i * 8 + 2 * j] = bf16_lo(cv[j]);
+            sv[lane * HEAD_DIM + i * 8 + 2 * j + 1] = bf16_hi(cv[j]);
+        }
+    }
+    __syncwarp();
+    float s[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < HEAD_DIM; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(sk + j * HEAD_DIM + d);
+            acc = fmaf(q[d], k4.x, acc); acc = fmaf(q[d + 1], k4.y, acc);
+            acc = fmaf(q[d + 2], k4.z, acc); acc = fmaf(q[d + 3], k4.w, acc);
+        }
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.f / sum;
+    float o[HEAD_DIM];
+#pragma unroll
+    for (int d = 0; d < HEAD_DIM; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float pj = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < HEAD_DIM; d += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(sv + j * HEAD_DIM + d);
+            o[d] = fmaf(pj, v4.x, o[d]); o[d + 1] = fmaf(pj, v4.y, o[d + 1]);
+            o[d + 2] = fmaf(pj, v4.z, o[d + 2]); o[d + 3] = fmaf(pj, v4.w, o[d + 3]);
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + row * D_MODEL + warp * HEAD_DIM);
+#pragma unroll
+    for (int i = 0; i < HEAD_DIM / 8; ++i)
+        dst[i] = make_uint4(pack_bf16(o[i * 8], o[i * 8 + 1]), pack_bf16(o[i * 8 + 2], o[i * 8 + 3]),
+                            pack_bf16(o[i * 8 + 4], o[i * 8 + 5]), pack_bf16(o[i * 8 + 6], o[i * 8 + 7]));
+}
+
+int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    const size_t smem = 8 * 2 * 32 * HEAD_DIM * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        KOCR_CUDA(cudaFuncSetAttribute(chunk_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    chunk_attention_kernel<<<n_chunks, 256, smem, stream>>>(qkv, out);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm / positional add over rows of 384.  Warp per row, 12 elements per lane.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_row_outputs(const float (&y)[12], long row, int lane, float* out_f32,
+                                                  __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int col = j * 128 + lane * 4;
+        if (out_f32)
+            *reinterpret_cast<float4*>(out_f32 + row * D_MODEL + col) =
+                make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        if (out_bf16) {
+            const uint32_t p0 = pack_bf16(y[4 * j], y[4 * j + 1]), p1 = pack_bf16(y[4 * j + 2], y[4 * j + 3]);
+            *reinterpret_cast<uint2*>(out_bf16 + row * D_MODEL + col) = make_uint2(p0, p1);
+            if (out_lo) {
+                const uint32_t l0 = pack_bf16(y[4 * j] - bf16_lo(p0), y[4 * j + 1] - bf16_hi(p0));
+                const uint32_t l1 = pack_bf16(y[4 * j + 2] - bf16_lo(p1), y[4 * j + 3] - bf16_hi(p1));
+                *reinterpret_cast<uint2*>(out_lo + row * D_MODEL + col) = make_uint2(l0, l1);
+            }
+        }
+    }
+}
+
+template <bool DO_LN>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ b, const float* __restrict__ pos,
+                                                        const int* __restrict__ row_pos, float* out_f32,
+                                                        __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo, int rows) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[12];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(x + row * D_MODEL + j * 128 + lane * 4);
+        v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+    }
+    if (DO_LN) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) s += v[j];
+        const float mean = warp_sum(s) * (1.f / D_MODEL);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / D_MODEL) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 gg = *reinterpret_cast<const float4*>(g + j * 128 + lane * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(b + j * 128 + lane * 4);
+            v[4 * j] = (v[4 * j] - mean) * rstd * gg.x + bb.x;
+            v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * gg.y + bb.y;
+            v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * gg.z + bb.z;
+            v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * gg.w + bb.w;
+        }
+    }
+    if (pos) {
+        const long pr = row_pos[row];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 pp = *reinterpret_cast<const float4*>(pos + pr * D_MODEL + j * 128 + lane * 4);
+            v[4 * j] += pp.x; v[4 * j + 1] += pp.y; v[4 * j + 2] += pp.z; v[4 * j + 3] += pp.w;
+        }
+    }
+    store_row_outputs(v, row, lane, out_f32, out_bf16, out_lo);
+}
+
+int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
+                     float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
+                     cudaStream_t stream) {
+    if (rows == 0) return 0;
+    layernorm_kernel<true><<<(rows + 7) / 8, 256, 0, stream>>>(x, g, b, pos, row_pos, out_f32, out_bf16, out_bf16_lo, rows);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
+                   __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    layernorm_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(x, nullptr, nullptr, pos, row_pos, out_f32, out_bf16,
+                                                                out_bf16_lo, rows);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// BiLSTM recurrence.  Cluster of 2 CTAs per (group of <= 8 lines, direction); CTA `rank` owns hidden
+// units [rank*96, rank*96+96) i.e. 384 gate rows (i,f,g,o x 96), whose recurrent weights stay in
+// shared memory (bf16x2, k-pair major) for all timesteps.  Each step: gates = gin + W_hh h (fp32
+// FMA), cell update, and the new half of h is written to both CTAs' shared memory (DSMEM) followed
+// by one cluster barrier.
+// whh_packed layout (built on the host): [dir][rank][kp = 0..95][row = 0..383] u32 = bf16x2
+// {W[grow][2kp], W[grow][2kp+1]}, grow = gate*192 + rank*96 + jj for row = gate*96 + jj.
+// ------------------------------------------------------------------------------------------
+static constexpr int LSTM_ROWS = 384;      // gate rows per CTA
+static constexpr int LSTM_KP = LSTM_H / 2; // 96 k-pairs
+static constexpr int LSTM_LPG = 8;         // lines per group
+
+size_t bilstm_whh_packed_elems() { return (size_t)2 * 2 * LSTM_KP * LSTM_ROWS * 2; }   // bf16 elements
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_ROWS, 1)
+bilstm_kernel(const float* __restrict__ gin, const uint32_t* __restrict__ whh, const int* __restrict__ line_tok_off,
+              const int* __restrict__ line_T, const LstmGroup* __restrict__ groups, float* __restrict__ mem_f32,
+              __nv_bfloat16* __restrict__ mem_bf16, __nv_bfloat16* __restrict__ mem_lo) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_raw);                                 // [96][384]
+    float* s_h = reinterpret_cast<float*>(s_raw + LSTM_KP * LSTM_ROWS * 4);              // [2][8][192]
+    float* s_g = s_h + 2 * LSTM_LPG * LSTM_H;                                            // [8][384]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int dir = blockIdx.y & 1;
+    const LstmGroup grp = groups[blockIdx.y >> 1];
+    const int tid = threadIdx.x;
+
+    int tok_off[LSTM_LPG], T[LSTM_LPG];
+    int maxT = 0;
+#pragma unroll
+    for (int l = 0; l < LSTM_LPG; ++l) {
+        const int li = grp.line[l];
+        tok_off[l] = li >= 0 ? line_tok_off[li] : 0;
+        T[l] = li >= 0 ? line_T[li] : 0;
+        maxT = max(maxT, T[l]);
+    }
+    {   // load this CTA's weight slice
+        const uint4* src = reinterpret_cast<const uint4*>(whh + ((size_t)dir * 2 + rank) * LSTM_KP * LSTM_ROWS);
+        uint4* dst = reinterpret_cast<uint4*>(s_w);
+        for (int i = tid; i < LSTM_KP * LSTM_ROWS / 4; i += blockDim.x) dst[i] = src[i];
+        for (int i = tid; i < 2 * LSTM_LPG * LSTM_H; i += blockDim.x) s_h[i] = 0.f;
+    }
+    float* peer_h = cluster.map_shared_rank(s_h, rank ^ 1);
+    cluster.sync();
+
+    const int gate = tid / 96, jj = tid - gate * 96;
+    const int grow = dir * 768 + gate * LSTM_H + rank * 96 + jj;      // column of gin for this thread's row
+    float c_state[2] = {0.f, 0.f};
+    int cur = 0;
+    for (int s = 0; s < maxT; ++s) {
+        // ---- phase A: gate pre-activations for this CTA's 384 rows x 8 lines
+        float gv[LSTM_LPG];
+#pragma unroll
+        for (int l = 0; l < LSTM_LPG; ++l) {
+            gv[l] = 0.f;
+            if (s < T[l]) {
+                const int pos = dir == 0 ? s : T[l] - 1 - s;
+                gv[l] = __ldg(gin + (long)(tok_off[l] + pos) * (8 * LSTM_H) + grow);
+            }
+        }
+        float acc[LSTM_LPG];
+#pragma unroll
+        for (int l = 0; l < LSTM_LPG; ++l) acc[l] = 0.f;
+        const float* hc = s_h + cur * LSTM_LPG * LSTM_H;
+#pragma unroll 4
+        for (int kp = 0; kp < LSTM_KP; kp += 2) {
+            const uint32_t w01 = s_w[kp * LSTM_ROWS + tid];
+            const uint32_t w23 = s_w[(kp + 1) * LSTM_ROWS + tid];
+            const float w0 = bf16_lo(w01), w1 = bf16_hi(w01), w2 = bf16_lo(w23), w3 = bf16_hi(w23);
+#pragma unroll
+            for (int l = 0; l < LSTM_LPG; ++l) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hc + l * LSTM_H + 2 * kp);
+                acc[l] = fmaf(w0, h4.x, acc[l]); acc[l] = fmaf(w1, h4.y, acc[l]);
+                acc[l] = fmaf(w2, h4.z, acc[l]); acc[l] = fmaf(w3, h4.w, acc[l]);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < LSTM_LPG; ++l) s_g[l * LSTM_ROWS + tid] = acc[l] + gv[l];
+        __syncthreads();
+        // ---- phase B: cell update for (line, hidden unit) items; 768 items over 384 threads
+        float* hn = s_h + (cur ^ 1) * LSTM_LPG * LSTM_H;
+        float* hn_peer = peer_h + (cur ^ 1) * LSTM_LPG * LSTM_H;
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int item = tid + rep * LSTM_ROWS;
+            const int l = item / 96, j = item - l * 96;
+            if (s < T[l]) {
+                const float* gp = s_g + l * LSTM_ROWS + j;
+                const float ig = sigmoid_acc(gp[0]), fg = sigmoid_acc(gp[96]);
+                const float gg = tanhf(gp[192]), og = sigmoid_acc(gp[288]);
+                const float c = fg * c_state[rep] + ig * gg;
+                c_state[rep] = c;
+                const float h = og * tanhf(c);
+                const int hidx = l * LSTM_H + rank * 96 + j;
+                hn[hidx] = h;
+                hn_peer[hidx] = h;
+                const int pos = dir == 0 ? s : T[l] - 1 - s;
+                const long o = (long)(tok_off[l] + pos) * D_MODEL + dir * LSTM_H + rank * 96 + j;
+                mem_f32[o] = h;
+                if (mem_bf16) {
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+                    mem_bf16[o] = hb;
+                    if (mem_lo) mem_lo[o] = __float2bfloat16_rn(h - __bfloat162float(hb));
+                }
+            }
+        }
+        cluster.sync();
+        cur ^= 1;
+    }
+}
+
+int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* line_tok_off, const int* line_T,
+                  const LstmGroup* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
+                  __nv_bfloat16* mem_bf16_lo, cudaStream_t stream) {
+    if (n_groups == 0) return 0;
+    const size_t smem = (size_t)LSTM_KP * LSTM_ROWS * 4 + 2 * LSTM_LPG * LSTM_H * 4 + LSTM_LPG * LSTM_ROWS * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KOCR_CUDA(cudaFuncSetAttribute(bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    bilstm_kernel<<<dim3(2, n_groups * 2), LSTM_ROWS, smem, stream>>>(
+        gin, reinterpret_cast<const uint32_t*>(whh_packed), line_tok_off, line_T, groups, mem_f32, mem_bf16,
+        mem_bf16_lo);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoder step kernels (one launch each per generated position t, batched over lines).
+// tokens: int32 [n_lines, DEC_MAX + 1]; tokens[l][0] = <sos>.
+// ------------------------------------------------------------------------------------------
+static constexpr int TOK_LD = DEC_MAX + 1;
+
+__global__ void dec_embed_kernel(const int* __restrict__ tokens, int t, const float* __restrict__ tok_emb,
+                                 const float* __restrict__ pos_emb, float* __restrict__ x,
+                                 __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xb_lo, int n_lines) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // n_lines * 96 float4
+    if (idx >= n_lines * (D_MODEL / 4)) return;
+    const int l = idx / (D_MODEL / 4), c4 = idx - l * (D_MODEL / 4);
+    const int tok = tokens[l * TOK_LD + t];
+    const float4 e = reinterpret_cast<const float4*>(tok_emb + (long)tok * D_MODEL)[c4];
+    const float4 p = reinterpret_cast<const float4*>(pos_emb + (long)t * D_MODEL)[c4];
+    const float4 v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+    reinterpret_cast<float4*>(x)[idx] = v;
+    const uint32_t p0 = pack_bf16(v.x, v.y), p1 = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(xb)[idx] = make_uint2(p0, p1);
+    if (xb_lo)
+        reinterpret_cast<uint2*>(xb_lo)[idx] = make_uint2(pack_bf16(v.x - bf16_lo(p0), v.y - bf16_hi(p0)),
+                                                          pack_bf16(v.z - bf16_lo(p1), v.w - bf16_hi(p1)));
+}
+
+int launch_dec_embed(const int* tokens, int t, const float* tok_emb, const float* pos_emb, float* x,
+                     __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines, cudaStream_t stream) {
+    const int total = n_lines * (D_MODEL / 4);
+    dec_embed_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tokens, t, tok_emb, pos_emb, x, xb, xb_lo, n_lines);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__device__ __forceinline__ void store_attn_out(float o, long idx, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(o);
+    out[idx] = hb;
+    if (out_lo) out_lo[idx] = __float2bfloat16_rn(o - __bfloat162float(hb));
+}
+
+// Causal self-attention for the newest position t against the cache (keys 0..t); keys whose token is
+// <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.
+__global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
+                                                            float* __restrict__ vcache, const int* __restrict__ tokens,
+                                                            int t, __nv_bfloat16* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ out_lo) {
+    __shared__ float s_q[D_MODEL];
+    __shared__ float s_p[N_HEAD][DEC_MAX];
+    const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* row = qkv + (long)l * 3 * D_MODEL;
+    float* kc = kcache + (long)l * DEC_MAX * D_MODEL;
+    float* vc = vcache + (long)l * DEC_MAX * D_MODEL;
+    for (int i = tid; i < D_MODEL; i += blockDim.x) {
+        s_q[i] = row[i] * rsqrtf((float)HEAD_DIM);
+        kc[(long)t * D_MODEL + i] = row[D_MODEL + i];
+        vc[(long)t * D_MODEL + i] = row[2 * D_MODEL + i];
+    }
+    __syncthreads();
+    const int nk = t + 1;
+    const float* qh = s_q + warp * HEAD_DIM;
+    float mx = -INFINITY;
+    for (int j = lane; j < nk; j += 32) {
+        float acc = -INFINITY;
+        if (tokens[l * TOK_LD + j] != 0) {
+            const float4* kp = reinterpret_cast<const float4*>(kc + (long)j * D_MODEL + warp * HEAD_DIM);
+            acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < HEAD_DIM / 4; ++d) {
+                const float4 k4 = kp[d];
+                acc = fmaf(qh[4 * d], k4.x, acc); acc = fmaf(qh[4 * d + 1], k4.y, acc);
+                acc = fmaf(qh[4 * d + 2], k4.z, acc); acc = fmaf(qh[4 * d + 3], k4.w, acc);
+            }
+        }
+        s_p[warp][j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+        const float e = __expf(s_p[warp][j] - mx);
+        s_p[warp][j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int d = lane; d < HEAD_DIM; d += 32) {
+        float o = 0.f;
+        for (int j = 0; j < nk; ++j) o = fmaf(s_p[warp][j], vc[(long)j * D_MODEL + warp * HEAD_DIM + d], o);
+        store_attn_out(o * inv, (long)l * D_MODEL + warp * HEAD_DIM + d, out, out_lo);
+    }
+}
+
+int launch_dec_self_attn(const float* qkv, float* kcache, float* vcache, const int* tokens, int t,
+                         __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream) {
+    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, t, out, out_lo);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Cross-attention of one query per line over the line's T memory tokens (K/V precomputed once per line,
+// bf16 [Mtok, 1536]: layer*768 + {0: K, 384: V}).  CTA per line, warp per head.
+__global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q,
+                                                             const __nv_bfloat16* __restrict__ kv, int layer,
+                                                             const int* __restrict__ line_tok_off,
+                                                             const int* __restrict__ line_T, int max_T,
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             __nv_bfloat16* __restrict__ out_lo) {
+    extern __shared__ float s_dyn[];               // [8][max_T] scores, then [384] q
+    const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* s_p = s_dyn + (long)warp * max_T;
+    float* s_q = s_dyn + (long)N_HEAD * max_T;
+    const int T = line_T[l];
+    const __nv_bfloat16* kbase = kv + (long)line_tok_off[l] * (4 * D_MODEL) + layer * 2 * D_MODEL + warp * HEAD_DIM;
+    const __nv_bfloat16* vbase = kbase + D_MODEL;
+    for (int i = tid; i < D_MODEL; i += blockDim.x) s_q[i] = q[(long)l * D_MODEL + i] * rsqrtf((float)HEAD_DIM);
+    __syncthreads();
+    const float* qh = s_q + warp * HEAD_DIM;
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long)j * (4 * D_MODEL));
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_DIM / 8; ++i) {
+            const uint4 k8 = __ldg(kp + i);
+            acc = fmaf(qh[8 * i], bf16_lo(k8.x), acc); acc = fmaf(qh[8 * i + 1], bf16_hi(k8.x), acc);
+            acc = fmaf(qh[8 * i + 2], bf16_lo(k8.y), acc); acc = fmaf(qh[8 * i + 3], bf16_hi(k8.y), acc);
+            acc = fmaf(qh[8 * i + 4], bf16_lo(k8.z), acc); acc = fmaf(qh[8 * i + 5], bf16_hi(k8.z), acc);
+            acc = fmaf(qh[8 * i + 6], bf16_lo(k8.w), acc); acc = fmaf(qh[8 * i + 7], bf16_hi(k8.w), acc);
+        }
+        s_p[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+        const float e = __expf(s_p[j] - mx);
+        s_p[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    // P.V: lanes 0..23 own one bf16 pair of the 48 head dims each; 4 independent partial sums for ILP
+    if (lane < HEAD_DIM / 2) {
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(vbase) + lane;
+        int j = 0;
+        for (; j + 1 < T; j += 2) {
+            const uint32_t a = __ldg(vp + (long)j * (2 * D_MODEL));
+            const uint32_t b = __ldg(vp + (long)(j + 1) * (2 * D_MODEL));
+            o0 = fmaf(s_p[j], bf16_lo(a), o0); o1 = fmaf(s_p[j], bf16_hi(a), o1);
+            o2 = fmaf(s_p[j + 1], bf16_lo(b), o2); o3 = fmaf(s_p[j + 1], bf16_hi(b), o3);
+        }
+        if (j < T) {
+            const uint32_t a = __ldg(vp + (long)j * (2 * D_MODEL));
+            o0 = fmaf(s_p[j], bf16_lo(a), o0); o1 = fmaf(s_p[j], bf16_hi(a), o1);
+        }
+        const long oi = (long)l * D_MODEL + warp * HEAD_DIM + 2 * lane;
+        store_attn_out((o0 + o2) * inv, oi, out, out_lo);
+        store_attn_out((o1 + o3) * inv, oi + 1, out, out_lo);
+    }
+}
+
+int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
+                          const int* line_T, int max_T, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
+                          cudaStream_t stream) {
+    const size_t smem = ((size_t)N_HEAD * max_T + D_MODEL) * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
+        KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, out, out_lo);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// argmax over the 124 real logits (ties -> lowest index, torch.argmax), greedy bookkeeping
+// (predictor.py:90-97): stop BEFORE appending <eos>.
+__global__ void dec_argmax_kernel(const float* __restrict__ logits, int* __restrict__ tokens,
+                                  int* __restrict__ lengths, int* __restrict__ finished, int* __restrict__ n_active,
+                                  int t, int n_lines) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    if (finished[l]) return;
+    const float* lg = logits + (long)l * VOCAB_PAD;
+    float best = lg[0];
+    int bi = 0;
+    for (int i = 1; i < VOCAB; ++i) {
+        const float v = lg[i];
+        if (v > best) { best = v; bi = i; }
+    }
+    if (bi == 3) {                       // <eos>
+        finished[l] = 1;
+    } else {
+        tokens[l * TOK_LD + t + 1] = bi;
+        lengths[l] = t + 2;
+        if (t + 1 >= DEC_MAX) finished[l] = 1; else atomicAdd(n_active + t, 1);
+    }
+}
+
+int launch_dec_argmax(const float* logits, int* tokens, int* lengths, int* finished, int* n_active, int t,
+                      int n_lines, cudaStream_t stream) {
+    dec_argmax_kernel<<<(n_lines + 127) / 128, 128, 0, stream>>>(logits, tokens, lengths, finished, n_active, t, n_lines);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace kocr

@@ -1,0 +1,72 @@
+"""OCRPredictor - inference driver with the reference's constructor and predict / predict_batch
+signatures (reference: netra_ocr/recognition/predictor.py:12-199), running on libkocr_b200.so.
+
+Differences that do not change results: chunks of many lines are batched on the GPU regardless of
+`batch_size` (lines are independent, predictor.py:150-193), BiLSTM/decoding are batched across lines
+with a KV cache instead of one line and one full-prefix pass per token.  There is no CPU path."""
+import logging
+from pathlib import Path
+
+import numpy as np
+
+from .config import OCRConfig
+from .tokenizer import Tokenizer
+from .preprocessor import ImagePreprocessor
+from ..checkpoint import load_checkpoint, detect_variant
+from ..weights import pack_blob
+from .._native import Recognizer, LineBatch
+
+logger = logging.getLogger(__name__)
+
+
+class OCRPredictor:
+    def __init__(self, model_path, tokenizer: Tokenizer, config: OCRConfig, model_class,
+                 max_lines: int = 256, max_chunks: int = 4096):
+        self.cfg = config
+        self.tokenizer = tokenizer
+        import torch
+        self.device = torch.device(self.cfg.device)
+        if self.device.type != "cuda":
+            raise RuntimeError("khmer_ocr_cnn_transformer_b200 has no CPU path: OCRConfig.device must be 'cuda'")
+        logger.info(f"Init Model: dim={self.cfg.emb_dim}, max_seq={self.cfg.max_seq_len}")
+        self.model_spec = model_class(vocab_size=len(tokenizer), pad_idx=tokenizer.pad_idx,
+                                      emb_dim=self.cfg.emb_dim, max_global_len=self.cfg.max_seq_len)
+        self._max_lines, self._max_chunks = max_lines, max_chunks
+        self._load_weights(model_path)
+        self.preprocessor = ImagePreprocessor(config, self.model)
+
+    def _load_weights(self, path):
+        sd = load_checkpoint(Path(path))
+        variant = detect_variant(sd)
+        want = getattr(self.model_spec, "variant", variant)
+        if variant != want:
+            logger.warning(f"checkpoint looks like '{variant}' but model_class is '{want}'; using the checkpoint")
+        index = self.device.index if self.device.index is not None else 0
+        self.model = Recognizer(pack_blob(sd), device=index, max_lines=self._max_lines, max_chunks=self._max_chunks)
+
+    # ------------------------------------------------------------------------------------
+    def _decode_ids(self, tokens, lengths):
+        return [self.tokenizer.decode([int(t) for t in tokens[i, :lengths[i]]]) for i in range(tokens.shape[0])]
+
+    def _recognize_gray(self, grays):
+        """Greedy recognition of grey uint8 lines, batched to the handle's capacity."""
+        results = [None] * len(grays)
+        from ..scheduling import plan_batches
+        for idxs in plan_batches([g.shape for g in grays], self._max_lines, self._max_chunks, self.cfg.max_seq_len):
+            batch = LineBatch([grays[i] for i in idxs])
+            tokens, lengths = self.model.recognize_lines(batch, max_steps=self.cfg.decode_max_len)
+            for i, text in zip(idxs, self._decode_ids(tokens, lengths)):
+                results[i] = text
+        return results
+
+    def predict(self, image_input, beam_width: int = 3) -> str:
+        if beam_width > 1:
+            logger.warning("beam search is not implemented on the CUDA path yet; decoding greedily")
+        return self._recognize_gray([ImagePreprocessor.to_gray(image_input)])[0]
+
+    def predict_batch(self, image_list: list, beam_width: int = 1, batch_size: int = 8) -> list:
+        if not image_list:
+            return []
+        if beam_width > 1:
+            logger.warning("beam search is not implemented on the CUDA path yet; decoding greedily")
+        return self._recognize_gray([ImagePreprocessor.to_gray(im) for im in image_list])

@@ -1,0 +1,164 @@
+"""Pack a reference state_dict into the weight blob `kocr_create` consumes (host logic, numpy only).
+
+What the packing does:
+  * eval-mode BatchNorm folded into the preceding conv:  w' = w * g/sqrt(var+eps),
+    b' = (b - mean) * g/sqrt(var+eps) + beta            (se_model.py:39-58, BatchNorm2d eps 1e-5)
+  * conv weights (Cout, Cin, 3, 3) -> K-major bf16 [Cout][tap = r*3+s][Cin] for the implicit GEMM
+  * patch projection Conv2d(512->D, (2,1)) -> bf16 [D][kh*512 + c]           (se_model.py:92-97)
+  * nn.Linear / in_proj weights are already [N][K] K-major: bf16 cast only
+  * LSTM: W_ih of both directions stacked [1536][384]; b = b_ih + b_hh; W_hh re-laid out for the
+    2-CTA persistent kernel as bf16x2 [dir][rank][k-pair][row]               (se_model.py:228-234)
+  * decoder cross-attention K/V projections of both layers stacked [1536][384]
+  * out_proj padded from 124 to 128 rows (pad logits are never read by the argmax)
+bf16 conversion is round-to-nearest-even, identical to __float2bfloat16_rn.
+"""
+from __future__ import annotations
+
+import struct
+import numpy as np
+
+from .checkpoint import detect_variant, validate_state_dict
+
+BN_EPS = 1e-5
+MAGIC = b"KOCRW001"
+DT_F32, DT_BF16, DT_I32 = 0, 1, 2
+LSTM_H = 192
+
+
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> bf16, returned as uint16 bit patterns."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    rounding = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    out = ((u + rounding) >> 16).astype(np.uint16)
+    nan = np.isnan(x)
+    if nan.any():
+        out[nan] = 0x7FC0
+    return out
+
+
+def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def fold_bn(w, b, gamma, beta, mean, var):
+    s = (gamma / np.sqrt(var.astype(np.float32) + np.float32(BN_EPS))).astype(np.float32)
+    return (w * s.reshape(-1, 1, 1, 1)).astype(np.float32), ((b - mean) * s + beta).astype(np.float32)
+
+
+def conv_to_kmajor(w):
+    """(Cout, Cin, 3, 3) -> (Cout, 9*Cin) with k = (r*3+s)*Cin + c."""
+    co, ci = w.shape[:2]
+    return np.ascontiguousarray(w.transpose(0, 2, 3, 1).reshape(co, 9 * ci))
+
+
+def pack_whh(w_f, w_b):
+    """[2 dirs][768][192] -> bf16 [dir][rank][kp=96][row=384][2]; row = gate*96 + jj <-> W row
+    gate*192 + rank*96 + jj; element pair = k (2kp, 2kp+1)."""
+    out = np.empty((2, 2, LSTM_H // 2, 384, 2), np.float32)
+    for d, w in enumerate((w_f, w_b)):
+        w4 = w.reshape(4, 2, 96, LSTM_H // 2, 2)            # gate, rank, jj, kp, pair
+        out[d] = w4.transpose(1, 3, 0, 2, 4).reshape(2, LSTM_H // 2, 384, 2)
+    return out
+
+
+def pack_tensors(sd: dict) -> dict:
+    """Reference state_dict (numpy fp32) -> {blob entry name: (dtype, ndarray)}."""
+    variant, D, max_len, dec_max, = validate_state_dict(sd)
+    vocab = sd["dec.tok_emb.weight"].shape[0]
+    se = variant == "se"
+    t: dict[str, tuple[int, np.ndarray]] = {}
+
+    def f32(name, a):
+        t[name] = (DT_F32, np.ascontiguousarray(a, dtype=np.float32))
+
+    def bf16(name, a):
+        t[name] = (DT_BF16, f32_to_bf16_bits(np.ascontiguousarray(a, dtype=np.float32)))
+
+    t["meta"] = (DT_I32, np.asarray([0 if se else 1, D, max_len, dec_max, vocab, 0, 0, 0], np.int32))
+    for i in range(1, 7):
+        p = f"cnn.conv{i}"
+        w, b = fold_bn(sd[p + ".0.weight"], sd[p + ".0.bias"], sd[p + ".1.weight"], sd[p + ".1.bias"],
+                       sd[p + ".1.running_mean"], sd[p + ".1.running_var"])
+        if i == 1:
+            f32("conv1.w", w.reshape(64, 9))
+            f32("conv1.b", b)
+        else:
+            bf16(f"conv{i}.w", conv_to_kmajor(w))
+            f32(f"conv{i}.b", b)
+    w7, b7 = sd["cnn.conv7.weight"], sd["cnn.conv7.bias"]
+    if se:
+        w7, b7 = fold_bn(w7, b7, sd["cnn.bn7.weight"], sd["cnn.bn7.bias"], sd["cnn.bn7.running_mean"],
+                         sd["cnn.bn7.running_var"])
+        for k in (3, 4, 5):
+            f32(f"se{k}.w0", sd[f"cnn.se{k}.fc.0.weight"][:, :, 0])
+            f32(f"se{k}.b0", sd[f"cnn.se{k}.fc.0.bias"])
+            f32(f"se{k}.w2", sd[f"cnn.se{k}.fc.2.weight"][:, :, 0])
+            f32(f"se{k}.b2", sd[f"cnn.se{k}.fc.2.bias"])
+    bf16("conv7.w", conv_to_kmajor(w7))
+    f32("conv7.b", b7)
+    pw = sd["patch.proj.weight"][:, :, :, 0]                       # (D, 512, 2)
+    bf16("patch.w", pw.transpose(0, 2, 1).reshape(D, 1024))       # k = kh*512 + c
+    f32("patch.b", sd["patch.proj.bias"])
+    f32("patch.pos", sd["patch.pos_emb"][:32])
+    for l in range(2):
+        p = f"enc.layers.{l}."
+        bf16(f"enc{l}.in_w", sd[p + "self_attn.in_proj_weight"]); f32(f"enc{l}.in_b", sd[p + "self_attn.in_proj_bias"])
+        bf16(f"enc{l}.out_w", sd[p + "self_attn.out_proj.weight"]); f32(f"enc{l}.out_b", sd[p + "self_attn.out_proj.bias"])
+        bf16(f"enc{l}.l1_w", sd[p + "linear1.weight"]); f32(f"enc{l}.l1_b", sd[p + "linear1.bias"])
+        bf16(f"enc{l}.l2_w", sd[p + "linear2.weight"]); f32(f"enc{l}.l2_b", sd[p + "linear2.bias"])
+        for k in (1, 2):
+            f32(f"enc{l}.n{k}_g", sd[p + f"norm{k}.weight"]); f32(f"enc{l}.n{k}_b", sd[p + f"norm{k}.bias"])
+    f32("global_pos", sd["global_pos"])
+    if se:
+        p = "context_bilstm."
+        bf16("lstm.w_ih", np.concatenate([sd[p + "weight_ih_l0"], sd[p + "weight_ih_l0_reverse"]], 0))
+        f32("lstm.b", np.concatenate([sd[p + "bias_ih_l0"] + sd[p + "bias_hh_l0"],
+                                      sd[p + "bias_ih_l0_reverse"] + sd[p + "bias_hh_l0_reverse"]]))
+        bf16("lstm.w_hh", pack_whh(sd[p + "weight_hh_l0"], sd[p + "weight_hh_l0_reverse"]))
+    f32("dec.tok_emb", sd["dec.tok_emb.weight"])
+    f32("dec.pos", sd["dec.pos_emb"])
+    kv_w, kv_b = [], []
+    for l in range(2):
+        p = f"dec.decoder.layers.{l}."
+        bf16(f"dec{l}.sa_in_w", sd[p + "self_attn.in_proj_weight"]); f32(f"dec{l}.sa_in_b", sd[p + "self_attn.in_proj_bias"])
+        bf16(f"dec{l}.sa_out_w", sd[p + "self_attn.out_proj.weight"]); f32(f"dec{l}.sa_out_b", sd[p + "self_attn.out_proj.bias"])
+        cw, cb = sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"]
+        bf16(f"dec{l}.ca_q_w", cw[:D]); f32(f"dec{l}.ca_q_b", cb[:D])
+        kv_w.append(cw[D:]); kv_b.append(cb[D:])                   # rows: K (D) then V (D)
+        bf16(f"dec{l}.ca_out_w", sd[p + "multihead_attn.out_proj.weight"]); f32(f"dec{l}.ca_out_b", sd[p + "multihead_attn.out_proj.bias"])
+        bf16(f"dec{l}.l1_w", sd[p + "linear1.weight"]); f32(f"dec{l}.l1_b", sd[p + "linear1.bias"])
+        bf16(f"dec{l}.l2_w", sd[p + "linear2.weight"]); f32(f"dec{l}.l2_b", sd[p + "linear2.bias"])
+        for k in (1, 2, 3):
+            f32(f"dec{l}.n{k}_g", sd[p + f"norm{k}.weight"]); f32(f"dec{l}.n{k}_b", sd[p + f"norm{k}.bias"])
+    bf16("dec.ca_kv_w", np.concatenate(kv_w, 0))
+    f32("dec.ca_kv_b", np.concatenate(kv_b, 0))
+    ow = np.zeros((128, D), np.float32); ow[:vocab] = sd["dec.out_proj.weight"]
+    ob = np.zeros(128, np.float32); ob[:vocab] = sd["dec.out_proj.bias"]
+    bf16("dec.out_w", ow)
+    f32("dec.out_b", ob)
+    return t
+
+
+def pack_blob(sd: dict) -> bytes:
+    """Serialise: header {magic[8], u32 n, u32 0}, n entries {name[48], u32 dtype, u32 0, u64 offset,
+    u64 nbytes}, then 256-byte-aligned payloads."""
+    tensors = pack_tensors(sd)
+    n = len(tensors)
+    head = 16 + n * 72
+    off = (head + 255) // 256 * 256
+    entries, payload = [], []
+    for name, (dt, arr) in tensors.items():
+        raw = arr.tobytes()
+        nb = name.encode()
+        assert len(nb) < 48
+        entries.append(struct.pack("<48sIIQQ", nb, dt, 0, off, len(raw)))
+        pad = (-len(raw)) % 256
+        payload.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+    blob = MAGIC + struct.pack("<II", n, 0) + b"".join(entries)
+    blob += b"\0" * ((-len(blob)) % 256)
+    return blob + b"".join(payload)
+
+
+def variant_of(sd: dict) -> str:
+    return detect_variant(sd)

@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Generate the committed fixtures under tests/golden/ by IMPORTING THE REFERENCE.
+
+Runs only in the build container (needs /root/reference, read-only).  Nothing in the `-m gpu`
+tests, `smoke()` or `bench.py` runs this; they read the files it wrote.
+
+  python tests/golden/make_fixtures.py bank      # wordbank.npz      (Pillow + reference fonts)
+  python tests/golden/make_fixtures.py train     # fixture_se_ckpt.npz  (reference model, CPU training)
+  python tests/golden/make_fixtures.py golden    # golden_*.npz      (reference outputs = pinned oracle)
+
+Why a trained checkpoint: with default random init the reference's decoder output is
+input-independent and top-1/top-2 logit gaps are ~1e-3, so token-level parity under bf16 would be
+meaningless.  A few hundred teacher-forced Adam steps of the reference's own training
+forward (`KhmerOCR.forward`, se_model.py:240-289; recipe of notebook cells 14/16/17: Adam, CE with
+ignore_index=pad) on synthetic lines give real margins, non-trivial BatchNorm statistics and a
+learned <eos>.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+import warnings
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(REPO))
+warnings.filterwarnings("ignore")
+
+from khmer_ocr_cnn_transformer_b200 import synth                      # noqa: E402
+from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict  # noqa: E402
+from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import build_vocab  # noqa: E402
+
+CKPT = HERE / "fixture_se_ckpt.npz"
+MAX_GLOBAL_LEN = 1024      # fixture checkpoint keeps 1024 global positions (c4 needs 928)
+
+
+# ------------------------------------------------------------------------------------------
+def pseudo_words(rng, n):
+    """Vocab-derived pseudo-corpus: Khmer syllables (consonant [+ coeng consonant] [+ vowel]
+    [+ sign]), digit strings and a little ASCII punctuation."""
+    cons = [chr(c) for c in list(range(0x1780, 0x179D)) + list(range(0x179F, 0x17A3))]
+    vowels = [chr(c) for c in range(0x17B6, 0x17C6)]
+    signs = [chr(c) for c in (0x17C6, 0x17C7, 0x17C8, 0x17CB)]
+    kdigits = [chr(c) for c in range(0x17E0, 0x17EA)]
+    punct = list("!?%()-.,:/") + ["។", "ៗ", "«", "»"]
+    words = []
+    while len(words) < n:
+        r = rng.random()
+        if r < 0.8:
+            w = ""
+            for _ in range(int(rng.integers(1, 4))):
+                w += cons[int(rng.integers(len(cons)))]
+                if rng.random() < 0.25:
+                    w += "្" + cons[int(rng.integers(len(cons)))]
+                if rng.random() < 0.7:
+                    w += vowels[int(rng.integers(len(vowels)))]
+                if rng.random() < 0.15:
+                    w += signs[int(rng.integers(len(signs)))]
+        elif r < 0.9:
+            src = kdigits if rng.random() < 0.5 else list("0123456789")
+            w = "".join(src[int(rng.integers(10))] for _ in range(int(rng.integers(1, 5))))
+        else:
+            w = cons[int(rng.integers(len(cons)))] + punct[int(rng.integers(len(punct)))]
+        words.append(w)
+    return words
+
+
+def stage_bank(args):
+    from PIL import Image, ImageDraw, ImageFont
+    vocab = build_vocab()
+    rng = np.random.Generator(np.random.PCG64(1234))
+    fonts = sorted((REF / "fonts").glob("*.ttf"))
+    sizes = [14, 22, 28]                       # generate_document_text.py uses 14; 22/28 widen the range
+    pix, offs, widths, heights, group, space, tok_flat, tok_off = [], [0], [], [], [], [], [], [0]
+    g = 0
+    for fpath in fonts:
+        for size in sizes:
+            font = ImageFont.truetype(str(fpath), size, layout_engine=ImageFont.Layout.BASIC)
+            asc, desc = font.getmetrics()
+            canvas_h = asc + desc + 2
+            sp = max(2, int(round(font.getlength(" "))))
+            words = pseudo_words(rng, args.words_per_group)
+            for w in words:
+                bbox = ImageDraw.Draw(Image.new("L", (1, 1))).textbbox((0, 0), w, font=font)
+                tw = bbox[2] - bbox[0]
+                if tw <= 0:
+                    continue
+                img = Image.new("L", (tw + 2, canvas_h), 255)
+                ImageDraw.Draw(img).text((1 - bbox[0], 1), w, fill=0, font=font)
+                a = np.asarray(img, np.uint8)
+                pix.append(a.reshape(-1))
+                offs.append(offs[-1] + a.size)
+                widths.append(a.shape[1]); heights.append(a.shape[0]); group.append(g)
+                toks = [vocab.get(ch, 1) for ch in w]
+                tok_flat.extend(toks); tok_off.append(tok_off[-1] + len(toks))
+            space.append(sp)
+            g += 1
+    out = HERE / "wordbank.npz"
+    np.savez_compressed(out, pixels=np.concatenate(pix), offsets=np.asarray(offs, np.int64),
+                        widths=np.asarray(widths, np.int32), heights=np.asarray(heights, np.int32),
+                        group=np.asarray(group, np.int32), space=np.asarray(space, np.int32),
+                        tok_flat=np.asarray(tok_flat, np.int32), tok_off=np.asarray(tok_off, np.int64))
+    print(f"wrote {out}: {len(widths)} words, {g} groups, {out.stat().st_size/1e6:.2f} MB")
+
+
+# ------------------------------------------------------------------------------------------
+def _ref_model(sd=None, variant="se", max_global_len=MAX_GLOBAL_LEN):
+    import torch
+    sys.path.insert(0, str(REF))
+    if variant == "se":
+        from netra_ocr.recognition.model.se_model import KhmerOCR
+    else:
+        from netra_ocr.recognition.model.vgg_model import KhmerOCR
+    m = KhmerOCR(vocab_size=124, pad_idx=0, emb_dim=384, max_global_len=max_global_len)
+    if sd is not None:
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in sd.items()},
+                          strict=True)
+    return m
+
+
+def stage_train(args):
+    import torch
+    import torch.nn.functional as F
+    from oracle import recognizer_np as O
+    torch.set_num_threads(args.threads)
+    torch.manual_seed(0)
+    # start from the seeded numpy init so the whole fixture is reproducible from this script
+    m = _ref_model(seeded_state_dict("se", seed=7, max_global_len=MAX_GLOBAL_LEN))
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=args.lr)
+    # fixed pool = the lines the parity tests and the c2 bench use (seed 0), plus fresh ones
+    bank = synth.WordBank()
+    pool_imgs, pool_lbls = synth.make_lines(args.pool, 400, 800, seed=0, bank=bank)
+    extra_imgs, extra_lbls = synth.make_lines(args.pool, 200, 1000, seed=1, bank=bank)
+    imgs, lbls = pool_imgs + extra_imgs, pool_lbls + extra_lbls
+    chunks = [torch.from_numpy(O.preprocess_gray(im)[1]) for im in imgs]
+    rng = np.random.Generator(np.random.PCG64(99))
+    t0 = time.time()
+    for step in range(args.steps):
+        if step == int(args.steps * 0.8):
+            for gparam in opt.param_groups:
+                gparam["lr"] = args.lr * 0.3
+        idx = rng.choice(len(imgs), args.batch, replace=False)
+        chunk_lists = [list(chunks[i]) for i in idx]
+        L = max(len(lbls[i]) for i in idx) + 1
+        tin = torch.zeros(args.batch, L, dtype=torch.long)
+        tout = torch.zeros(args.batch, L, dtype=torch.long)
+        for r, i in enumerate(idx):
+            ids = [int(t) for t in lbls[i]]
+            tin[r, :len(ids) + 1] = torch.tensor([2] + ids)
+            tout[r, :len(ids) + 1] = torch.tensor(ids + [3])
+        logits = m(chunk_lists, tin)
+        loss = F.cross_entropy(logits.reshape(-1, 124), tout.reshape(-1), ignore_index=0)
+        opt.zero_grad(); loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        if step % 10 == 0 or step == args.steps - 1:
+            print(f"step {step} loss {loss.item():.4f} elapsed {time.time()-t0:.0f}s", flush=True)
+        if (step + 1) % 100 == 0 or step == args.steps - 1:
+            _save_ckpt(m)
+    _save_ckpt(m)
+
+
+def _save_ckpt(m):
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    # fp16 storage halves the file; the CHECKPOINT is *defined* as these fp16 values widened to fp32.
+    # running_var / BN params stay fp32 (tiny, and fp16 would lose range).
+    out = {}
+    for k, v in sd.items():
+        small = v.ndim == 1
+        out[k] = v.astype(np.float32) if small else v.astype(np.float16)
+    np.savez_compressed(CKPT, **out)
+    print(f"wrote {CKPT} {CKPT.stat().st_size/1e6:.1f} MB", flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def stage_golden(args):
+    import torch
+    from PIL import Image
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    sys.path.insert(0, str(REF))
+    from netra_ocr.recognition.preprocessor import ImagePreprocessor
+    from netra_ocr.recognition.config import OCRConfig
+    from netra_ocr.recognition.predictor import OCRPredictor
+    from netra_ocr.recognition.tokenizer import Tokenizer
+    torch.set_num_threads(args.threads)
+    cfg = OCRConfig(device="cpu", max_seq_len=MAX_GLOBAL_LEN)
+    pre = ImagePreprocessor(cfg)
+    rng = np.random.Generator(np.random.PCG64(2024))
+
+    # ---- (1) preprocessing goldens: random + structured images, reference output bit patterns
+    prep = {}
+    cases = [(30, 375), (48, 400), (61, 333), (20, 40), (48, 100), (96, 1000), (17, 911), (50, 52),
+             (48, 84), (48, 85), (33, 1650), (48, 2400)]
+    for ci, (h, w) in enumerate(cases):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if ci % 2:
+            img[:, : w // 3] = 255
+        ref = pre.process(Image.fromarray(img)).numpy()
+        prep[f"img{ci}"] = img
+        prep[f"chunks{ci}"] = ref
+    rgb = rng.integers(0, 256, (33, 77, 3), dtype=np.uint8)
+    prep["rgb"] = rgb
+    prep["rgb_l"] = np.asarray(Image.fromarray(rgb).convert("L"))
+    np.savez_compressed(HERE / "golden_preprocess.npz", **prep)
+
+    # ---- (2) model goldens on the trained SE fixture
+    sd = load_checkpoint(CKPT)
+    tmp = Path("/tmp/fixture_se.pth")
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, tmp)
+    from netra_ocr.recognition.model.se_model import KhmerOCR as SE
+    tok = Tokenizer(REF / "netra_ocr/recognition/char2idx.json")
+    pred = OCRPredictor(tmp, tok, cfg, SE)
+    m = pred.model
+    bank = synth.WordBank()
+    imgs, lbls = synth.make_lines(6, 400, 800, seed=0, bank=bank)        # first lines of the c2 batch
+    # c1: a line resized to exactly 48x400 (5 chunks), a short one (2 chunks), a long one
+    extra, _ = synth.make_lines(3, 100, 1500, seed=5, bank=bank)
+    c1 = np.asarray(Image.fromarray(imgs[0]).resize((400, 48), Image.Resampling.BILINEAR))
+    imgs = imgs + extra + [c1]
+    g = {}
+    texts = []
+    for li, im in enumerate(imgs):
+        chunks = pre.process(Image.fromarray(im))
+        with torch.no_grad():
+            f = m.cnn(chunks)
+            p = m.patch(f)[0]
+            e = m.enc(p.transpose(0, 1).contiguous()).transpose(0, 1)
+            merged = e.reshape(1, -1, 384)
+            limit = min(merged.shape[1], m.global_pos.size(0))
+            merged = merged[:, :limit] + m.global_pos[:limit].unsqueeze(0)
+            mem, _ = m.context_bilstm(merged)
+            # greedy tokens exactly as the reference loop does it
+            gen = [2]
+            step_logits = []
+            mask = torch.zeros((1, mem.shape[1]), dtype=torch.bool)
+            for _ in range(cfg.decode_max_len):
+                lg = m.dec(torch.LongTensor([gen]), mem, mask)
+                step_logits.append(lg[0, -1].numpy().copy())
+                nx = int(torch.argmax(lg[0, -1]).item())
+                if nx == 3:
+                    break
+                gen.append(nx)
+        text = pred.predict(Image.fromarray(im), beam_width=1)
+        assert text == tok.decode(gen), (text, tok.decode(gen))
+        texts.append(text)
+        g[f"img{li}"] = im
+        g[f"cnn{li}"] = f.numpy()[:2].astype(np.float32)          # first two chunks only (size)
+        g[f"enc{li}"] = e.numpy().astype(np.float32)
+        g[f"mem{li}"] = mem[0].numpy().astype(np.float32)
+        g[f"tokens{li}"] = np.asarray(gen, np.int32)
+        g[f"step_logits{li}"] = np.stack(step_logits).astype(np.float32)
+        if li < len(lbls):
+            g[f"label{li}"] = lbls[li]
+        print(li, im.shape, chunks.shape, len(gen), repr(text[:40]), flush=True)
+    g["n_lines"] = np.asarray(len(imgs))
+    # predict_batch on all of them (the production entry) must agree with per-line predict
+    batch_texts = pred.predict_batch([Image.fromarray(i) for i in imgs], beam_width=1, batch_size=8)
+    assert batch_texts == texts
+    g["texts"] = np.asarray(texts)
+    np.savez_compressed(HERE / "golden_se.npz", **g)
+
+    # ---- (3) VGG baseline (config 5) with the seeded init (no SE, no BiLSTM, bare conv7)
+    vsd = seeded_state_dict("vgg", seed=11, max_global_len=MAX_GLOBAL_LEN)
+    vm = _ref_model(vsd, "vgg").eval()
+    gv = {}
+    for li, im in enumerate(imgs[:3]):
+        chunks = pre.process(Image.fromarray(im))
+        with torch.no_grad():
+            f = vm.cnn(chunks)
+            p = vm.patch(f)[0]
+            e = vm.enc(p.transpose(0, 1).contiguous()).transpose(0, 1)
+            mem = e.reshape(1, -1, 384) + vm.global_pos[: e.shape[0] * 32].unsqueeze(0)
+            gen = [2]
+            step_logits = []
+            mask = torch.zeros((1, mem.shape[1]), dtype=torch.bool)
+            for _ in range(24):
+                lg = vm.dec(torch.LongTensor([gen]), mem, mask)
+                step_logits.append(lg[0, -1].numpy().copy())
+                nx = int(torch.argmax(lg[0, -1]).item())
+                if nx == 3:
+                    break
+                gen.append(nx)
+        gv[f"img{li}"] = im
+        gv[f"enc{li}"] = e.numpy().astype(np.float32)
+        gv[f"mem{li}"] = mem[0].numpy().astype(np.float32)
+        gv[f"tokens{li}"] = np.asarray(gen, np.int32)
+        gv[f"step_logits{li}"] = np.stack(step_logits).astype(np.float32)
+    gv["n_lines"] = np.asarray(3)
+    np.savez_compressed(HERE / "golden_vgg.npz", **gv)
+    for f in ("golden_preprocess.npz", "golden_se.npz", "golden_vgg.npz"):
+        print(f, f"{(HERE / f).stat().st_size/1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("stage", choices=["bank", "train", "golden"])
+    ap.add_argument("--words-per-group", type=int, default=36)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--pool", type=int, default=256)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--threads", type=int, default=6)
+    a = ap.parse_args()
+    {"bank": stage_bank, "train": stage_train, "golden": stage_golden}[a.stage](a)

@@ -1,0 +1,35 @@
+"""Shared test helpers (layout conversions, error metrics, fixture loading)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def bf16_u16_to_f32(a: np.ndarray) -> np.ndarray:
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def pl_to_nchw(buf_u16: np.ndarray, n: int, H: int, W: int, C: int) -> np.ndarray:
+    """padded-linear bf16 buffer [(n*(H+1)*(W+1)), C] -> fp32 (n, C, H, W) plus the pad values."""
+    x = bf16_u16_to_f32(buf_u16).reshape(n, H + 1, W + 1, C)
+    valid = x[:, :H, :W, :].transpose(0, 3, 1, 2)
+    pads = np.concatenate([x[:, H, :, :].reshape(-1), x[:, :, W, :].reshape(-1)])
+    return np.ascontiguousarray(valid), pads
+
+
+def rel_err(a: np.ndarray, b: np.ndarray) -> float:
+    """||a-b||_2 / ||b||_2"""
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) /
+                 (np.linalg.norm(b.astype(np.float64)) + 1e-30))
+
+
+def max_err(a, b) -> float:
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+
+
+def load_fixture_ckpt():
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    return load_checkpoint(GOLDEN / "fixture_se_ckpt.npz")

@@ -1,0 +1,80 @@
+"""tcgen05 GEMM unit tests through the C ABI: tcgen05 kernel vs the CUDA-core check kernel vs numpy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(impl, a, w, M, N, taps, cin, tap_off, bias, relu, pl):
+    import torch
+    from khmer_ocr_cnn_transformer_b200 import _native
+    lib = _native.load_library()
+    out32 = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    out16 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    to = np.asarray(tap_off, np.int32)
+    b = torch.from_numpy(bias).cuda() if bias is not None else None
+    _native.check(lib.kocr_test_gemm(impl, a.data_ptr(), a.shape[0], w.data_ptr(), M, N, taps, cin,
+                                     to.ctypes.data, b.data_ptr() if b is not None else None, relu,
+                                     pl[0], pl[1], out32.data_ptr(), out16.data_ptr(), None))
+    torch.cuda.synchronize()
+    return out32.cpu().numpy(), out16.float().cpu().numpy()
+
+
+def _reference(a, w, M, N, taps, cin, tap_off, bias, relu, pl):
+    A = a.float().cpu().numpy().astype(np.float64)
+    W = w.float().cpu().numpy().astype(np.float64).reshape(N, taps, cin)
+    rows = A.shape[0]
+    out = np.zeros((M, N))
+    for t in range(taps):
+        idx = np.arange(M) + tap_off[t]
+        ok = (idx >= 0) & (idx < rows)
+        sh = np.zeros((M, cin))
+        sh[ok] = A[idx[ok]]
+        out += sh @ W[:, t, :].T
+    if bias is not None:
+        out += bias
+    if relu:
+        out = np.maximum(out, 0)
+    if pl[0] > 0:
+        S, P = (pl[0] + 1) * (pl[1] + 1), pl[1] + 1
+        r = np.arange(M) % S
+        valid = ((r // P) < pl[0]) & ((r % P) < pl[1])
+        out[~valid] = 0
+    return out
+
+
+CASES = [
+    # M, N, taps, cin, relu, pl
+    (128, 128, 1, 64, 0, (0, 0)),          # one tile, one k-block
+    (128, 128, 1, 384, 0, (0, 0)),         # k loop wraps the 6-stage ring once
+    (300, 384, 1, 1024, 1, (0, 0)),        # partial M tile, 3 N tiles, ring wraps many times
+    (1000, 256, 1, 384, 0, (0, 0)),        # BN=256 path
+    (2 * 338, 256, 9, 128, 1, (12, 25)),   # conv3-like implicit GEMM with row mask
+    (5 * 104, 512, 9, 512, 1, (3, 25)),    # conv7-like, K = 4608
+    (37, 128, 1, 384, 0, (0, 0)),          # decode-step sized
+    (148 * 128 * 2 + 77, 128, 1, 64, 0, (0, 0)),   # persistent loop: several tiles per CTA
+]
+
+
+@pytest.mark.parametrize("M,N,taps,cin,relu,pl", CASES)
+def test_gemm_tcgen05_matches_check_kernel_and_numpy(M, N, taps, cin, relu, pl):
+    import torch
+    rng = np.random.default_rng(M * 7 + N)
+    rows = M
+    a = torch.from_numpy(rng.standard_normal((rows, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = torch.from_numpy((rng.standard_normal((N, taps * cin)) / np.sqrt(taps * cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    if taps == 9:
+        P = pl[1] + 1
+        tap_off = [(r - 1) * P + (s - 1) for r in range(3) for s in range(3)]
+    else:
+        tap_off = [0]
+    ref = _reference(a, w, M, N, taps, cin, tap_off, bias, relu, pl)
+    chk32, _ = _run(1, a, w, M, N, taps, cin, tap_off, bias, relu, pl)
+    assert np.abs(chk32 - ref).max() < 2e-3, "CUDA-core check kernel disagrees with numpy"
+    tc32, tc16 = _run(0, a, w, M, N, taps, cin, tap_off, bias, relu, pl)
+    err = np.abs(tc32 - ref).max()
+    assert err < 2e-3, f"tcgen05 fp32 output max err {err}"
+    # the bf16 output is the fp32 result rounded to nearest-even
+    want16 = torch.from_numpy(tc32).to(torch.bfloat16).float().numpy()
+    assert np.array_equal(tc16, want16)

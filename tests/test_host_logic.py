@@ -1,0 +1,144 @@
+"""CPU tests of the host-side logic and of the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from khmer_ocr_cnn_transformer_b200 import _native, weights, scheduling, synth
+from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict, state_dict_spec, validate_state_dict
+from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import Tokenizer, build_vocab
+from khmer_ocr_cnn_transformer_b200.recognition.config import OCRConfig
+
+REPO = Path(__file__).resolve().parent.parent
+REC = REPO / "khmer_ocr_cnn_transformer_b200" / "recognition"
+
+
+def test_vocab_layout():
+    v = build_vocab()
+    assert len(v) == 124
+    assert [v["<pad>"], v["<unk>"], v["<sos>"], v["<eos>"], v[" "]] == [0, 1, 2, 3, 4]
+    assert v["ក"] == 42 and v["‹"] == 122 and v["›"] == 123
+    assert json.load(open(REC / "char2idx.json", encoding="utf-8")) == v
+    ref = Path("/root/reference/netra_ocr/recognition/char2idx.json")
+    if ref.exists():
+        assert json.load(open(ref, encoding="utf-8")) == v
+
+
+def test_tokenizer_decode():
+    tok = Tokenizer(REC / "char2idx.json")
+    assert (tok.sos_idx, tok.eos_idx, tok.pad_idx, len(tok)) == (2, 3, 0, 124)
+    assert tok.decode([2, 42, 0, 4, 43, 3, 44]) == "ក ខ"      # skip sos/pad, stop at eos
+    with pytest.raises(FileNotFoundError):
+        Tokenizer(REC / "nope.json")
+
+
+def test_config_defaults():
+    c = OCRConfig()
+    assert (c.img_height, c.chunk_width, c.chunk_overlap, c.emb_dim, c.max_seq_len, c.decode_max_len) == \
+        (48, 100, 16, 384, 4096, 256)
+
+
+def test_state_dict_spec_counts():
+    se = state_dict_spec("se")
+    vgg = state_dict_spec("vgg")
+    # 137 entries in the reference = 116 parameters + 14 running stats + 7 num_batches_tracked
+    assert len(se) == 137 - 7 and len(vgg) == 112 - 6
+    n_se = sum(int(np.prod(s)) for k, s in se.items() if "running" not in k)
+    assert n_se == 17_579_980                       # SURVEY.md §2.1 parameter count
+
+
+def test_bf16_rounding_matches_torch():
+    import torch
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 3
+    x[:4] = [0.0, -0.0, 1.0000001, 65504.0]
+    mine = weights.f32_to_bf16_bits(x)
+    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(mine, ref)
+
+
+def test_pack_blob_layout_and_folding():
+    sd = seeded_state_dict("se", 3)
+    assert validate_state_dict(sd)[0] == "se"
+    t = weights.pack_tensors(sd)
+    # BN folding identity on one output channel
+    w, b = weights.fold_bn(sd["cnn.conv2.0.weight"], sd["cnn.conv2.0.bias"], sd["cnn.conv2.1.weight"],
+                           sd["cnn.conv2.1.bias"], sd["cnn.conv2.1.running_mean"], sd["cnn.conv2.1.running_var"])
+    x = np.random.default_rng(1).standard_normal((64, 3, 3)).astype(np.float32)
+    pre = (sd["cnn.conv2.0.weight"][5] * x).sum() + sd["cnn.conv2.0.bias"][5]
+    bn = (pre - sd["cnn.conv2.1.running_mean"][5]) / np.sqrt(sd["cnn.conv2.1.running_var"][5] + 1e-5) * \
+        sd["cnn.conv2.1.weight"][5] + sd["cnn.conv2.1.bias"][5]
+    assert abs(((w[5] * x).sum() + b[5]) - bn) < 1e-4
+    # K-major conv layout: k = (r*3+s)*Cin + c
+    km = weights.conv_to_kmajor(w)
+    assert km.shape == (128, 576) and km[7, (1 * 3 + 2) * 64 + 9] == w[7, 9, 1, 2]
+    # patch layout: k = kh*512 + c
+    pw = weights.bf16_bits_to_f32(t["patch.w"][1]).reshape(384, 1024)
+    ref = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(sd["patch.proj.weight"][3, 17, 1, 0].reshape(1)))[0]
+    assert pw[3, 512 + 17] == ref
+    # LSTM recurrent packing: [dir][rank][kp][row][pair]
+    whh = weights.bf16_bits_to_f32(t["lstm.w_hh"][1]).reshape(2, 2, 96, 384, 2)
+    src = sd["context_bilstm.weight_hh_l0_reverse"]
+    gate, rank, jj, kp, pair = 2, 1, 40, 33, 1
+    want = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(src[gate * 192 + rank * 96 + jj, 2 * kp + pair].reshape(1)))[0]
+    assert whh[1, rank, kp, gate * 96 + jj, pair] == want
+    blob = weights.pack_blob(sd)
+    assert blob[:8] == b"KOCRW001" and len(blob) % 256 == 0
+    vt = weights.pack_tensors(seeded_state_dict("vgg", 4))
+    assert "lstm.w_ih" not in vt and "se3.w0" not in vt and vt["meta"][1][0] == 1
+
+
+def test_scheduling_chunk_counts_match_reference_rule():
+    # W=400 -> 5, 800 -> 10, 1600 -> 20, 2400 -> 29, 100 -> 2
+    for w, n in [(400, 5), (800, 10), (1600, 20), (2400, 29), (100, 2), (84, 1), (85, 2), (50, 1)]:
+        assert scheduling.chunks_for(48, w) == n
+    assert scheduling.resized_width(30, 375) == 600 and scheduling.resized_width(20, 10) == 50
+    assert scheduling.chunks_for(48, 48 * 300, max_seq_len=4096) == 128       # truncation at 4096 tokens
+
+
+def test_plan_batches_and_sharding():
+    rng = np.random.default_rng(0)
+    shapes = [(int(rng.integers(20, 70)), int(rng.integers(100, 2000))) for _ in range(500)]
+    batches = scheduling.plan_batches(shapes, max_lines=64, max_chunks=300)
+    assert sorted(i for b in batches for i in b) == list(range(500))
+    for b in batches:
+        assert len(b) <= 64 and sum(scheduling.chunks_for(*shapes[i]) for i in b) <= 300
+    for ws in (1, 2, 4, 8):
+        shards = scheduling.shard_lines(shapes, ws)
+        assert sorted(i for s in shards for i in s) == list(range(500))
+        loads = [sum(scheduling.chunks_for(*shapes[i]) for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(scheduling.chunks_for(*s) for s in shapes)
+    assert scheduling.plan_batches([], 8, 8) == []
+
+
+def test_synth_lines_are_deterministic():
+    a, la = synth.make_lines(4, 400, 800, seed=0)
+    b, lb = synth.make_lines(4, 400, 800, seed=0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and all(np.array_equal(x, y) for x, y in zip(la, lb))
+    for im in a:
+        assert im.dtype == np.uint8 and im.ndim == 2 and (im == 255).mean() > 0.5
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = (REPO / "include" / "kocr.h").read_text()
+    declared = set(re.findall(r"\b(kocr_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.kocr_abi_version() == 1
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    blob = weights.pack_blob(seeded_state_dict("vgg", 0, max_global_len=64))
+    with pytest.raises(_native.KocrError, match="no CUDA device"):
+        _native.Recognizer(blob, max_lines=2, max_chunks=8)
+    from khmer_ocr_cnn_transformer_b200.recognition.predictor import OCRPredictor
+    from khmer_ocr_cnn_transformer_b200.recognition.model.se_model import KhmerOCR
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        OCRPredictor("x.pth", Tokenizer(REC / "char2idx.json"), OCRConfig(device="cpu"), KhmerOCR)
