@@ -83,8 +83,13 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
 
 /* Options (tests / parity tooling):
  *   "trace_logits"  1 -> decode_greedy records the last-position logits of every step
- *   "force_tokens"  1 -> decode_greedy feeds the ids set with kocr_set_forced_tokens instead of its argmax */
+ *   "force_tokens"  1 -> decode_greedy feeds the ids set with kocr_set_forced_tokens instead of its argmax
+ *   "kernel_timing" 1 -> per-launch CUDA-event timing (see kocr_read_kernel_timing); setting it clears the totals */
 int kocr_set_option(kocr_handle* h, const char* name, int value);
+/* With option "kernel_timing" = 1 every launch of the one-time stages (2-5a) is bracketed by CUDA events
+ * on its stream.  This call synchronises and writes one line per launch site:
+ * "<site> <total ms> <launches> <algorithmic FLOPs summed over those launches>\n". */
+int kocr_read_kernel_timing(kocr_handle* h, char* text_out, size_t cap);
 int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens /* [n_lines, KOCR_TOKENS_LD] */, int n_lines);
 
 /* Copy an intermediate of the last batch to the host (tests only).  Names: "chunks" f32 (n,1,48,100);

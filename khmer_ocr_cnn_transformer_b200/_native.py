@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing",
 ]
 
 _lib = None
@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.kocr_set_forced_tokens.argtypes = [vp, vp, i32]
     lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
+    lib.kocr_read_kernel_timing.restype = i32
     lib.kocr_launch_count.restype = i64
     lib.kocr_test_gemm.argtypes = [i32, vp, i64, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp]
     for f in ("kocr_create", "kocr_destroy", "kocr_model_info", "kocr_gather_chunks",
@@ -175,6 +177,16 @@ class Recognizer:
         dtype = self.DEBUG_DTYPES.get(name, np.uint16)       # bf16 buffers come back as raw uint16
         out = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
         check(self.lib.kocr_debug_read(self._h, name.encode(), _ptr(out), out.nbytes, C.byref(n)))
+        return out
+
+    def kernel_timing(self) -> dict:
+        """{site: {"ms": total, "launches": n, "flops": algorithmic FLOPs over those launches}}"""
+        buf = C.create_string_buffer(1 << 16)
+        check(self.lib.kocr_read_kernel_timing(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n, fl = line.split()
+            out[name] = {"ms": float(ms), "launches": int(n), "flops": float(fl)}
         return out
 
     def workspace_bytes(self) -> int:

@@ -63,15 +63,20 @@ int launch_bilstm(const float* gin /*[Mtok,1536]*/, const __nv_bfloat16* whh_pac
 size_t bilstm_whh_packed_elems();
 
 // ---- decoder step kernels ---------------------------------------------------------------
-int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, int t, const float* tok_emb, const float* pos_emb,
-                     float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines, cudaStream_t stream);
+// The generated position of a step is t = *step_base + step_off: step_base lives on the device so that a
+// captured CUDA graph of 8 steps can be replayed for every group of 8 positions.
+int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base, int step_off, const float* tok_emb,
+                     const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
+                     cudaStream_t stream);
 int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache, float* vcache /*[L, DEC_MAX, 384]*/,
-                         const int* tokens, int t, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
-                         cudaStream_t stream);
+                         const int* tokens, const int* step_base, int step_off, const int* finished,
+                         __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
 int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,
-                          const int* line_tok_off, const int* line_T, int max_T, __nv_bfloat16* out,
-                          __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
+                          const int* line_tok_off, const int* line_T, int max_T, const int* finished,
+                          __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
 int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,
-                      int t, int n_lines, cudaStream_t stream);
+                      const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
+                      cudaStream_t stream);
+int launch_dec_bump(int* step_base, int n, cudaStream_t stream);
 
 }  // namespace kocr

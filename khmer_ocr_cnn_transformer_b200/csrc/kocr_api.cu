@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace kocr {
@@ -83,6 +84,19 @@ struct kocr_handle {
     // options
     int trace_logits = 0, force_tokens = 0;
     bool have_forced = false;
+    cudaStream_t own_stream = nullptr;       // used when the caller passes stream == NULL (blocking stream:
+                                             // implicitly ordered with the legacy default stream)
+    struct DecGraph { cudaGraphExec_t exec = nullptr; size_t nodes = 0; };
+    std::map<std::tuple<int, int, int, int>, DecGraph> dec_graphs;   // (n_lines, max_T bucket, trace, force)
+    bool decode_warmed = false;
+    int use_graphs = 1;
+    // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
+    int kernel_timing = 0;
+    struct Site { std::string name; double flops = 0; double ms = 0; int count = 0; };
+    std::vector<Site> sites;
+    struct Pending { int site; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
     // device arrays inside staging_dev
     LineDesc* d_lines = nullptr; int* d_chunk_line = nullptr; int* d_row_pos = nullptr;
     int* d_line_tok_off = nullptr; int* d_line_T = nullptr; LstmGroup* d_groups = nullptr;
@@ -196,7 +210,7 @@ int carve_workspace(kocr_handle* h) {
         {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2},
         {"vtab", L * (size_t)preprocess_vtab_ints_per_line() * 4},
         {"tokens", L * KOCR_TOKENS_LD * 4}, {"forced", L * KOCR_TOKENS_LD * 4}, {"lengths", L * 4},
-        {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4},
+        {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4}, {"step_base", 64},
         {"dx", L * D * 4}, {"dxb", L * D * 2}, {"dqkv", L * 3 * D * 4}, {"dao", L * D * 2}, {"dy", L * D * 4},
         {"dq", L * D * 4}, {"dh", L * 4 * D * 2}, {"logits", L * VOCAB_PAD * 4},
         {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
@@ -218,6 +232,7 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaMalloc(&h->staging_dev, h->staging_bytes));
     KOCR_CUDA(cudaMallocHost(&h->pinned_flag, 64));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming));
+    KOCR_CUDA(cudaStreamCreate(&h->own_stream));
     return 0;
 }
 
@@ -230,6 +245,27 @@ int ensure(Buf& b, size_t bytes) {
     b.bytes = want;
     return 0;
 }
+
+// ---- per-launch timing ------------------------------------------------------------------------
+struct SiteTimer {
+    kocr_handle* h; cudaStream_t s; int idx = -1; cudaEvent_t a = nullptr, b = nullptr;
+    SiteTimer(kocr_handle* h_, const char* name, double flops, cudaStream_t s_) : h(h_), s(s_) {
+        if (!h->kernel_timing) return;
+        for (size_t i = 0; i < h->sites.size(); ++i) if (h->sites[i].name == name) idx = (int)i;
+        if (idx < 0) { kocr_handle::Site st; st.name = name; h->sites.push_back(st); idx = (int)h->sites.size() - 1; }
+        h->sites[idx].flops += flops;
+        auto get = [&]() { cudaEvent_t e = nullptr; if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, s);
+    }
+    ~SiteTimer() {
+        if (idx < 0) return;
+        cudaEventRecord(b, s);
+        kocr_handle::Pending p; p.site = idx; p.a = a; p.b = b;
+        h->pending.push_back(p);
+    }
+};
+#define TIMED(name, flops, call) do { SiteTimer _t(h, name, flops, s); KOCR_TRY(call); } while (0)
 
 // ---- GEMM convenience wrappers -------------------------------------------------------------
 GemmEpilogue ep_none() {
@@ -265,18 +301,20 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     if (NC == 0) return 0;
     const bool se = h->variant == 0;
     auto B = [&](const char* n) { return buf<__nv_bfloat16>(h, n); };
-    KOCR_TRY(launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s)); ++g_launches;
-    KOCR_TRY(gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
-    KOCR_TRY(launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
-    KOCR_TRY(gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
-    KOCR_TRY(gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
-    KOCR_TRY(launch_se_pool(B("conv4"), B("pool3"), NC, 12, 25, 256, se ? &h->se[0] : nullptr, s)); ++g_launches;
-    KOCR_TRY(gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
-    KOCR_TRY(gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
-    KOCR_TRY(launch_se_pool(B("conv6"), B("pool4"), NC, 6, 25, 512, se ? &h->se[1] : nullptr, s)); ++g_launches;
+    const double nc = NC;
+    auto cf = [&](int H, int W, int ci, int co) { return 2.0 * nc * H * W * 9.0 * ci * co; };   // algorithmic conv FLOPs
+    TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s)); ++g_launches;
+    TIMED("conv2", cf(24, 50, 64, 128), gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
+    TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
+    TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
+    TIMED("conv4", cf(12, 25, 256, 256), gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
+    TIMED("se3_pool3", se ? nc * 409600.0 : 0, launch_se_pool(B("conv4"), B("pool3"), NC, 12, 25, 256, se ? &h->se[0] : nullptr, s)); ++g_launches;
+    TIMED("conv5", cf(6, 25, 256, 512), gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
+    TIMED("conv6", cf(6, 25, 512, 512), gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
+    TIMED("se4_pool4", se ? nc * 1638400.0 : 0, launch_se_pool(B("conv6"), B("pool4"), NC, 6, 25, 512, se ? &h->se[1] : nullptr, s)); ++g_launches;
     // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
-    KOCR_TRY(gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
-    KOCR_TRY(launch_se_finalpool(B("conv7"), B("patch_in"), NC, 3, 25, 512, se ? &h->se[2] : nullptr, s)); ++g_launches;
+    TIMED("conv7", cf(3, 25, 512, 512), gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
+    TIMED("se5_finalpool", se ? nc * 1638400.0 : 0, launch_se_finalpool(B("conv7"), B("patch_in"), NC, 3, 25, 512, se ? &h->se[2] : nullptr, s)); ++g_launches;
 
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");
@@ -285,27 +323,27 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
         GemmEpilogue e = ep_none();
         e.bias = h->patch_b; e.addend = h->patch_pos; e.ld_add = D_MODEL; e.add_period = TOK_PER_CHUNK;
         e.out_f32 = x; e.ld_f32 = D_MODEL; e.out_bf16 = xb; e.ld_bf16 = D_MODEL;
-        KOCR_TRY(gemm_linear(h, B("patch_in"), M, h->patch_w, D_MODEL, 1024, e, s));
+        TIMED("patch_proj", 2.0 * M * 1024 * D_MODEL, gemm_linear(h, B("patch_in"), M, h->patch_w, D_MODEL, 1024, e, s));
     }
     for (int l = 0; l < 2; ++l) {
         const EncLayerW& w = h->enc[l];
         GemmEpilogue e = ep_none();
         e.bias = w.in_b; e.out_bf16 = B("qkv"); e.ld_bf16 = 3 * D_MODEL;
-        KOCR_TRY(gemm_linear(h, xb, M, w.in_w, 3 * D_MODEL, D_MODEL, e, s));
-        KOCR_TRY(launch_chunk_attention(B("qkv"), B("ao"), NC, s)); ++g_launches;
+        TIMED("enc_qkv", 2.0 * M * D_MODEL * 3 * D_MODEL, gemm_linear(h, xb, M, w.in_w, 3 * D_MODEL, D_MODEL, e, s));
+        TIMED("enc_attention", 2.0 * 2.0 * M * 32 * D_MODEL, launch_chunk_attention(B("qkv"), B("ao"), NC, s)); ++g_launches;
         e = ep_none();
         e.bias = w.out_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
-        KOCR_TRY(gemm_linear(h, B("ao"), M, w.out_w, D_MODEL, D_MODEL, e, s));
-        KOCR_TRY(launch_layernorm(y, w.n1_g, w.n1_b, nullptr, nullptr, x, xb, nullptr, (int)M, s)); ++g_launches;
+        TIMED("enc_out_proj", 2.0 * M * D_MODEL * D_MODEL, gemm_linear(h, B("ao"), M, w.out_w, D_MODEL, D_MODEL, e, s));
+        TIMED("enc_layernorm", 0, launch_layernorm(y, w.n1_g, w.n1_b, nullptr, nullptr, x, xb, nullptr, (int)M, s)); ++g_launches;
         e = ep_none();
         e.bias = w.l1_b; e.relu = 1; e.out_bf16 = B("hff"); e.ld_bf16 = 1024;
-        KOCR_TRY(gemm_linear(h, xb, M, w.l1_w, 1024, D_MODEL, e, s));
+        TIMED("enc_ffn1", 2.0 * M * D_MODEL * 1024, gemm_linear(h, xb, M, w.l1_w, 1024, D_MODEL, e, s));
         e = ep_none();
         e.bias = w.l2_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
-        KOCR_TRY(gemm_linear(h, B("hff"), M, w.l2_w, D_MODEL, 1024, e, s));
+        TIMED("enc_ffn2", 2.0 * M * D_MODEL * 1024, gemm_linear(h, B("hff"), M, w.l2_w, D_MODEL, 1024, e, s));
         // last layer: fuse the merge's "+ global_pos[t]" (predictor.py:178-183) into the LayerNorm
         const bool last = l == 1;
-        KOCR_TRY(launch_layernorm(y, w.n2_g, w.n2_b, last ? h->global_pos : nullptr, last ? h->d_row_pos : nullptr, x,
+        TIMED("enc_layernorm", 0, launch_layernorm(y, w.n2_g, w.n2_b, last ? h->global_pos : nullptr, last ? h->d_row_pos : nullptr, x,
                                   xb, nullptr, (int)M, s)); ++g_launches;
     }
     return 0;
@@ -318,8 +356,8 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
     if (h->variant == 0) {
         GemmEpilogue e = ep_none();
         e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
-        KOCR_TRY(gemm_linear(h, buf<__nv_bfloat16>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
-        KOCR_TRY(launch_bilstm(buf<float>(h, "gin"), h->lstm_w_hh, h->d_line_tok_off, h->d_line_T, h->d_groups,
+        TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, buf<__nv_bfloat16>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
+        TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm(buf<float>(h, "gin"), h->lstm_w_hh, h->d_line_tok_off, h->d_line_T, h->d_groups,
                                h->n_groups, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
         ++g_launches;
         memb = buf<__nv_bfloat16>(h, "memb");
@@ -327,18 +365,21 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
     // cross-attention K/V of both decoder layers, once per line (depends only on the memory)
     GemmEpilogue e = ep_none();
     e.bias = h->dec_kv_b; e.out_bf16 = buf<__nv_bfloat16>(h, "kv"); e.ld_bf16 = 4 * D_MODEL;
-    KOCR_TRY(gemm_linear(h, memb, M, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
+    TIMED("cross_kv_proj", 2.0 * M * D_MODEL * 4 * D_MODEL, gemm_linear(h, memb, M, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
     return 0;
 }
 
-int decode_step(kocr_handle* h, int t, cudaStream_t s) {
+// One generated position for every line of the batch; the position is *step_base + off (device side).
+int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     const int L = h->n_lines;
     const int D = D_MODEL;
     int* tokens = buf<int>(h, "tokens");
+    const int* sb = buf<int>(h, "step_base");
+    const int* fin = buf<int>(h, "finished");
     float* dx = buf<float>(h, "dx"); float* dy = buf<float>(h, "dy");
     __nv_bfloat16* dxb = buf<__nv_bfloat16>(h, "dxb");
     __nv_bfloat16* dao = buf<__nv_bfloat16>(h, "dao");
-    KOCR_TRY(launch_dec_embed(tokens, t, h->dec_tok_emb, h->dec_pos, dx, dxb, nullptr, L, s)); ++g_launches;
+    KOCR_TRY(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxb, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         float* kc = buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
@@ -346,7 +387,7 @@ int decode_step(kocr_handle* h, int t, cudaStream_t s) {
         GemmEpilogue e = ep_none();
         e.bias = w.sa_in_b; e.out_f32 = buf<float>(h, "dqkv"); e.ld_f32 = 3 * D;
         KOCR_TRY(gemm_linear(h, dxb, L, w.sa_in_w, 3 * D, D, e, s));
-        KOCR_TRY(launch_dec_self_attn(buf<float>(h, "dqkv"), kc, vc, tokens, t, dao, nullptr, L, s)); ++g_launches;
+        KOCR_TRY(launch_dec_self_attn(buf<float>(h, "dqkv"), kc, vc, tokens, sb, off, fin, dao, nullptr, L, s)); ++g_launches;
         e = ep_none();
         e.bias = w.sa_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
         KOCR_TRY(gemm_linear(h, dao, L, w.sa_out_w, D, D, e, s));
@@ -355,7 +396,7 @@ int decode_step(kocr_handle* h, int t, cudaStream_t s) {
         e.bias = w.ca_q_b; e.out_f32 = buf<float>(h, "dq"); e.ld_f32 = D;
         KOCR_TRY(gemm_linear(h, dxb, L, w.ca_q_w, D, D, e, s));
         KOCR_TRY(launch_dec_cross_attn(buf<float>(h, "dq"), buf<__nv_bfloat16>(h, "kv"), l, h->d_line_tok_off,
-                                       h->d_line_T, h->max_T, dao, nullptr, L, s)); ++g_launches;
+                                       h->d_line_T, max_T, fin, dao, nullptr, L, s)); ++g_launches;
         e = ep_none();
         e.bias = w.ca_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
         KOCR_TRY(gemm_linear(h, dao, L, w.ca_out_w, D, D, e, s));
@@ -371,18 +412,48 @@ int decode_step(kocr_handle* h, int t, cudaStream_t s) {
     GemmEpilogue e = ep_none();
     e.bias = h->dec_out_b; e.out_f32 = buf<float>(h, "logits"); e.ld_f32 = VOCAB_PAD;
     KOCR_TRY(gemm_linear(h, dxb, L, h->dec_out_w, VOCAB_PAD, D, e, s));
-    if (h->trace_logits) {
-        KOCR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
-                                    (size_t)DEC_MAX * VOCAB_PAD * 4, buf<float>(h, "logits"), VOCAB_PAD * 4,
-                                    VOCAB_PAD * 4, L, cudaMemcpyDeviceToDevice, s));
-    }
+    const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
+    float* trace = h->trace_logits ? reinterpret_cast<float*>(h->trace.p) : nullptr;
     KOCR_TRY(launch_dec_argmax(buf<float>(h, "logits"), tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"),
-                               buf<int>(h, "n_active"), t, L, s)); ++g_launches;
-    if (h->force_tokens && h->have_forced && t + 1 < KOCR_TOKENS_LD) {
-        // teacher forcing: overwrite the freshly chosen ids of column t+1 with the caller's
-        KOCR_CUDA(cudaMemcpy2DAsync(tokens + t + 1, KOCR_TOKENS_LD * 4, buf<int>(h, "forced") + t + 1,
-                                    KOCR_TOKENS_LD * 4, 4, L, cudaMemcpyDeviceToDevice, s));
+                               buf<int>(h, "n_active"), sb, off, L, forced, trace, s)); ++g_launches;
+    return 0;
+}
+
+static const int DEC_GROUP = 8;     // positions per captured graph / per early-exit poll
+
+// `n` consecutive positions followed by the step_base bump, eagerly on stream s.
+int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
+    for (int i = 0; i < n; ++i) KOCR_TRY(decode_step(h, i, max_T, s));
+    KOCR_TRY(launch_dec_bump(buf<int>(h, "step_base"), n, s)); ++g_launches;
+    return 0;
+}
+
+// The same 8 positions as one CUDA graph (captured once per (n_lines, max_T bucket, options)).
+int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
+    auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits, (h->force_tokens && h->have_forced) ? 1 : 0);
+    auto it = h->dec_graphs.find(key);
+    if (it == h->dec_graphs.end()) {
+        const int64_t before = g_launches + gemm_tc_launch_count();
+        cudaGraph_t graph = nullptr;
+        KOCR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_group_eager(h, DEC_GROUP, max_T, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        KOCR_CHECK(ce == cudaSuccess && graph != nullptr, "decode graph capture failed: %s", cudaGetErrorString(ce));
+        kocr_handle::DecGraph g;
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        KOCR_CHECK(ce == cudaSuccess, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        g.nodes = (size_t)(g_launches + gemm_tc_launch_count() - before);
+        g_launches -= (int64_t)g.nodes;      // captured, not launched: counted per replay below
+        if (h->dec_graphs.size() > 64) {
+            for (auto& d : h->dec_graphs) cudaGraphExecDestroy(d.second.exec);
+            h->dec_graphs.clear();
+        }
+        it = h->dec_graphs.emplace(key, g).first;
     }
+    KOCR_CUDA(cudaGraphLaunch(it->second.exec, s));
+    g_launches += (int64_t)it->second.nodes;
     return 0;
 }
 
@@ -462,6 +533,10 @@ int kocr_destroy(kocr_handle* h) {
     if (h->staging_dev) cudaFree(h->staging_dev);
     if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
     if (h->staging_done) cudaEventDestroy(h->staging_done);
+    for (auto& g : h->dec_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -487,7 +562,7 @@ int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes
     KOCR_CHECK(h != nullptr, "kocr_gather_chunks: null handle");
     KOCR_CHECK(n_lines >= 0 && n_lines <= h->max_lines, "kocr_gather_chunks: %d lines exceed capacity %d", n_lines,
                h->max_lines);
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
     KOCR_CUDA(cudaSetDevice(h->device));
     h->n_lines = n_lines; h->n_chunks = 0; h->n_tok = 0; h->max_T = 0; h->n_groups = 0; h->max_new_w = 0;
     h->line_T.assign(n_lines, 0); h->line_first_chunk.assign(n_lines, 0); h->line_n_chunks.assign(n_lines, 0);
@@ -575,19 +650,19 @@ int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes
 int kocr_sevgg_encoder_forward(kocr_handle* h, void* stream) {
     KOCR_CHECK(h != nullptr, "kocr_sevgg_encoder_forward: null handle");
     KOCR_CUDA(cudaSetDevice(h->device));
-    return stage_cnn_encoder(h, reinterpret_cast<cudaStream_t>(stream));
+    return stage_cnn_encoder(h, stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream);
 }
 
 int kocr_merge_bilstm_forward(kocr_handle* h, void* stream) {
     KOCR_CHECK(h != nullptr, "kocr_merge_bilstm_forward: null handle");
     KOCR_CUDA(cudaSetDevice(h->device));
-    return stage_memory(h, reinterpret_cast<cudaStream_t>(stream));
+    return stage_memory(h, stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream);
 }
 
 int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream) {
     KOCR_CHECK(h != nullptr, "kocr_decode_greedy: null handle");
     KOCR_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
     const int L = h->n_lines;
     if (L == 0) return 0;
     if (max_steps <= 0 || max_steps > h->dec_max_len) max_steps = h->dec_max_len;
@@ -595,6 +670,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
     KOCR_CUDA(cudaMemsetAsync(tokens, 0, (size_t)L * KOCR_TOKENS_LD * 4, s));
     KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "finished"), 0, (size_t)L * 4, s));
     KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "n_active"), 0, (DEC_MAX + 1) * 4, s));
+    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "step_base"), 0, 64, s));
     {   // tokens[:, 0] = <sos> (2), lengths = 1
         std::vector<int32_t> init((size_t)L, 2), ones((size_t)L, 1);
         KOCR_CUDA(cudaMemcpy2DAsync(tokens, KOCR_TOKENS_LD * 4, init.data(), 4, 4, L, cudaMemcpyHostToDevice, s));
@@ -605,17 +681,23 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         KOCR_TRY(ensure(h->trace, (size_t)h->max_lines * DEC_MAX * VOCAB_PAD * 4));
         KOCR_CUDA(cudaMemsetAsync(h->trace.p, 0, (size_t)L * DEC_MAX * VOCAB_PAD * 4, s));
     }
-    int t = 0;
-    const int check_every = 8;
-    for (; t < max_steps; ++t) {
-        KOCR_TRY(decode_step(h, t, s));
-        if (!h->force_tokens && (t + 1) % check_every == 0 && t + 1 < max_steps) {
-            KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + t, 4, cudaMemcpyDeviceToHost, s));
+    const bool forcing = h->force_tokens && h->have_forced;
+    const int max_T = (h->max_T + 127) / 128 * 128;      // bucketed: only sizes the cross-attention scratch
+    int done = 0;
+    while (done < max_steps) {
+        const int n = std::min(DEC_GROUP, max_steps - done);
+        // the first group of a process runs eagerly (it sets the kernels' function attributes)
+        if (n == DEC_GROUP && h->use_graphs && h->decode_warmed) KOCR_TRY(decode_group_graph(h, max_T, s));
+        else KOCR_TRY(decode_group_eager(h, n, max_T, s));
+        h->decode_warmed = true;
+        done += n;
+        if (!forcing && done < max_steps) {
+            KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
             KOCR_CUDA(cudaStreamSynchronize(s));
-            if (*h->pinned_flag == 0) { ++t; break; }
+            if (*h->pinned_flag == 0) break;     // every line has emitted <eos>
         }
     }
-    h->last_steps = t;
+    h->last_steps = done;
     if (tokens_out) KOCR_CUDA(cudaMemcpyAsync(tokens_out, tokens, (size_t)L * KOCR_TOKENS_LD * 4, cudaMemcpyDeviceToHost, s));
     if (lengths_out) KOCR_CUDA(cudaMemcpyAsync(lengths_out, buf<int>(h, "lengths"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(cudaStreamSynchronize(s));
@@ -636,6 +718,12 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     KOCR_CHECK(h != nullptr && name != nullptr, "kocr_set_option: null argument");
     if (strcmp(name, "trace_logits") == 0) { h->trace_logits = value; return 0; }
     if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
+    if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
+    if (strcmp(name, "kernel_timing") == 0) {
+        h->kernel_timing = value;
+        if (value) { h->sites.clear(); }
+        return 0;
+    }
     KOCR_CHECK(false, "kocr_set_option: unknown option '%s'", name);
     return 0;
 }
@@ -646,6 +734,27 @@ int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens, int n_lines) {
     KOCR_CUDA(cudaSetDevice(h->device));
     KOCR_CUDA(cudaMemcpy(buf<int>(h, "forced"), tokens, (size_t)n_lines * KOCR_TOKENS_LD * 4, cudaMemcpyHostToDevice));
     h->have_forced = true;
+    return 0;
+}
+
+int kocr_read_kernel_timing(kocr_handle* h, char* text_out, size_t cap) {
+    KOCR_CHECK(h != nullptr && text_out != nullptr && cap > 0, "kocr_read_kernel_timing: null argument");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    KOCR_CUDA(cudaDeviceSynchronize());
+    for (auto& p : h->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { h->sites[p.site].ms += ms; h->sites[p.site].count += 1; }
+        h->event_pool.push_back(p.a); h->event_pool.push_back(p.b);
+    }
+    h->pending.clear();
+    std::string out;
+    char line[256];
+    for (auto& st : h->sites) {
+        snprintf(line, sizeof line, "%s %.6f %d %.1f\n", st.name.c_str(), st.ms, st.count, st.flops);
+        out += line;
+    }
+    KOCR_CHECK(out.size() + 1 <= cap, "kocr_read_kernel_timing: buffer too small");
+    memcpy(text_out, out.c_str(), out.size() + 1);
     return 0;
 }
 

@@ -316,12 +316,14 @@ int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* 
 // ------------------------------------------------------------------------------------------
 static constexpr int TOK_LD = DEC_MAX + 1;
 
-__global__ void dec_embed_kernel(const int* __restrict__ tokens, int t, const float* __restrict__ tok_emb,
+__global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_base, int step_off,
+                                 const float* __restrict__ tok_emb,
                                  const float* __restrict__ pos_emb, float* __restrict__ x,
                                  __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xb_lo, int n_lines) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // n_lines * 96 float4
     if (idx >= n_lines * (D_MODEL / 4)) return;
     const int l = idx / (D_MODEL / 4), c4 = idx - l * (D_MODEL / 4);
+    const int t = *step_base + step_off;
     const int tok = tokens[l * TOK_LD + t];
     const float4 e = reinterpret_cast<const float4*>(tok_emb + (long)tok * D_MODEL)[c4];
     const float4 p = reinterpret_cast<const float4*>(pos_emb + (long)t * D_MODEL)[c4];
@@ -334,10 +336,12 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, int t, const fl
                                                           pack_bf16(v.z - bf16_lo(p1), v.w - bf16_hi(p1)));
 }
 
-int launch_dec_embed(const int* tokens, int t, const float* tok_emb, const float* pos_emb, float* x,
-                     __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines, cudaStream_t stream) {
+int launch_dec_embed(const int* tokens, const int* step_base, int step_off, const float* tok_emb,
+                     const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
+                     cudaStream_t stream) {
     const int total = n_lines * (D_MODEL / 4);
-    dec_embed_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tokens, t, tok_emb, pos_emb, x, xb, xb_lo, n_lines);
+    dec_embed_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tokens, step_base, step_off, tok_emb, pos_emb, x, xb,
+                                                              xb_lo, n_lines);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -352,11 +356,15 @@ __device__ __forceinline__ void store_attn_out(float o, long idx, __nv_bfloat16*
 // <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.
 __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
                                                             float* __restrict__ vcache, const int* __restrict__ tokens,
-                                                            int t, __nv_bfloat16* __restrict__ out,
+                                                            const int* __restrict__ step_base, int step_off,
+                                                            const int* __restrict__ finished,
+                                                            __nv_bfloat16* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ out_lo) {
     __shared__ float s_q[D_MODEL];
     __shared__ float s_p[N_HEAD][DEC_MAX];
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (finished[l]) return;                      // line already emitted <eos>: nothing downstream reads it
+    const int t = *step_base + step_off;
     const float* row = qkv + (long)l * 3 * D_MODEL;
     float* kc = kcache + (long)l * DEC_MAX * D_MODEL;
     float* vc = vcache + (long)l * DEC_MAX * D_MODEL;
@@ -401,9 +409,11 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     }
 }
 
-int launch_dec_self_attn(const float* qkv, float* kcache, float* vcache, const int* tokens, int t,
-                         __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream) {
-    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, t, out, out_lo);
+int launch_dec_self_attn(const float* qkv, float* kcache, float* vcache, const int* tokens, const int* step_base,
+                         int step_off, const int* finished, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
+                         cudaStream_t stream) {
+    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, step_base, step_off, finished, out,
+                                                      out_lo);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -414,10 +424,12 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
                                                              const __nv_bfloat16* __restrict__ kv, int layer,
                                                              const int* __restrict__ line_tok_off,
                                                              const int* __restrict__ line_T, int max_T,
+                                                             const int* __restrict__ finished,
                                                              __nv_bfloat16* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out_lo) {
     extern __shared__ float s_dyn[];               // [8][max_T] scores, then [384] q
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (finished[l]) return;
     float* s_p = s_dyn + (long)warp * max_T;
     float* s_q = s_dyn + (long)N_HEAD * max_T;
     const int T = line_T[l];
@@ -473,34 +485,54 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 }
 
 int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
-                          const int* line_T, int max_T, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
-                          cudaStream_t stream) {
+                          const int* line_T, int max_T, const int* finished, __nv_bfloat16* out,
+                          __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream) {
     const size_t smem = ((size_t)N_HEAD * max_T + D_MODEL) * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-        KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
-        KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+    KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
+    static bool attr_set = false;
+    if (!attr_set) {     // once, outside any stream capture (the first decode group of a process runs eagerly)
+        KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
     }
-    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, out, out_lo);
+    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, finished, out,
+                                                          out_lo);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
 
-// argmax over the 124 real logits (ties -> lowest index, torch.argmax), greedy bookkeeping
-// (predictor.py:90-97): stop BEFORE appending <eos>.
-__global__ void dec_argmax_kernel(const float* __restrict__ logits, int* __restrict__ tokens,
-                                  int* __restrict__ lengths, int* __restrict__ finished, int* __restrict__ n_active,
-                                  int t, int n_lines) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+// argmax over the 124 real logits (ties -> lowest index, torch.argmax) and the greedy bookkeeping of
+// predictor.py:90-97 (stop BEFORE appending <eos>).  Warp per line.  Optional: copy the logits row into the
+// trace [n_lines, DEC_MAX, 128]; teacher forcing (the next id comes from `forced`, lines never finish).
+__global__ void __launch_bounds__(128) dec_argmax_kernel(const float* __restrict__ logits, int* __restrict__ tokens,
+                                                         int* __restrict__ lengths, int* __restrict__ finished,
+                                                         int* __restrict__ n_active, const int* __restrict__ step_base,
+                                                         int step_off, int n_lines, const int* __restrict__ forced,
+                                                         float* __restrict__ trace) {
+    const int l = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (l >= n_lines) return;
     if (finished[l]) return;
-    const float* lg = logits + (long)l * VOCAB_PAD;
-    float best = lg[0];
-    int bi = 0;
-    for (int i = 1; i < VOCAB; ++i) {
-        const float v = lg[i];
-        if (v > best) { best = v; bi = i; }
+    const int t = *step_base + step_off;
+    const float4 v4 = reinterpret_cast<const float4*>(logits + (long)l * VOCAB_PAD)[lane];
+    if (trace) reinterpret_cast<float4*>(trace + ((long)l * DEC_MAX + t) * VOCAB_PAD)[lane] = v4;
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = lane * 4 + j;
+        if (i < VOCAB && v[j] > best) { best = v[j]; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane != 0) return;
+    if (forced) {
+        tokens[l * TOK_LD + t + 1] = forced[l * TOK_LD + t + 1];
+        lengths[l] = t + 2;
+        return;
     }
     if (bi == 3) {                       // <eos>
         finished[l] = 1;
@@ -511,9 +543,18 @@ __global__ void dec_argmax_kernel(const float* __restrict__ logits, int* __restr
     }
 }
 
-int launch_dec_argmax(const float* logits, int* tokens, int* lengths, int* finished, int* n_active, int t,
-                      int n_lines, cudaStream_t stream) {
-    dec_argmax_kernel<<<(n_lines + 127) / 128, 128, 0, stream>>>(logits, tokens, lengths, finished, n_active, t, n_lines);
+int launch_dec_argmax(const float* logits, int* tokens, int* lengths, int* finished, int* n_active,
+                      const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
+                      cudaStream_t stream) {
+    dec_argmax_kernel<<<(n_lines + 3) / 4, 128, 0, stream>>>(logits, tokens, lengths, finished, n_active, step_base,
+                                                             step_off, n_lines, forced, trace);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void dec_bump_kernel(int* step_base, int n) { *step_base += n; }
+int launch_dec_bump(int* step_base, int n, cudaStream_t stream) {
+    dec_bump_kernel<<<1, 1, 0, stream>>>(step_base, n);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }

@@ -8,7 +8,7 @@ from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict, load_checkpoint
 
 n_lines = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-ck = Path(__file__).resolve().parent.parent / "tests/golden/fixture_se_ckpt.npz"
+ck = Path(__file__).resolve().parent.parent / ("tmp_ckpt.npz" if "--tmp" in sys.argv else "tests/golden/fixture_se_ckpt.npz")
 sd = load_checkpoint(ck) if ck.exists() and "--seeded" not in sys.argv else seeded_state_dict("se", 0, max_global_len=1024)
 rec = _native.Recognizer(weights.pack_blob(sd), max_lines=n_lines, max_chunks=n_lines * 12)
 imgs, _ = synth.make_lines(n_lines, 400, 800, seed=0)
