@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--in-flight", type=int, default=4,
+                    help="batches in flight per GPU (one handle + stream + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -172,16 +174,38 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     sd, wname = load_state_dict()
-    imgs = make_batch(rank)
-    batch = _native.LineBatch(imgs)
-    rec = _native.Recognizer(weights.pack_blob(sd), device=local_rank, max_lines=LINES_PER_STEP,
-                             max_chunks=LINES_PER_STEP * 11)
-    pix_host = torch.from_numpy(batch.pixels).pin_memory()
-    pix_dev = pix_host.cuda()
-    tok_host = torch.zeros((LINES_PER_STEP, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
-    len_host = torch.zeros(LINES_PER_STEP, dtype=torch.int32).pin_memory()
-    tok_np, len_np = tok_host.numpy(), len_host.numpy()
-    n_chunks = int(rec.gather_chunks(batch, pixels_dev_ptr=pix_dev.data_ptr()).sum())
+    blob = weights.pack_blob(sd)
+    S = max(1, args.in_flight)
+
+    class Worker:
+        """One in-flight batch: its own handle (weights + workspace + stream), its own pinned buffers."""
+
+        def __init__(self, w):
+            self.imgs = make_batch(rank * 64 + w)           # rank 0 / worker 0 == the parity-test batch (seed 0)
+            self.batch = _native.LineBatch(self.imgs)
+            self.rec = _native.Recognizer(blob, device=local_rank, max_lines=LINES_PER_STEP,
+                                          max_chunks=LINES_PER_STEP * 11)
+            self.pix_host = torch.from_numpy(self.batch.pixels).pin_memory()
+            self.pix_dev = self.pix_host.cuda()
+            self.tok_host = torch.zeros((LINES_PER_STEP, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
+            self.len_host = torch.zeros(LINES_PER_STEP, dtype=torch.int32).pin_memory()
+            self.tok_np, self.len_np = self.tok_host.numpy(), self.len_host.numpy()
+            self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
+            self.batch_host.__dict__.update(self.batch.__dict__)
+            self.batch_host.pixels = self.pix_host.numpy()
+            self.n_chunks = int(self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr()).sum())
+
+        def step_resident(self):
+            self.rec.recognize_lines(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr(), tokens_out=self.tok_np,
+                                     lengths_out=self.len_np)
+
+        def step_e2e(self):       # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
+            self.rec.recognize_lines(self.batch_host, tokens_out=self.tok_np, lengths_out=self.len_np)
+
+    workers = [Worker(w) for w in range(S)]
+    n_chunks = workers[0].n_chunks
+    batch = workers[0].batch
+    rec = workers[0].rec
 
     def barrier():
         torch.cuda.synchronize()
@@ -189,53 +213,79 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        rec.recognize_lines(batch, pixels_dev_ptr=pix_dev.data_ptr(), tokens_out=tok_np, lengths_out=len_np)
+    def run_steps(kind, steps):
+        """`steps` passes over a 256-line batch, at most S in flight (one host thread per in-flight batch)."""
+        counter = {"next": 0}
+        lock = threading.Lock()
+        errors = []
 
-    batch_host = _native.LineBatch.__new__(_native.LineBatch)
-    batch_host.__dict__.update(batch.__dict__)
-    batch_host.pixels = pix_host.numpy()
+        def loop(wk):
+            try:
+                torch.cuda.set_device(local_rank)
+                fn = wk.step_resident if kind == "resident" else wk.step_e2e
+                while True:
+                    with lock:
+                        i = counter["next"]
+                        if i >= steps:
+                            return
+                        counter["next"] = i + 1
+                    fn()
+            except Exception as e:  # surface worker failures instead of hanging
+                errors.append(e)
+
+        threads = [threading.Thread(target=loop, args=(wk,)) for wk in workers[:min(S, steps)]]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
     gathered = [torch.zeros((LINES_PER_STEP, _native.TOKENS_LD), dtype=torch.int32, device="cuda")
                 for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    def step_e2e():
-        rec.recognize_lines(batch_host, tokens_out=tok_np, lengths_out=len_np)      # H2D pixels ... D2H ids
-        if world > 1:       # the only collective: decoded ids to rank 0 (NCCL gather over NVLink)
-            dist.gather(tok_host.cuda(non_blocking=True), gathered, dst=0)
-
-    def timed(fn, steps):
+    def timed(kind, steps):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         a.record()
-        for _ in range(steps):
-            fn()
+        run_steps(kind, steps)
+        if world > 1 and kind == "e2e":   # the only collective: decoded ids to rank 0 (NCCL gather over NVLink)
+            dist.gather(workers[0].tok_host.cuda(non_blocking=True), gathered, dst=0)
         b.record()
         barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
         ms = torch.tensor([a.elapsed_time(b)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), wall_ms
 
-    for _ in range(args.warmup):
-        step_resident()
-    for _ in range(args.warmup):
-        step_e2e()
+    run_steps("resident", max(args.warmup, S))
+    run_steps("e2e", max(args.warmup, S))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = _native.launch_count()
-    ms_res = timed(step_resident, args.steps)
+    ms_res, wall_res = timed("resident", args.steps)
     launches = _native.launch_count() - launches0
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, wall_e2e = timed("e2e", args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    mean_len = float(len_np.mean())
+    mean_len = float(np.mean([wk.len_np.mean() for wk in workers]))
     decode_steps = int(rec.debug_read("last_steps"))
 
-    # ---- instrumented pass: CUDA events around every launch of stages 2-5a (roofline evidence)
+    # ---- single in-flight latency of one step (for context)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        workers[0].step_e2e()
+    lat_ms = (time.perf_counter() - t0) * 1e3 / 3
+
+    # ---- instrumented pass: CUDA events around every launch of stages 2-5a (roofline evidence),
+    #      one batch in flight so that the per-launch times are not perturbed by other streams
     rec.set_option("kernel_timing", 1)
     for _ in range(args.steps):
-        step_resident()
+        workers[0].step_resident()
     kt = rec.kernel_timing()
     rec.set_option("kernel_timing", 0)
     peaks = load_peaks()
@@ -258,7 +308,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1:
-        v, dt = cpu_oracle_lines_per_s(sd, imgs, args.cpu_lines)
+        v, dt = cpu_oracle_lines_per_s(sd, workers[0].imgs, args.cpu_lines)
         cpu = {"value": v, "unit": "lines/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"first {args.cpu_lines} lines of the c2 batch through the numpy oracle ({dt:.1f} s)"}
 
@@ -270,12 +320,13 @@ def main():
             "config": {"workload": f"c2: {LINES_PER_STEP} synthetic Khmer text lines per GPU, resized width "
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
-                       "mean_decoded_len": mean_len, "decode_steps": decode_steps,
+                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S,
+                       "single_in_flight_e2e_ms_per_step": lat_ms, "wall_ms_resident": wall_res, "wall_ms_e2e": wall_e2e,
                        "l2": "per-step working set (~1.6 MB of activations per chunk, >3 GB per step) exceeds the 126 MB L2",
                        "parallelism": f"lines sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e, "unit": "lines/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(batch.pixel_bytes) * world,
-                    "d2h_bytes_per_step": int(tok_host.numel() * 4 + len_host.numel() * 4) * world},
+                    "d2h_bytes_per_step": int(LINES_PER_STEP * (_native.TOKENS_LD + 1) * 4) * world},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256> @ conv6 (implicit GEMM, M=chunks*182, N=512, K=4608)",
@@ -292,7 +343,8 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    rec.close()
+    for wk in workers:
+        wk.rec.close()
     if world > 1:
         dist.destroy_process_group()
 

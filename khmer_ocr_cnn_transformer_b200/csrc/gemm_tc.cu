@@ -6,6 +6,7 @@
 // Accumulators: 2 stages x BN fp32 columns in TMEM so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Operands: NSTAGE-deep ring of {A 16 KB, B BN*128 B} in shared memory.
 #include "gemm_tc.cuh"
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -289,8 +290,8 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t 
     return 0;
 }
 
-static long g_gemm_launches = 0;
-long gemm_tc_launch_count() { return g_gemm_launches; }
+static std::atomic<long> g_gemm_launches{0};
+long gemm_tc_launch_count() { return g_gemm_launches.load(); }
 
 static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     KOCR_CHECK(p.cin % BK == 0, "gemm: cin %d not a multiple of %d", p.cin, BK);

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <map>
@@ -23,7 +24,7 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-static int64_t g_launches = 0;     // non-GEMM kernel launches (GEMM launches are counted in gemm_tc.cu)
+static std::atomic<int64_t> g_launches{0};     // non-GEMM kernel launches (GEMM launches are counted in gemm_tc.cu)
 
 // ---- packed weight blob ---------------------------------------------------------------
 struct BlobHeader { char magic[8]; uint32_t n_entries; uint32_t reserved; };
@@ -213,7 +214,7 @@ int carve_workspace(kocr_handle* h) {
         {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4}, {"step_base", 64},
         {"dx", L * D * 4}, {"dxb", L * D * 2}, {"dqkv", L * 3 * D * 4}, {"dao", L * D * 2}, {"dy", L * D * 4},
         {"dq", L * D * 4}, {"dh", L * 4 * D * 2}, {"logits", L * VOCAB_PAD * 4},
-        {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
+        {"kcache", 2 * L * DEC_MAX * D * 2}, {"vcache", 2 * L * DEC_MAX * D * 2},
     };
     size_t total = 0;
     for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -382,8 +383,8 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     KOCR_TRY(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxb, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
-        float* kc = buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        float* vc = buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        __nv_bfloat16* kc = buf<__nv_bfloat16>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        __nv_bfloat16* vc = buf<__nv_bfloat16>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         GemmEpilogue e = ep_none();
         e.bias = w.sa_in_b; e.out_f32 = buf<float>(h, "dqkv"); e.ld_f32 = 3 * D;
         KOCR_TRY(gemm_linear(h, dxb, L, w.sa_in_w, 3 * D, D, e, s));
@@ -433,7 +434,7 @@ int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
     auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
-        const int64_t before = g_launches + gemm_tc_launch_count();
+        const int64_t before = g_launches.load() + gemm_tc_launch_count();
         cudaGraph_t graph = nullptr;
         KOCR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         int rc = decode_group_eager(h, DEC_GROUP, max_T, s);
@@ -444,7 +445,7 @@ int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
         ce = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         KOCR_CHECK(ce == cudaSuccess, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-        g.nodes = (size_t)(g_launches + gemm_tc_launch_count() - before);
+        g.nodes = (size_t)(g_launches.load() + gemm_tc_launch_count() - before);
         g_launches -= (int64_t)g.nodes;      // captured, not launched: counted per replay below
         if (h->dec_graphs.size() > 64) {
             for (auto& d : h->dec_graphs) cudaGraphExecDestroy(d.second.exec);
@@ -466,7 +467,7 @@ extern "C" {
 
 int kocr_abi_version(void) { return KOCR_ABI_VERSION; }
 const char* kocr_last_error(void) { return get_error(); }
-int64_t kocr_launch_count(void) { return g_launches + gemm_tc_launch_count(); }
+int64_t kocr_launch_count(void) { return g_launches.load() + gemm_tc_launch_count(); }
 
 int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_lines, int max_chunks,
                 kocr_handle** out) {

@@ -354,8 +354,10 @@ __device__ __forceinline__ void store_attn_out(float o, long idx, __nv_bfloat16*
 
 // Causal self-attention for the newest position t against the cache (keys 0..t); keys whose token is
 // <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.
-__global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
-                                                            float* __restrict__ vcache, const int* __restrict__ tokens,
+__global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ kcache,
+                                                            __nv_bfloat16* __restrict__ vcache,
+                                                            const int* __restrict__ tokens,
                                                             const int* __restrict__ step_base, int step_off,
                                                             const int* __restrict__ finished,
                                                             __nv_bfloat16* __restrict__ out,
@@ -366,12 +368,12 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     if (finished[l]) return;                      // line already emitted <eos>: nothing downstream reads it
     const int t = *step_base + step_off;
     const float* row = qkv + (long)l * 3 * D_MODEL;
-    float* kc = kcache + (long)l * DEC_MAX * D_MODEL;
-    float* vc = vcache + (long)l * DEC_MAX * D_MODEL;
+    __nv_bfloat16* kc = kcache + (long)l * DEC_MAX * D_MODEL;
+    __nv_bfloat16* vc = vcache + (long)l * DEC_MAX * D_MODEL;
     for (int i = tid; i < D_MODEL; i += blockDim.x) {
         s_q[i] = row[i] * rsqrtf((float)HEAD_DIM);
-        kc[(long)t * D_MODEL + i] = row[D_MODEL + i];
-        vc[(long)t * D_MODEL + i] = row[2 * D_MODEL + i];
+        kc[(long)t * D_MODEL + i] = __float2bfloat16_rn(row[D_MODEL + i]);
+        vc[(long)t * D_MODEL + i] = __float2bfloat16_rn(row[2 * D_MODEL + i]);
     }
     __syncthreads();
     const int nk = t + 1;
@@ -380,13 +382,15 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     for (int j = lane; j < nk; j += 32) {
         float acc = -INFINITY;
         if (tokens[l * TOK_LD + j] != 0) {
-            const float4* kp = reinterpret_cast<const float4*>(kc + (long)j * D_MODEL + warp * HEAD_DIM);
+            const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)j * D_MODEL + warp * HEAD_DIM);
             acc = 0.f;
 #pragma unroll
-            for (int d = 0; d < HEAD_DIM / 4; ++d) {
-                const float4 k4 = kp[d];
-                acc = fmaf(qh[4 * d], k4.x, acc); acc = fmaf(qh[4 * d + 1], k4.y, acc);
-                acc = fmaf(qh[4 * d + 2], k4.z, acc); acc = fmaf(qh[4 * d + 3], k4.w, acc);
+            for (int i = 0; i < HEAD_DIM / 8; ++i) {
+                const uint4 k8 = kp[i];
+                acc = fmaf(qh[8 * i], bf16_lo(k8.x), acc); acc = fmaf(qh[8 * i + 1], bf16_hi(k8.x), acc);
+                acc = fmaf(qh[8 * i + 2], bf16_lo(k8.y), acc); acc = fmaf(qh[8 * i + 3], bf16_hi(k8.y), acc);
+                acc = fmaf(qh[8 * i + 4], bf16_lo(k8.z), acc); acc = fmaf(qh[8 * i + 5], bf16_hi(k8.z), acc);
+                acc = fmaf(qh[8 * i + 6], bf16_lo(k8.w), acc); acc = fmaf(qh[8 * i + 7], bf16_hi(k8.w), acc);
             }
         }
         s_p[warp][j] = acc;
@@ -402,14 +406,22 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = 1.f / sum;
-    for (int d = lane; d < HEAD_DIM; d += 32) {
-        float o = 0.f;
-        for (int j = 0; j < nk; ++j) o = fmaf(s_p[warp][j], vc[(long)j * D_MODEL + warp * HEAD_DIM + d], o);
-        store_attn_out(o * inv, (long)l * D_MODEL + warp * HEAD_DIM + d, out, out_lo);
+    if (lane < HEAD_DIM / 2) {           // lanes 0..23 own one bf16 pair of the 48 head dims
+        float o0 = 0.f, o1 = 0.f;
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(vc + warp * HEAD_DIM) + lane;
+        for (int j = 0; j < nk; ++j) {
+            const uint32_t v2 = vp[(long)j * (D_MODEL / 2)];
+            o0 = fmaf(s_p[warp][j], bf16_lo(v2), o0);
+            o1 = fmaf(s_p[warp][j], bf16_hi(v2), o1);
+        }
+        const long oi = (long)l * D_MODEL + warp * HEAD_DIM + 2 * lane;
+        store_attn_out(o0 * inv, oi, out, out_lo);
+        store_attn_out(o1 * inv, oi + 1, out, out_lo);
     }
 }
 
-int launch_dec_self_attn(const float* qkv, float* kcache, float* vcache, const int* tokens, const int* step_base,
+int launch_dec_self_attn(const float* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* tokens,
+                         const int* step_base,
                          int step_off, const int* finished, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
                          cudaStream_t stream) {
     dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, step_base, step_off, finished, out,
