@@ -126,150 +126,131 @@ int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, in
 }
 
 // ------------------------------------------------------------------------------------------
-// SE gate + pooling.  One CTA (256 threads) per chunk; smem: gate/mean [W][C] f32 + z [W][R].
-// FINAL == false: out = padded-linear (H/2, W, C) of gate * max over row pairs.
-// FINAL == true : out = [n*32 + k][kh*C + c] = adaptive average over (rows kh..kh+1, column bin k).
+// 1D-SE (SequenceSE, se_model.py:8-30).  The squeeze (mean over H) and the gated pooling are
+// HBM-bound elementwise kernels; the two 1x1 Conv1d layers of the excitation are real contractions
+// over channels and run on the tcgen05 GEMM (reduced width padded to 128), see kocr_api.cu.
 // ------------------------------------------------------------------------------------------
-template <bool FINAL>
-__global__ void __launch_bounds__(256) se_pool_kernel(const __nv_bfloat16* __restrict__ in,
-                                                      __nv_bfloat16* __restrict__ out, int H, int W, int C,
-                                                      SEWeights se, int use_se) {
-    extern __shared__ float s_dyn[];
-    float* s_gate = s_dyn;                 // [W][C]   (column means first, then the gate)
-    float* s_z = s_dyn + W * C;            // [W][R]
-    const int n = blockIdx.x;
+// squeeze: padded-linear (H, W, C) bf16 -> column means [n*W + w][C] bf16.  Thread per (n, w, 8 channels).
+__global__ void __launch_bounds__(256) se_col_mean_kernel(const __nv_bfloat16* __restrict__ in,
+                                                          __nv_bfloat16* __restrict__ means, long total, int H,
+                                                          int W, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
     const PLGeom gi = make_pl(H, W);
-    const __nv_bfloat16* src = in + (long)n * gi.S * C;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (use_se) {
-        // (1) squeeze: mean over H per (column, channel)            se_model.py:23
-        const int cp = C / 2;
-        for (int it = tid; it < W * cp; it += blockDim.x) {
-            const int w = it / cp, c2 = it - w * cp;
-            float s0 = 0.f, s1 = 0.f;
-            for (int h = 0; h < H; ++h) {
-                const uint32_t v = reinterpret_cast<const uint32_t*>(src + ((long)h * gi.P + w) * C)[c2];
-                s0 += bf16_lo(v); s1 += bf16_hi(v);
-            }
-            s_gate[w * C + 2 * c2] = s0 / (float)H;
-            s_gate[w * C + 2 * c2 + 1] = s1 / (float)H;
-        }
-        __syncthreads();
-        // (2) excite FC1 + ReLU: warp owns reduced channel r, weights in registers, shuffle-reduce
-        const int R = se.R;
-        for (int r = warp; r < R; r += 8) {
-            float wr[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) wr[j] = (lane + 32 * j) < C ? se.w0[(long)r * C + lane + 32 * j] : 0.f;
-            const float br = se.b0[r];
-            for (int w = 0; w < W; ++w) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (lane + 32 * j < C) acc = fmaf(wr[j], s_gate[w * C + lane + 32 * j], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) s_z[w * R + r] = fmaxf(acc + br, 0.f);
-            }
-        }
-        __syncthreads();
-        // (3) FC2 + sigmoid: thread owns channel c, loops over columns
-        for (int c = tid; c < C; c += blockDim.x) {
-            float w2[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) w2[r] = r < R ? se.w2[(long)c * R + r] : 0.f;
-            const float b2 = se.b2[c];
-            for (int w = 0; w < W; ++w) {
-                float acc = b2;
-#pragma unroll
-                for (int r = 0; r < 32; ++r)
-                    if (r < R) acc = fmaf(w2[r], s_z[w * R + r], acc);
-                s_gate[w * C + c] = 1.f / (1.f + __expf(-acc));
-            }
-        }
-        __syncthreads();
-    }
-
     const int cgs = C / 8;
-    if (!FINAL) {
-        // (4a) gate * max over the row pair, write padded-linear (H/2, W, C) including zero pads
-        const PLGeom go = make_pl(H / 2, W);
-        uint4* dst = reinterpret_cast<uint4*>(out + (long)n * go.S * C);
-        for (int it = tid; it < go.S * cgs; it += blockDim.x) {
-            const int cg = it % cgs, r = it / cgs;
-            const int oh = r / go.P, ow = r - oh * go.P;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (oh < go.H && ow < go.W) {
-                const uint4 a = reinterpret_cast<const uint4*>(src + ((long)(2 * oh) * gi.P + ow) * C)[cg];
-                const uint4 b = reinterpret_cast<const uint4*>(src + ((long)(2 * oh + 1) * gi.P + ow) * C)[cg];
-                o = max4(a, b);
-                if (use_se) {
-                    const float* gp = s_gate + ow * C + cg * 8;
-                    o = make_uint4(pack_bf16(bf16_lo(o.x) * gp[0], bf16_hi(o.x) * gp[1]),
-                                   pack_bf16(bf16_lo(o.y) * gp[2], bf16_hi(o.y) * gp[3]),
-                                   pack_bf16(bf16_lo(o.z) * gp[4], bf16_hi(o.z) * gp[5]),
-                                   pack_bf16(bf16_lo(o.w) * gp[6], bf16_hi(o.w) * gp[7]));
-                }
-            }
-            dst[it] = o;
-        }
-    } else {
-        // (4b) AdaptiveAvgPool2d((2, 32)) over gate * x; rows [kh*(H)/2 .. ) generalised bins
-        __nv_bfloat16* dst = out + (long)n * TOK_PER_CHUNK * 2 * C;
-        for (int it = tid; it < TOK_PER_CHUNK * 2 * cgs; it += blockDim.x) {
-            const int cg = it % cgs;
-            const int kh = (it / cgs) & 1;
-            const int k = it / (2 * cgs);
-            const int h0 = (kh * H) / 2, h1 = ((kh + 1) * H + 1) / 2;
-            const int w0 = (k * W) / TOK_PER_CHUNK, w1 = ((k + 1) * W + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int h = h0; h < h1; ++h)
-                for (int w = w0; w < w1; ++w) {
-                    const uint4 a = reinterpret_cast<const uint4*>(src + ((long)h * gi.P + w) * C)[cg];
-                    float x[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
-                                  bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
-                    if (use_se) {
-                        const float* gp = s_gate + w * C + cg * 8;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] *= gp[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] += x[j];
-                }
-            const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
-            const uint4 o = make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                                       pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
-            reinterpret_cast<uint4*>(dst + ((long)k * 2 + kh) * C)[cg] = o;
-        }
+    const int cg = (int)(idx % cgs);
+    const long col = idx / cgs;                 // n*W + w
+    const int n = (int)(col / W), w = (int)(col - (long)n * W);
+    const uint4* p = reinterpret_cast<const uint4*>(in + ((long)n * gi.S + w) * C) + cg;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int h = 0; h < H; ++h) {
+        const uint4 a = __ldg(p + (long)h * gi.P * cgs);
+        acc[0] += bf16_lo(a.x); acc[1] += bf16_hi(a.x); acc[2] += bf16_lo(a.y); acc[3] += bf16_hi(a.y);
+        acc[4] += bf16_lo(a.z); acc[5] += bf16_hi(a.z); acc[6] += bf16_lo(a.w); acc[7] += bf16_hi(a.w);
     }
+    const float inv = 1.f / (float)H;
+    reinterpret_cast<uint4*>(means)[idx] =
+        make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
+                   pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
 }
 
-template <bool FINAL>
-static int launch_se_generic(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
-                             const SEWeights* se, cudaStream_t stream) {
+int launch_se_col_mean(const __nv_bfloat16* in, __nv_bfloat16* means, int n_chunks, int H, int W, int C,
+                       cudaStream_t stream) {
     if (n_chunks == 0) return 0;
-    KOCR_CHECK(C % 64 == 0 && C <= 512, "se_pool: unsupported channel count %d", C);
-    KOCR_CHECK(se == nullptr || se->R <= 32, "se_pool: reduction width %d > 32", se ? se->R : 0);
-    const size_t smem = (size_t)W * C * 4 + (size_t)W * 32 * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(se_pool_kernel<FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
-    KOCR_CHECK(smem <= 64 * 1024, "se_pool: smem %zu too large", smem);
-    SEWeights z = {nullptr, nullptr, nullptr, nullptr, 0};
-    se_pool_kernel<FINAL><<<n_chunks, 256, smem, stream>>>(in, out, H, W, C, se ? *se : z, se ? 1 : 0);
+    const long total = (long)n_chunks * W * (C / 8);
+    se_col_mean_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, means, total, H, W, C);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_se_pool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
-                   const SEWeights* se, cudaStream_t stream) {
-    return launch_se_generic<false>(in, out, n_chunks, H, W, C, se, stream);
+__device__ __forceinline__ void load_gate8(const float* __restrict__ gate, long off, float (&g)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(gate + off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(gate + off) + 1);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
 }
-int launch_se_finalpool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
-                        const SEWeights* se, cudaStream_t stream) {
-    return launch_se_generic<true>(in, out, n_chunks, H, W, C, se, stream);
+
+// gate (optional, fp32 [n*W + w][C], already sigmoid-ed) * max over row pairs -> padded-linear (H/2, W, C).
+// The gate is positive, so max(x1*g, x2*g) == g*max(x1, x2) exactly (se_model.py:30,49).
+__global__ void __launch_bounds__(256) se_apply_pool_kernel(const __nv_bfloat16* __restrict__ in,
+                                                            const float* __restrict__ gate,
+                                                            __nv_bfloat16* __restrict__ out, long total, int H,
+                                                            int W, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const PLGeom gi = make_pl(H, W), go = make_pl(H / 2, W);
+    const int cgs = C / 8;
+    const int cg = (int)(idx % cgs);
+    const long q = idx / cgs;
+    const int n = (int)(q / go.S);
+    const int r = (int)(q - (long)n * go.S);
+    const int oh = r / go.P, ow = r - oh * go.P;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (oh < go.H && ow < go.W) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + ((long)n * gi.S + (long)(2 * oh) * gi.P + ow) * C) + cg;
+        o = max4(__ldg(p), __ldg(p + (long)gi.P * cgs));
+        if (gate) {
+            float g[8];
+            load_gate8(gate, ((long)n * W + ow) * C + cg * 8, g);
+            o = make_uint4(pack_bf16(bf16_lo(o.x) * g[0], bf16_hi(o.x) * g[1]),
+                           pack_bf16(bf16_lo(o.y) * g[2], bf16_hi(o.y) * g[3]),
+                           pack_bf16(bf16_lo(o.z) * g[4], bf16_hi(o.z) * g[5]),
+                           pack_bf16(bf16_lo(o.w) * g[6], bf16_hi(o.w) * g[7]));
+        }
+    }
+    reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
+int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H, int W,
+                         int C, cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    const PLGeom go = make_pl(H / 2, W);
+    const long total = (long)n_chunks * go.S * (C / 8);
+    se_apply_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, gate, out, total, H, W, C);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// gate (optional) * x, then AdaptiveAvgPool2d((2, 32)) -> patch-projection operand
+// out[n*32 + k][kh*C + c] (se_model.py:61,78: bin k covers columns [floor(k*W/32), ceil((k+1)*W/32))).
+__global__ void __launch_bounds__(256) se_apply_finalpool_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                 const float* __restrict__ gate,
+                                                                 __nv_bfloat16* __restrict__ out, long total, int H,
+                                                                 int W, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const PLGeom gi = make_pl(H, W);
+    const int cgs = C / 8;
+    const int cg = (int)(idx % cgs);
+    const int kh = (int)((idx / cgs) & 1);
+    const long nk = idx / (2 * cgs);                 // n*32 + k
+    const int n = (int)(nk / TOK_PER_CHUNK), k = (int)(nk - (long)n * TOK_PER_CHUNK);
+    const int h0 = (kh * H) / 2, h1 = ((kh + 1) * H + 1) / 2;
+    const int w0 = (k * W) / TOK_PER_CHUNK, w1 = ((k + 1) * W + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int w = w0; w < w1; ++w) {
+        float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (gate) load_gate8(gate, ((long)n * W + w) * C + cg * 8, g);
+        for (int h = h0; h < h1; ++h) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + ((long)n * gi.S + (long)h * gi.P + w) * C) + cg);
+            acc[0] += bf16_lo(a.x) * g[0]; acc[1] += bf16_hi(a.x) * g[1];
+            acc[2] += bf16_lo(a.y) * g[2]; acc[3] += bf16_hi(a.y) * g[3];
+            acc[4] += bf16_lo(a.z) * g[4]; acc[5] += bf16_hi(a.z) * g[5];
+            acc[6] += bf16_lo(a.w) * g[6]; acc[7] += bf16_hi(a.w) * g[7];
+        }
+    }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+    reinterpret_cast<uint4*>(out)[idx] =
+        make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
+                   pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+}
+
+int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H,
+                              int W, int C, cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    const long total = (long)n_chunks * TOK_PER_CHUNK * 2 * (C / 8);
+    se_apply_finalpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, gate, out, total, H, W, C);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace kocr

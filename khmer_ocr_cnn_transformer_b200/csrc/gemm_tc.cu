@@ -170,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (ep.relu) f[j] = fmaxf(f[j], 0.f);
+                    if (ep.relu == 1) f[j] = fmaxf(f[j], 0.f);
+                    else if (ep.relu == 2) f[j] = 1.f / (1.f + __expf(-f[j]));
                     if (!valid) f[j] = 0.f;
                 }
                 if (ep.out_f32) {
@@ -227,7 +228,8 @@ __global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ a, long
         const long ar = ep.add_period > 0 ? (row % ep.add_period) : row;
         acc += ep.addend[ar * ep.ld_add + n];
     }
-    if (ep.relu) acc = fmaxf(acc, 0.f);
+    if (ep.relu == 1) acc = fmaxf(acc, 0.f);
+    else if (ep.relu == 2) acc = 1.f / (1.f + __expf(-acc));
     if (ep.pl_S > 0) {
         const int r = (int)(row % ep.pl_S);
         const int h = r / ep.pl_P, ww = r - h * ep.pl_P;

@@ -13,7 +13,7 @@ namespace kocr {
 
 struct GemmEpilogue {
     const float* bias;        // [N] or nullptr
-    int relu;                 // apply max(x, 0)
+    int relu;                 // activation: 0 none, 1 max(x, 0), 2 sigmoid
     // row-validity mask for padded-linear outputs: rows whose (h, w) is a pad position get 0.
     int pl_S, pl_P, pl_H, pl_W;   // pl_S == 0 -> no mask
     // optional fp32 addend: out += addend[(period ? row % period : row) * ld_add + n]

@@ -36,13 +36,16 @@ int launch_conv1_pool(const float* d_chunks, const float* w /*[64][9]*/, const f
                       __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
 // 2x2 max-pool between padded-linear layouts (C multiple of 8).
 int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
-// 1D-SE gate (optional) + (2,1) max-pool: padded-linear (H, W, C) -> padded-linear (H/2, W, C).
-struct SEWeights { const float* w0; const float* b0; const float* w2; const float* b2; int R; };
-int launch_se_pool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
-                   const SEWeights* se /*null -> plain pool*/, cudaStream_t stream);
-// 1D-SE gate (optional) + AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n_chunks*32, 2*C] (k = kh*C + c).
-int launch_se_finalpool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
-                        const SEWeights* se, cudaStream_t stream);
+// 1D-SE: squeeze -> column means bf16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;
+// gate fp32 [n*W + w][C] (null = no SE) * (2,1) max-pool -> padded-linear (H/2, W, C), or
+// gate * x -> AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n*32 + k][kh*C + c].
+struct SEWeights { const __nv_bfloat16* w0p; const float* b0p; const __nv_bfloat16* w2p; const float* b2; };
+int launch_se_col_mean(const __nv_bfloat16* in, __nv_bfloat16* means, int n_chunks, int H, int W, int C,
+                       cudaStream_t stream);
+int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H, int W,
+                         int C, cudaStream_t stream);
+int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H,
+                              int W, int C, cudaStream_t stream);
 
 // ---- stage 4/5 helpers -----------------------------------------------------------------
 // per-chunk 32-token, 8-head attention: qkv bf16 [M, 1152] -> out bf16 [M, 384].

@@ -132,11 +132,10 @@ int resolve_weights(kocr_handle* h) {
     if (h->variant == 0) {
         static const int sc[3] = {256, 512, 512};
         for (int i = 0; i < 3; ++i) {
-            const int C = sc[i], R = C / 16;
-            h->se[i].R = R;
-            snprintf(nm, sizeof nm, "se%d.w0", i + 3); W_F32(h->se[i].w0, nm, R * C);
-            snprintf(nm, sizeof nm, "se%d.b0", i + 3); W_F32(h->se[i].b0, nm, R);
-            snprintf(nm, sizeof nm, "se%d.w2", i + 3); W_F32(h->se[i].w2, nm, C * R);
+            const int C = sc[i];
+            snprintf(nm, sizeof nm, "se%d.w0p", i + 3); W_BF16(h->se[i].w0p, nm, 128 * C);
+            snprintf(nm, sizeof nm, "se%d.b0p", i + 3); W_F32(h->se[i].b0p, nm, 128);
+            snprintf(nm, sizeof nm, "se%d.w2p", i + 3); W_BF16(h->se[i].w2p, nm, C * 128);
             snprintf(nm, sizeof nm, "se%d.b2", i + 3); W_F32(h->se[i].b2, nm, C);
         }
         W_BF16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
@@ -206,6 +205,7 @@ int carve_workspace(kocr_handle* h) {
         {"conv3", NC * G2.S * 256 * 2},  {"conv4", NC * G2.S * 256 * 2}, {"pool3", NC * G3.S * 256 * 2},
         {"conv5", NC * G3.S * 512 * 2},  {"conv6", NC * G3.S * 512 * 2}, {"pool4", NC * G4.S * 512 * 2},
         {"conv7", NC * G4.S * 512 * 2},  {"patch_in", M * 1024 * 2},
+        {"se_mean", NC * 25 * 512 * 2},  {"se_z", NC * 25 * 128 * 2},   {"se_gate", NC * 25 * 512 * 4},
         {"x", M * D * 4},   {"xb", M * D * 2},  {"qkv", M * 3 * D * 2}, {"ao", M * D * 2}, {"y", M * D * 4},
         {"hff", M * 1024 * 2},
         {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2},
@@ -297,6 +297,28 @@ int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n
     return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, h->num_sms, s);
 }
 
+// SequenceSE excitation for every column of the batch: means -> FC1+ReLU (width padded to 128) -> FC2+sigmoid.
+// Returns the fp32 gate [n*W + w][C] in the workspace (null for the VGG baseline).
+int se_gate(kocr_handle* h, const __nv_bfloat16* act, int NC, int H, int W, int C, const SEWeights& w, const char* site,
+            const float** gate_out, cudaStream_t s) {
+    __nv_bfloat16* means = buf<__nv_bfloat16>(h, "se_mean");
+    __nv_bfloat16* z = buf<__nv_bfloat16>(h, "se_z");
+    float* gate = buf<float>(h, "se_gate");
+    const long rows = (long)NC * W;
+    char nm[64];
+    snprintf(nm, sizeof nm, "%s_squeeze", site);
+    TIMED(nm, 0, launch_se_col_mean(act, means, NC, H, W, C, s)); ++g_launches;
+    GemmEpilogue e = ep_none();
+    e.bias = w.b0p; e.relu = 1; e.out_bf16 = z; e.ld_bf16 = 128;
+    snprintf(nm, sizeof nm, "%s_fc", site);
+    TIMED(nm, 2.0 * rows * C * (C / 16), gemm_linear(h, means, rows, w.w0p, 128, C, e, s));
+    e = ep_none();
+    e.bias = w.b2; e.relu = 2; e.out_f32 = gate; e.ld_f32 = C;
+    TIMED(nm, 2.0 * rows * C * (C / 16), gemm_linear(h, z, rows, w.w2p, C, 128, e, s));
+    *gate_out = gate;
+    return 0;
+}
+
 int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     const int NC = h->n_chunks;
     if (NC == 0) return 0;
@@ -309,13 +331,17 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
     TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
     TIMED("conv4", cf(12, 25, 256, 256), gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
-    TIMED("se3_pool3", se ? nc * 409600.0 : 0, launch_se_pool(B("conv4"), B("pool3"), NC, 12, 25, 256, se ? &h->se[0] : nullptr, s)); ++g_launches;
+    const float* gate = nullptr;
+    if (se) KOCR_TRY(se_gate(h, B("conv4"), NC, 12, 25, 256, h->se[0], "se3", &gate, s));
+    TIMED("se3_apply_pool3", 0, launch_se_apply_pool(B("conv4"), gate, B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
     TIMED("conv5", cf(6, 25, 256, 512), gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
     TIMED("conv6", cf(6, 25, 512, 512), gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
-    TIMED("se4_pool4", se ? nc * 1638400.0 : 0, launch_se_pool(B("conv6"), B("pool4"), NC, 6, 25, 512, se ? &h->se[1] : nullptr, s)); ++g_launches;
+    if (se) KOCR_TRY(se_gate(h, B("conv6"), NC, 6, 25, 512, h->se[1], "se4", &gate, s));
+    TIMED("se4_apply_pool4", 0, launch_se_apply_pool(B("conv6"), gate, B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
     // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
     TIMED("conv7", cf(3, 25, 512, 512), gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
-    TIMED("se5_finalpool", se ? nc * 1638400.0 : 0, launch_se_finalpool(B("conv7"), B("patch_in"), NC, 3, 25, 512, se ? &h->se[2] : nullptr, s)); ++g_launches;
+    if (se) KOCR_TRY(se_gate(h, B("conv7"), NC, 3, 25, 512, h->se[2], "se5", &gate, s));
+    TIMED("se5_apply_finalpool", 0, launch_se_apply_finalpool(B("conv7"), gate, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
 
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");

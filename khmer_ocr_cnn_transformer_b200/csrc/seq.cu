@@ -431,7 +431,9 @@ int launch_dec_self_attn(const float* qkv, __nv_bfloat16* kcache, __nv_bfloat16*
 }
 
 // Cross-attention of one query per line over the line's T memory tokens (K/V precomputed once per line,
-// bf16 [Mtok, 1536]: layer*768 + {0: K, 384: V}).  CTA per line, warp per head.
+// bf16 [Mtok, 1536]: layer*768 + {0: K, 384: V}).  CTA per line.  A K (or V) row of all 8 heads is 768
+// contiguous bytes: a warp reads one key per iteration, 24 B (12 dims, a quarter of one head) per lane, so
+// every global read is a fully coalesced 768-byte burst; the 8 warps stride over the keys.
 __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q,
                                                              const __nv_bfloat16* __restrict__ kv, int layer,
                                                              const int* __restrict__ line_tok_off,
@@ -439,67 +441,114 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
                                                              const int* __restrict__ finished,
                                                              __nv_bfloat16* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out_lo) {
-    extern __shared__ float s_dyn[];               // [8][max_T] scores, then [384] q
+    extern __shared__ __align__(16) float s_dyn[];       // [8 heads][max_T] scores | [8 warps][384] partial outputs
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (finished[l]) return;
-    float* s_p = s_dyn + (long)warp * max_T;
-    float* s_q = s_dyn + (long)N_HEAD * max_T;
+    float* s_p = s_dyn;
+    float* s_o = s_dyn + (long)N_HEAD * max_T;
+    __shared__ float s_inv[N_HEAD];
     const int T = line_T[l];
-    const __nv_bfloat16* kbase = kv + (long)line_tok_off[l] * (4 * D_MODEL) + layer * 2 * D_MODEL + warp * HEAD_DIM;
-    const __nv_bfloat16* vbase = kbase + D_MODEL;
-    for (int i = tid; i < D_MODEL; i += blockDim.x) s_q[i] = q[(long)l * D_MODEL + i] * rsqrtf((float)HEAD_DIM);
+    const int head = lane >> 2;                  // 4 lanes per head, 12 dims each
+    const uint2* kbase = reinterpret_cast<const uint2*>(kv + (long)line_tok_off[l] * (4 * D_MODEL) + layer * 2 * D_MODEL) + lane * 3;
+    const uint2* vbase = kbase + (D_MODEL * 2) / 8;           // +768 bytes
+    const long row_stride = (4 * D_MODEL * 2) / 8;            // uint2 per token row
+    float qv[12];
+    {
+        const float sc = rsqrtf((float)HEAD_DIM);
+        const float4* qp = reinterpret_cast<const float4*>(q + (long)l * D_MODEL + lane * 12);
+        const float4 a = qp[0], b = qp[1], c = qp[2];
+        qv[0] = a.x * sc; qv[1] = a.y * sc; qv[2] = a.z * sc; qv[3] = a.w * sc;
+        qv[4] = b.x * sc; qv[5] = b.y * sc; qv[6] = b.z * sc; qv[7] = b.w * sc;
+        qv[8] = c.x * sc; qv[9] = c.y * sc; qv[10] = c.z * sc; qv[11] = c.w * sc;
+    }
+    // ---- scores
+    for (int j0 = warp; j0 < T; j0 += 32) {           // 4 keys in flight per warp
+        uint2 k[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
+            if (j < T) {
+                const uint2* kp = kbase + (long)j * row_stride;
+                k[u][0] = __ldg(kp); k[u][1] = __ldg(kp + 1); k[u][2] = __ldg(kp + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
+            if (j < T) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    acc = fmaf(qv[4 * i], bf16_lo(k[u][i].x), acc); acc = fmaf(qv[4 * i + 1], bf16_hi(k[u][i].x), acc);
+                    acc = fmaf(qv[4 * i + 2], bf16_lo(k[u][i].y), acc); acc = fmaf(qv[4 * i + 3], bf16_hi(k[u][i].y), acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if ((lane & 3) == 0) s_p[head * max_T + j] = acc;
+            }
+        }
+    }
     __syncthreads();
-    const float* qh = s_q + warp * HEAD_DIM;
-    float mx = -INFINITY;
-    for (int j = lane; j < T; j += 32) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long)j * (4 * D_MODEL));
+    // ---- softmax: warp w owns head w
+    {
+        float* ph = s_p + (long)warp * max_T;
+        float mx = -INFINITY;
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, ph[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) {
+            const float e = __expf(ph[j] - mx);
+            ph[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) s_inv[warp] = 1.f / sum;
+    }
+    __syncthreads();
+    // ---- P.V partial sums over this warp's keys
+    float o[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = 0.f;
+    const float* ph = s_p + (long)head * max_T;
+    for (int j0 = warp; j0 < T; j0 += 32) {
+        uint2 v[4][3];
+        float pj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
+            pj[u] = 0.f;
+            if (j < T) {
+                const uint2* vp = vbase + (long)j * row_stride;
+                v[u][0] = __ldg(vp); v[u][1] = __ldg(vp + 1); v[u][2] = __ldg(vp + 2);
+                pj[u] = ph[j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + 8 * u < T) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    o[4 * i] = fmaf(pj[u], bf16_lo(v[u][i].x), o[4 * i]); o[4 * i + 1] = fmaf(pj[u], bf16_hi(v[u][i].x), o[4 * i + 1]);
+                    o[4 * i + 2] = fmaf(pj[u], bf16_lo(v[u][i].y), o[4 * i + 2]); o[4 * i + 3] = fmaf(pj[u], bf16_hi(v[u][i].y), o[4 * i + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s_o[warp * D_MODEL + lane * 12 + i] = o[i];
+    __syncthreads();
+    for (int d = tid; d < D_MODEL; d += blockDim.x) {
         float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < HEAD_DIM / 8; ++i) {
-            const uint4 k8 = __ldg(kp + i);
-            acc = fmaf(qh[8 * i], bf16_lo(k8.x), acc); acc = fmaf(qh[8 * i + 1], bf16_hi(k8.x), acc);
-            acc = fmaf(qh[8 * i + 2], bf16_lo(k8.y), acc); acc = fmaf(qh[8 * i + 3], bf16_hi(k8.y), acc);
-            acc = fmaf(qh[8 * i + 4], bf16_lo(k8.z), acc); acc = fmaf(qh[8 * i + 5], bf16_hi(k8.z), acc);
-            acc = fmaf(qh[8 * i + 6], bf16_lo(k8.w), acc); acc = fmaf(qh[8 * i + 7], bf16_hi(k8.w), acc);
-        }
-        s_p[j] = acc;
-        mx = fmaxf(mx, acc);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < T; j += 32) {
-        const float e = __expf(s_p[j] - mx);
-        s_p[j] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    const float inv = 1.f / sum;
-    // P.V: lanes 0..23 own one bf16 pair of the 48 head dims each; 4 independent partial sums for ILP
-    if (lane < HEAD_DIM / 2) {
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-        const uint32_t* vp = reinterpret_cast<const uint32_t*>(vbase) + lane;
-        int j = 0;
-        for (; j + 1 < T; j += 2) {
-            const uint32_t a = __ldg(vp + (long)j * (2 * D_MODEL));
-            const uint32_t b = __ldg(vp + (long)(j + 1) * (2 * D_MODEL));
-            o0 = fmaf(s_p[j], bf16_lo(a), o0); o1 = fmaf(s_p[j], bf16_hi(a), o1);
-            o2 = fmaf(s_p[j + 1], bf16_lo(b), o2); o3 = fmaf(s_p[j + 1], bf16_hi(b), o3);
-        }
-        if (j < T) {
-            const uint32_t a = __ldg(vp + (long)j * (2 * D_MODEL));
-            o0 = fmaf(s_p[j], bf16_lo(a), o0); o1 = fmaf(s_p[j], bf16_hi(a), o1);
-        }
-        const long oi = (long)l * D_MODEL + warp * HEAD_DIM + 2 * lane;
-        store_attn_out((o0 + o2) * inv, oi, out, out_lo);
-        store_attn_out((o1 + o3) * inv, oi + 1, out, out_lo);
+        for (int w = 0; w < 8; ++w) acc += s_o[w * D_MODEL + d];
+        store_attn_out(acc * s_inv[d / HEAD_DIM], (long)l * D_MODEL + d, out, out_lo);
     }
 }
 
 int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
                           const int* line_T, int max_T, const int* finished, __nv_bfloat16* out,
                           __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream) {
-    const size_t smem = ((size_t)N_HEAD * max_T + D_MODEL) * sizeof(float);
+    const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);
     KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
     static bool attr_set = false;
     if (!attr_set) {     // once, outside any stream capture (the first decode group of a process runs eagerly)

@@ -5,6 +5,8 @@ What the packing does:
     b' = (b - mean) * g/sqrt(var+eps) + beta            (se_model.py:39-58, BatchNorm2d eps 1e-5)
   * conv weights (Cout, Cin, 3, 3) -> K-major bf16 [Cout][tap = r*3+s][Cin] for the implicit GEMM
   * patch projection Conv2d(512->D, (2,1)) -> bf16 [D][kh*512 + c]           (se_model.py:92-97)
+  * SE excitation Conv1d(C, C/16, 1) / Conv1d(C/16, C, 1) -> bf16 GEMM operands [128][C] and [C][128]
+    (reduced width zero-padded to the 128-wide N tile)                        (se_model.py:12-17)
   * nn.Linear / in_proj weights are already [N][K] K-major: bf16 cast only
   * LSTM: W_ih of both directions stacked [1536][384]; b = b_ih + b_hh; W_hh re-laid out for the
     2-CTA persistent kernel as bf16x2 [dir][rank][k-pair][row]               (se_model.py:228-234)
@@ -90,9 +92,16 @@ def pack_tensors(sd: dict) -> dict:
         w7, b7 = fold_bn(w7, b7, sd["cnn.bn7.weight"], sd["cnn.bn7.bias"], sd["cnn.bn7.running_mean"],
                          sd["cnn.bn7.running_var"])
         for k in (3, 4, 5):
-            f32(f"se{k}.w0", sd[f"cnn.se{k}.fc.0.weight"][:, :, 0])
-            f32(f"se{k}.b0", sd[f"cnn.se{k}.fc.0.bias"])
-            f32(f"se{k}.w2", sd[f"cnn.se{k}.fc.2.weight"][:, :, 0])
+            # excitation FCs as GEMM operands, reduced width R = C/16 zero-padded to 128
+            w0 = sd[f"cnn.se{k}.fc.0.weight"][:, :, 0]            # (R, C)
+            w2 = sd[f"cnn.se{k}.fc.2.weight"][:, :, 0]            # (C, R)
+            R, C = w0.shape
+            w0p = np.zeros((128, C), np.float32); w0p[:R] = w0
+            b0p = np.zeros(128, np.float32); b0p[:R] = sd[f"cnn.se{k}.fc.0.bias"]
+            w2p = np.zeros((C, 128), np.float32); w2p[:, :R] = w2
+            bf16(f"se{k}.w0p", w0p)
+            f32(f"se{k}.b0p", b0p)
+            bf16(f"se{k}.w2p", w2p)
             f32(f"se{k}.b2", sd[f"cnn.se{k}.fc.2.bias"])
     bf16("conv7.w", conv_to_kmajor(w7))
     f32("conv7.b", b7)

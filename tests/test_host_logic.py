@@ -87,7 +87,7 @@ def test_pack_blob_layout_and_folding():
     blob = weights.pack_blob(sd)
     assert blob[:8] == b"KOCRW001" and len(blob) % 256 == 0
     vt = weights.pack_tensors(seeded_state_dict("vgg", 4))
-    assert "lstm.w_ih" not in vt and "se3.w0" not in vt and vt["meta"][1][0] == 1
+    assert "lstm.w_ih" not in vt and "se3.w0p" not in vt and vt["meta"][1][0] == 1
 
 
 def test_scheduling_chunk_counts_match_reference_rule():
