@@ -27,7 +27,6 @@ def _get_predictor(model_path=None, vocab_path=None):
     if "vgg" in str(model_path).lower():
         model = VGG_KhmerOCR
     elif "resnet" in str(model_path).lower():
-        raise_resnet = True
         model = None
     else:
         model = SE_KhmerOCR
