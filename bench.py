@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--big-gemm-sms", type=int, default=0,
+                    help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs)")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="batches in flight per GPU (one handle + stream + host thread each)")
     args = ap.parse_args()
@@ -193,6 +195,8 @@ def main():
             self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
             self.batch_host.__dict__.update(self.batch.__dict__)
             self.batch_host.pixels = self.pix_host.numpy()
+            if args.big_gemm_sms > 0 and S > 1:
+                self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
             self.n_chunks = int(self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr()).sum())
 
         def step_resident(self):
@@ -320,7 +324,7 @@ def main():
             "config": {"workload": f"c2: {LINES_PER_STEP} synthetic Khmer text lines per GPU, resized width "
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
-                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S,
+                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S, "big_gemm_sms": args.big_gemm_sms,
                        "single_in_flight_e2e_ms_per_step": lat_ms, "wall_ms_resident": wall_res, "wall_ms_e2e": wall_e2e,
                        "l2": "per-step working set (~1.6 MB of activations per chunk, >3 GB per step) exceeds the 126 MB L2",
                        "parallelism": f"lines sharded over {world} GPU(s), no data-path collective"},

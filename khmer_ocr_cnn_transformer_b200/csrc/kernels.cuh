@@ -64,6 +64,12 @@ int launch_bilstm(const float* gin /*[Mtok,1536]*/, const __nv_bfloat16* whh_pac
                   const int* line_T, const LstmGroup* groups, int n_groups, float* mem_f32,
                   __nv_bfloat16* mem_bf16, __nv_bfloat16* mem_bf16_lo, cudaStream_t stream);
 size_t bilstm_whh_packed_elems();
+// tensor-core version: groups of 16 lines, recurrent weights as register-resident mma.sync fragments
+struct LstmGroup16 { int line[16]; };
+int launch_bilstm_mma(const float* gin, const __nv_bfloat16* whh_mma, const int* line_tok_off, const int* line_T,
+                      const LstmGroup16* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
+                      __nv_bfloat16* mem_bf16_lo, cudaStream_t stream);
+size_t bilstm_whh_mma_elems();
 
 // ---- decoder step kernels ---------------------------------------------------------------
 // The generated position of a step is t = *step_base + step_off: step_base lives on the device so that a

@@ -64,7 +64,9 @@ struct kocr_handle {
     const __nv_bfloat16* patch_w; const float *patch_b, *patch_pos;
     EncLayerW enc[2];
     const float* global_pos;
-    const __nv_bfloat16 *lstm_w_ih, *lstm_w_hh; const float* lstm_b;
+    const __nv_bfloat16 *lstm_w_ih, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
+    int big_gemm_sms = 0;        // >0: persistent grid size of the stage 2-5a GEMMs (leave SMs to other streams)
+    int lstm_impl = 1;           // 1 = tensor-core recurrence (mma fragments in registers), 0 = CUDA-core / SMEM weights
     const float *dec_tok_emb, *dec_pos;
     DecLayerW dec[2];
     const __nv_bfloat16 *dec_kv_w, *dec_out_w; const float *dec_kv_b, *dec_out_b;
@@ -101,6 +103,7 @@ struct kocr_handle {
     // device arrays inside staging_dev
     LineDesc* d_lines = nullptr; int* d_chunk_line = nullptr; int* d_row_pos = nullptr;
     int* d_line_tok_off = nullptr; int* d_line_T = nullptr; LstmGroup* d_groups = nullptr;
+    LstmGroup16* d_groups16 = nullptr; int n_groups16 = 0;
 };
 
 namespace {
@@ -141,6 +144,7 @@ int resolve_weights(kocr_handle* h) {
         W_BF16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
         W_F32(h->lstm_b, "lstm.b", 8 * LSTM_H);
         W_BF16(h->lstm_w_hh, "lstm.w_hh", bilstm_whh_packed_elems());
+        W_BF16(h->lstm_w_hh_mma, "lstm.w_hh_mma", bilstm_whh_mma_elems());
     }
     W_BF16(h->patch_w, "patch.w", D * 1024);
     W_F32(h->patch_b, "patch.b", D);
@@ -228,7 +232,8 @@ int carve_workspace(kocr_handle* h) {
         off += (it.bytes + 1023) / 1024 * 1024;
     }
     // staging for the small per-batch integer tables
-    h->staging_bytes = L * sizeof(LineDesc) + NC * 4 + M * 4 + L * 4 * 2 + (L / 8 + 2) * sizeof(LstmGroup) + 4096;
+    h->staging_bytes = L * sizeof(LineDesc) + NC * 4 + M * 4 + L * 4 * 2 + (L / 8 + 2) * sizeof(LstmGroup) +
+                       (L / 16 + 2) * sizeof(LstmGroup16) + 4096;
     KOCR_CUDA(cudaMallocHost(&h->staging_host, h->staging_bytes));
     KOCR_CUDA(cudaMalloc(&h->staging_dev, h->staging_bytes));
     KOCR_CUDA(cudaMallocHost(&h->pinned_flag, 64));
@@ -280,7 +285,8 @@ int gemm_linear(kocr_handle* h, const __nv_bfloat16* a, long rows, const __nv_bf
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = (int)rows; p.N = N; p.taps = 1; p.cin = K; p.ep = ep;
-    return launch_gemm_tc(a, rows, w, p, h->num_sms, s);
+    const int sms = (h->big_gemm_sms > 0 && rows > 4096) ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
+    return launch_gemm_tc(a, rows, w, p, sms, s);
 }
 
 int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, const PLGeom& g, int Cin,
@@ -294,7 +300,8 @@ int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n
     p.ep.bias = b; p.ep.relu = relu;
     p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W;
     p.ep.out_bf16 = out; p.ep.ld_bf16 = Cout;
-    return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, h->num_sms, s);
+    const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
+    return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, sms, s);
 }
 
 // SequenceSE excitation for every column of the batch: means -> FC1+ReLU (width padded to 128) -> FC2+sigmoid.
@@ -384,6 +391,10 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
         GemmEpilogue e = ep_none();
         e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
         TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, buf<__nv_bfloat16>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
+        if (h->lstm_impl == 1)
+            TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm_mma(buf<float>(h, "gin"), h->lstm_w_hh_mma, h->d_line_tok_off, h->d_line_T, h->d_groups16,
+                               h->n_groups16, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
+        else
         TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm(buf<float>(h, "gin"), h->lstm_w_hh, h->d_line_tok_off, h->d_line_T, h->d_groups,
                                h->n_groups, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
         ++g_launches;
@@ -656,7 +667,12 @@ int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes
     h->n_groups = (n_lines + 7) / 8;
     for (int g = 0; g < h->n_groups; ++g)
         for (int j = 0; j < 8; ++j) groups[g].line[j] = (g * 8 + j < n_lines) ? order[g * 8 + j] : -1;
-    const size_t used = reinterpret_cast<uint8_t*>(groups + h->n_groups) - h->staging_host;
+    LstmGroup16* groups16 = reinterpret_cast<LstmGroup16*>(groups + h->n_groups);
+    h->d_groups16 = reinterpret_cast<LstmGroup16*>(dev_of(groups16));
+    h->n_groups16 = (n_lines + 15) / 16;
+    for (int g = 0; g < h->n_groups16; ++g)
+        for (int j = 0; j < 16; ++j) groups16[g].line[j] = (g * 16 + j < n_lines) ? order[g * 16 + j] : -1;
+    const size_t used = reinterpret_cast<uint8_t*>(groups16 + h->n_groups16) - h->staging_host;
     KOCR_CHECK(used <= h->staging_bytes, "internal: staging overflow");
     KOCR_CUDA(cudaMemcpyAsync(h->staging_dev, h->staging_host, used, cudaMemcpyHostToDevice, s));
     KOCR_CUDA(cudaEventRecord(h->staging_done, s));
@@ -746,6 +762,8 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "trace_logits") == 0) { h->trace_logits = value; return 0; }
     if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
+    if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
+    if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
     if (strcmp(name, "kernel_timing") == 0) {
         h->kernel_timing = value;
         if (value) { h->sites.clear(); }

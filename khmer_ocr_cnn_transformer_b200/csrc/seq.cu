@@ -311,6 +311,166 @@ int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* 
 }
 
 // ------------------------------------------------------------------------------------------
+// BiLSTM recurrence, tensor-core version.  Cluster of 2 CTAs per (group of <= 16 lines, direction), 12 warps
+// per CTA.  Warp w of CTA `rank` owns hidden units [rank*96 + w*8, +8): its 32 gate rows x 192 recurrent weights
+// live in REGISTERS as mma.sync m16n8k16 A-fragments for all timesteps (2 m-tiles {i|f}, {g|o} x 12 k-steps).
+// Per step: D[32 gate rows x 16 lines] = W_hh[32 x 192] . h[192 x 16 lines] with h split into bf16 hi + lo parts
+// (both accumulated, fp32 accumulators), + the input projection; the fragment layout leaves all four gates of a
+// (unit, line) cell in one thread, so the cell update needs no exchange; the new h is written to both CTAs'
+// shared memory (DSMEM) and one cluster barrier closes the step.
+// The step is M = 32 rows per warp and strictly sequential: latency-bound, far too small for a tcgen05 tile.
+// whh_mma layout (host): [dir][rank][warp][mtile][kstep][lane] uint4 = the A fragment registers.
+// ------------------------------------------------------------------------------------------
+static constexpr int LM_LPG = 16;          // lines per group
+static constexpr int LM_HS = 200;          // padded row stride (bf16) of the h buffers: conflict-free B loads
+static constexpr int LM_THREADS = 384;
+
+size_t bilstm_whh_mma_elems() { return (size_t)2 * 2 * 12 * 2 * 12 * 32 * 8; }   // bf16 elements
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LM_THREADS, 1)
+bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, const int* __restrict__ line_tok_off,
+                  const int* __restrict__ line_T, const LstmGroup16* __restrict__ groups, float* __restrict__ mem_f32,
+                  __nv_bfloat16* __restrict__ mem_bf16, __nv_bfloat16* __restrict__ mem_lo) {
+    __shared__ __align__(16) __nv_bfloat16 s_h[2][2][LM_LPG][LM_HS];     // [buffer][hi/lo][line][k]
+    extern __shared__ __align__(16) float s_gin[];                       // [2][16][384] input-projection prefetch
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int dir = blockIdx.y & 1;
+    const LstmGroup16 grp = groups[blockIdx.y >> 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+
+    // recurrent weights -> registers (96 per thread)
+    uint4 afrag[2][12];
+    {
+        const uint4* src = whh + ((size_t)((dir * 2 + rank) * 12 + warp) * 2 * 12) * 32 + lane;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 12; ++ks) afrag[mt][ks] = __ldg(src + (mt * 12 + ks) * 32);
+    }
+    // this thread's four (unit, line) cells: unit = g, lines nt*8 + 2*tig + {0, 1}
+    int cell_off[4], cell_T[4];
+    int maxT = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int li = grp.line[(c >> 1) * 8 + 2 * tig + (c & 1)];
+        cell_off[c] = li >= 0 ? line_tok_off[li] : 0;
+        cell_T[c] = li >= 0 ? line_T[li] : 0;
+    }
+    for (int l = 0; l < LM_LPG; ++l) {
+        const int li = grp.line[l];
+        if (li >= 0) maxT = max(maxT, line_T[li]);
+    }
+    for (int i = tid; i < 2 * 2 * LM_LPG * LM_HS; i += LM_THREADS) (&s_h[0][0][0][0])[i] = __float2bfloat16_rn(0.f);
+    __nv_bfloat16* peer = cluster.map_shared_rank(&s_h[0][0][0][0], rank ^ 1);
+    cluster.sync();
+
+    const int hid = rank * 96 + warp * 8 + g;                 // hidden unit of this thread's cells
+    const int gcol = dir * 4 * LSTM_H + hid;                  // gin column of gate 0 (i); gates are LSTM_H apart
+    float c_state[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur = 0;
+    // The input projection of step s+1 is fetched with cp.async (global -> shared, no registers) while step s
+    // computes, so its HBM latency never sits on the recurrence's critical path.
+    auto prefetch_gin = [&](int step) {
+        float* dst = s_gin + (step & 1) * 16 * LM_THREADS + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (step < cell_T[c]) {
+                const int pos = dir == 0 ? step : cell_T[c] - 1 - step;
+                const float* gp = gin + (long)(cell_off[c] + pos) * (8 * LSTM_H) + gcol;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + (c * 4 + q) * LM_THREADS)),
+                                 "l"(gp + q * LSTM_H) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch_gin(0);
+    for (int s = 0; s < maxT; ++s) {
+        prefetch_gin(s + 1);            // (an empty group once s + 1 >= every T)
+        float acc[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+        const __nv_bfloat16* hhi = &s_h[cur][0][0][0];
+        const __nv_bfloat16* hlo = &s_h[cur][1][0][0];
+#pragma unroll
+        for (int ks = 0; ks < 12; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int o = (nt * 8 + g) * LM_HS + ks * 16 + 2 * tig;
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hhi + o);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(hhi + o + 8);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hlo + o);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(hlo + o + 8);
+                mma_bf16_16816(acc[0][nt], afrag[0][ks], bh0, bh1);
+                mma_bf16_16816(acc[1][nt], afrag[1][ks], bh0, bh1);
+                mma_bf16_16816(acc[0][nt], afrag[0][ks], bl0, bl1);
+                mma_bf16_16816(acc[1][nt], afrag[1][ks], bl0, bl1);
+            }
+        }
+        // cell update: acc[0][nt] = {i(l0), i(l1), f(l0), f(l1)}, acc[1][nt] = {g(l0), g(l1), o(l0), o(l1)}
+        asm volatile("cp.async.wait_group 1;" ::: "memory");        // this step's input projection has landed
+        const float* gsrc = s_gin + (s & 1) * 16 * LM_THREADS + tid;
+        const int nxt = cur ^ 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (s < cell_T[c]) {
+                const int nt = c >> 1, e = c & 1;
+                const float ig = sigmoid_acc(acc[0][nt][e] + gsrc[(c * 4 + 0) * LM_THREADS]);
+                const float fg = sigmoid_acc(acc[0][nt][2 + e] + gsrc[(c * 4 + 1) * LM_THREADS]);
+                const float gg = tanhf(acc[1][nt][e] + gsrc[(c * 4 + 2) * LM_THREADS]);
+                const float og = sigmoid_acc(acc[1][nt][2 + e] + gsrc[(c * 4 + 3) * LM_THREADS]);
+                const float cc = fg * c_state[c] + ig * gg;
+                c_state[c] = cc;
+                const float h = og * tanhf(cc);
+                const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+                const __nv_bfloat16 lb = __float2bfloat16_rn(h - __bfloat162float(hb));
+                const int line = nt * 8 + 2 * tig + e;
+                const int ohi = ((nxt * 2 + 0) * LM_LPG + line) * LM_HS + hid;
+                const int olo = ((nxt * 2 + 1) * LM_LPG + line) * LM_HS + hid;
+                (&s_h[0][0][0][0])[ohi] = hb; (&s_h[0][0][0][0])[olo] = lb;
+                peer[ohi] = hb; peer[olo] = lb;
+                const int pos = dir == 0 ? s : cell_T[c] - 1 - s;
+                const long o = (long)(cell_off[c] + pos) * D_MODEL + dir * LSTM_H + hid;
+                mem_f32[o] = h;
+                if (mem_bf16) { mem_bf16[o] = hb; if (mem_lo) mem_lo[o] = lb; }
+            }
+        }
+        cluster.sync();
+        cur = nxt;
+    }
+}
+
+int launch_bilstm_mma(const float* gin, const __nv_bfloat16* whh_mma, const int* line_tok_off, const int* line_T,
+                      const LstmGroup16* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
+                      __nv_bfloat16* mem_bf16_lo, cudaStream_t stream) {
+    if (n_groups == 0) return 0;
+    const size_t smem = 2 * 16 * LM_THREADS * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        KOCR_CUDA(cudaFuncSetAttribute(bilstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    bilstm_mma_kernel<<<dim3(2, n_groups * 2), LM_THREADS, smem, stream>>>(
+        gin, reinterpret_cast<const uint4*>(whh_mma), line_tok_off, line_T, groups, mem_f32, mem_bf16, mem_bf16_lo);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Decoder step kernels (one launch each per generated position t, batched over lines).
 // tokens: int32 [n_lines, DEC_MAX + 1]; tokens[l][0] = <sos>.
 // ------------------------------------------------------------------------------------------

@@ -63,6 +63,32 @@ def pack_whh(w_f, w_b):
     return out
 
 
+def pack_whh_mma(w_f, w_b):
+    """Recurrent weights as mma.sync m16n8k16 A-fragments for bilstm_mma_kernel:
+    [dir][rank][warp][mtile][kstep][lane][reg 0..3][2].  Warp w of CTA `rank` owns hidden units
+    rank*96 + w*8 + g (g = lane//4); m-tile 0 = gates (i | f), m-tile 1 = gates (g | o);
+    reg0 = (row g,   k0 + 2*tig + {0,1}), reg1 = (row g+8, same k),
+    reg2 = (row g,   k0 + 2*tig + 8 + {0,1}), reg3 = (row g+8, same), tig = lane % 4, k0 = 16*kstep."""
+    out = np.empty((2, 2, 12, 2, 12, 32, 4, 2), np.float32)
+    lane = np.arange(32)
+    g, tig = lane // 4, lane % 4
+    for d, w in enumerate((w_f, w_b)):
+        for rank in range(2):
+            for warp in range(12):
+                unit = rank * 96 + warp * 8 + g                       # (32,)
+                for mt in range(2):
+                    row_a = (2 * mt) * LSTM_H + unit                  # gate i / g
+                    row_b = (2 * mt + 1) * LSTM_H + unit              # gate f / o
+                    for ks in range(12):
+                        k = ks * 16 + 2 * tig
+                        for e in range(2):
+                            out[d, rank, warp, mt, ks, :, 0, e] = w[row_a, k + e]
+                            out[d, rank, warp, mt, ks, :, 1, e] = w[row_b, k + e]
+                            out[d, rank, warp, mt, ks, :, 2, e] = w[row_a, k + 8 + e]
+                            out[d, rank, warp, mt, ks, :, 3, e] = w[row_b, k + 8 + e]
+    return out
+
+
 def pack_tensors(sd: dict) -> dict:
     """Reference state_dict (numpy fp32) -> {blob entry name: (dtype, ndarray)}."""
     variant, D, max_len, dec_max, = validate_state_dict(sd)
@@ -124,6 +150,7 @@ def pack_tensors(sd: dict) -> dict:
         f32("lstm.b", np.concatenate([sd[p + "bias_ih_l0"] + sd[p + "bias_hh_l0"],
                                       sd[p + "bias_ih_l0_reverse"] + sd[p + "bias_hh_l0_reverse"]]))
         bf16("lstm.w_hh", pack_whh(sd[p + "weight_hh_l0"], sd[p + "weight_hh_l0_reverse"]))
+        bf16("lstm.w_hh_mma", pack_whh_mma(sd[p + "weight_hh_l0"], sd[p + "weight_hh_l0_reverse"]))
     f32("dec.tok_emb", sd["dec.tok_emb.weight"])
     f32("dec.pos", sd["dec.pos_emb"])
     kv_w, kv_b = [], []

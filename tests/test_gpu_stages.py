@@ -149,11 +149,14 @@ def test_backbone_and_encoder_parity_vgg(rec_seeded_vgg):
     _check_backbone(rec, sd, "vgg", _lines(4, 100, 700, seed=22), "vgg_seeded")
 
 
-def test_long_line_c4(rec_seeded_se):
-    """48x2400 line = 29 chunks, T = 928 (BASELINE config 4): BiLSTM over a long merged sequence."""
+@pytest.mark.parametrize("lstm_impl", [1, 0])
+def test_long_line_c4(rec_seeded_se, lstm_impl):
+    """48x2400 line = 29 chunks, T = 928 (BASELINE config 4): BiLSTM over a long merged sequence, with both
+    recurrence kernels (1 = tensor-core fragments in registers, 0 = CUDA-core with W_hh in shared memory)."""
     from khmer_ocr_cnn_transformer_b200 import _native
     from oracle import recognizer_np as O
     rec, sd = rec_seeded_se
+    rec.set_option("lstm_impl", lstm_impl)
     img = _lines(1, 2400, 2400, seed=9)[0]
     from PIL import Image
     img = np.asarray(Image.fromarray(img).resize((2400, 48), Image.Resampling.BILINEAR))
@@ -165,8 +168,9 @@ def test_long_line_c4(rec_seeded_se):
     enc = O.encoder_forward(sd, O.patch_forward(sd, O.cnn_forward(sd, chunks, "se")))
     mem = O.memory_for_line(sd, enc, "se")
     got = rec.debug_read("memory").reshape(-1, 384)[:928]
+    rec.set_option("lstm_impl", 1)
     e = rel_err(got, mem)
-    _report("c4_memory_rel_err", e)
+    _report(f"c4_memory_rel_err_lstm_impl{lstm_impl}", e)
     assert e < 3e-2
 
 

@@ -84,6 +84,15 @@ def test_pack_blob_layout_and_folding():
     gate, rank, jj, kp, pair = 2, 1, 40, 33, 1
     want = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(src[gate * 192 + rank * 96 + jj, 2 * kp + pair].reshape(1)))[0]
     assert whh[1, rank, kp, gate * 96 + jj, pair] == want
+    # tensor-core LSTM fragments: [dir][rank][warp][mtile][kstep][lane][reg][2]
+    fr = weights.bf16_bits_to_f32(t["lstm.w_hh_mma"][1]).reshape(2, 2, 12, 2, 12, 32, 4, 2)
+    rank, warp, mt, ks, lane, e = 1, 7, 1, 5, 22, 1
+    gg, tig = lane // 4, lane % 4
+    unit = rank * 96 + warp * 8 + gg
+    bf = lambda v: weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(np.asarray([v], np.float32)))[0]
+    assert fr[1, rank, warp, mt, ks, lane, 0, e] == bf(src[2 * 192 + unit, ks * 16 + 2 * tig + e])        # gate g, row g
+    assert fr[1, rank, warp, mt, ks, lane, 1, e] == bf(src[3 * 192 + unit, ks * 16 + 2 * tig + e])        # gate o, row g+8
+    assert fr[1, rank, warp, mt, ks, lane, 3, e] == bf(src[3 * 192 + unit, ks * 16 + 2 * tig + 8 + e])
     blob = weights.pack_blob(sd)
     assert blob[:8] == b"KOCRW001" and len(blob) % 256 == 0
     vt = weights.pack_tensors(seeded_state_dict("vgg", 4))
