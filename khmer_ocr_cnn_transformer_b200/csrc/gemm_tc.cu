@@ -33,7 +33,8 @@ struct GemmKernelParams {
     GemmEpilogue ep;
 };
 
-template <int BN>
+// BK is 128 bytes of K per row in both precisions: 64 bf16 or 32 fp32 (TF32) elements.
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmKernelParams p) {
@@ -63,6 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    constexpr int BKE = TF32 ? 32 : 64;           // K elements per 128-byte row
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = p.taps * p.cin_blocks;
 
@@ -80,15 +82,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(&tmap_a, &full_bar[stage], sa, cb * BK, m0 + p.tap_off[tap]);
-                    tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+                    tma_load_2d(&tmap_a, &full_bar[stage], sa, cb * BKE, m0 + p.tap_off[tap]);
+                    tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BKE, n0);
                     if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = make_idesc(BM, BN, TF32 ? 2u : 1u);
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -105,9 +107,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t da = make_sw128_kmajor_desc(sa);
                     const uint64_t db = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        // one MMA consumes 32 B of K (16 bf16 / 8 tf32) inside the 128 B swizzle row: +2 (16-byte units)
+                        if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem slot
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator ready
@@ -264,12 +267,13 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// bf16 row-major [rows, cols] matrix, box = {64 cols, box_rows}, 128-byte swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-    typedef std::tuple<const void*, uint64_t, uint64_t, uint32_t> Key;
+// row-major [rows, cols] matrix of bf16 (esize 2) or fp32 (esize 4), box = {128 bytes of K, box_rows},
+// 128-byte swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esize) {
+    typedef std::tuple<const void*, uint64_t, uint64_t, uint32_t, int> Key;
     static std::map<Key, CUtensorMap> cache;
     static std::mutex mu;
-    Key key(ptr, rows, cols, box_rows);
+    Key key(ptr, rows, cols, box_rows, esize);
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -278,10 +282,11 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t 
     PFN_encodeTiled enc = get_encode_fn();
     KOCR_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint64_t gstride[1] = {cols * (uint64_t)esize};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+    CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(ptr), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KOCR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu box_rows=%u", (int)r,
@@ -296,11 +301,12 @@ static std::atomic<long> g_gemm_launches{0};
 long gemm_tc_launch_count() { return g_gemm_launches.load(); }
 
 static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
-    KOCR_CHECK(p.cin % BK == 0, "gemm: cin %d not a multiple of %d", p.cin, BK);
+    const int bke = p.tf32 ? 32 : 64;
+    KOCR_CHECK(p.cin % bke == 0, "gemm: cin %d not a multiple of %d", p.cin, bke);
     KOCR_CHECK(p.N % BN == 0, "gemm: N %d not a multiple of the N tile %d", p.N, BN);
     KOCR_CHECK(p.taps == 1 || p.taps == 9, "gemm: taps must be 1 or 9");
     KOCR_CHECK(p.M > 0, "gemm: empty M");
-    kp.M = p.M; kp.N = p.N; kp.taps = p.taps; kp.cin_blocks = p.cin / BK;
+    kp.M = p.M; kp.N = p.N; kp.taps = p.taps; kp.cin_blocks = p.cin / bke;
     for (int i = 0; i < 9; ++i) kp.tap_off[i] = i < p.taps ? p.tap_off[i] : 0;
     kp.num_m_tiles = (p.M + BM - 1) / BM;
     kp.num_n_tiles = p.N / BN;
@@ -308,36 +314,42 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     return 0;
 }
 
-template <int BN>
-static int launch_impl(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p, int num_sms,
+template <int BN, bool TF32>
+static int launch_impl(const void* a, long rowsA, const void* w, const GemmProblem& p, int num_sms,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     GemmKernelParams kp;
     KOCR_TRY(fill_params(kp, p, BN));
     CUtensorMap ta, tb;
-    KOCR_TRY(make_tmap(&ta, a, (uint64_t)rowsA, (uint64_t)p.cin, BM));
-    KOCR_TRY(make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.taps * p.cin, BN));
+    const int esize = TF32 ? 4 : 2;
+    KOCR_TRY(make_tmap(&ta, a, (uint64_t)rowsA, (uint64_t)p.cin, BM, esize));
+    KOCR_TRY(make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.taps * p.cin, BN, esize));
     static bool attr_set = false;
     if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        KOCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int tiles = kp.num_m_tiles * kp.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
+    gemm_tc_kernel<BN, TF32><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
     KOCR_CUDA(cudaGetLastError());
     ++g_gemm_launches;
     return 0;
 }
 
-int launch_gemm_tc(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p, int num_sms,
+int launch_gemm_tc(const void* a, long rowsA, const void* w, const GemmProblem& p, int num_sms,
                    cudaStream_t stream) {
-    if (p.N % 256 == 0) return launch_impl<256>(a, rowsA, w, p, num_sms, stream);
-    return launch_impl<128>(a, rowsA, w, p, num_sms, stream);
+    if (p.tf32) {
+        if (p.N % 256 == 0) return launch_impl<256, true>(a, rowsA, w, p, num_sms, stream);
+        return launch_impl<128, true>(a, rowsA, w, p, num_sms, stream);
+    }
+    if (p.N % 256 == 0) return launch_impl<256, false>(a, rowsA, w, p, num_sms, stream);
+    return launch_impl<128, false>(a, rowsA, w, p, num_sms, stream);
 }
 
 int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p,
                            cudaStream_t stream) {
+    KOCR_CHECK(!p.tf32, "gemm check kernel: bf16 operands only");
     GemmKernelParams kp;
     KOCR_TRY(fill_params(kp, p, 128));
     const long total = (long)p.M * p.N;

@@ -33,13 +33,15 @@ struct GemmEpilogue {
 struct GemmProblem {
     int M, N;                 // output rows / cols (N multiple of the N tile)
     int taps;                 // 1 (linear) or 9 (3x3 conv)
-    int cin;                  // K per tap (multiple of 64)
+    int cin;                  // K per tap in elements (multiple of 64 for bf16, of 32 for tf32)
+    int tf32;                 // 0: bf16 operands (kind::f16), 1: fp32 operands consumed as TF32 (kind::tf32)
     int tap_off[9];           // row shift per tap
     GemmEpilogue ep;
 };
 
-// Host launchers (defined in gemm_tc.cu).  a: bf16 [rowsA, cin] row-major, w: bf16 [N, taps*cin].
-int launch_gemm_tc(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w,
+// Host launchers (defined in gemm_tc.cu).  a: [rowsA, cin] row-major, w: [N, taps*cin] (bf16 unless p.tf32).
+// With p.tf32 the operands are fp32 arrays (a: [rowsA, cin], w: [N, taps*cin]) read by the tensor core as TF32.
+int launch_gemm_tc(const void* a, long rowsA, const void* w,
                    const GemmProblem& p, int num_sms, cudaStream_t stream);
 // CUDA-core restatement of the same contract; used ONLY by tests to localise tcgen05 bugs.
 int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w,

@@ -78,11 +78,11 @@ int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base,
                      const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
                      cudaStream_t stream);
 int launch_dec_self_attn(const float* qkv /*[L,1152]*/, __nv_bfloat16* kcache,
-                         __nv_bfloat16* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base, int step_off, const int* finished,
-                         __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
+                         __nv_bfloat16* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
+                         int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream);
 int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,
                           const int* line_tok_off, const int* line_T, int max_T, const int* finished,
-                          __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream);
+                          float* out, int n_lines, cudaStream_t stream);
 int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,
                       const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
                       cudaStream_t stream);

@@ -489,6 +489,7 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __re
     const float4 p = reinterpret_cast<const float4*>(pos_emb + (long)t * D_MODEL)[c4];
     const float4 v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
     reinterpret_cast<float4*>(x)[idx] = v;
+    if (xb == nullptr) return;
     const uint32_t p0 = pack_bf16(v.x, v.y), p1 = pack_bf16(v.z, v.w);
     reinterpret_cast<uint2*>(xb)[idx] = make_uint2(p0, p1);
     if (xb_lo)
@@ -506,11 +507,7 @@ int launch_dec_embed(const int* tokens, const int* step_base, int step_off, cons
     return 0;
 }
 
-__device__ __forceinline__ void store_attn_out(float o, long idx, __nv_bfloat16* out, __nv_bfloat16* out_lo) {
-    const __nv_bfloat16 hb = __float2bfloat16_rn(o);
-    out[idx] = hb;
-    if (out_lo) out_lo[idx] = __float2bfloat16_rn(o - __bfloat162float(hb));
-}
+__device__ __forceinline__ void store_attn_out(float o, long idx, float* out) { out[idx] = o; }
 
 // Causal self-attention for the newest position t against the cache (keys 0..t); keys whose token is
 // <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.
@@ -520,8 +517,7 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
                                                             const int* __restrict__ tokens,
                                                             const int* __restrict__ step_base, int step_off,
                                                             const int* __restrict__ finished,
-                                                            __nv_bfloat16* __restrict__ out,
-                                                            __nv_bfloat16* __restrict__ out_lo) {
+                                                            float* __restrict__ out) {
     __shared__ float s_q[D_MODEL];
     __shared__ float s_p[N_HEAD][DEC_MAX];
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -575,17 +571,15 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
             o1 = fmaf(s_p[warp][j], bf16_hi(v2), o1);
         }
         const long oi = (long)l * D_MODEL + warp * HEAD_DIM + 2 * lane;
-        store_attn_out(o0 * inv, oi, out, out_lo);
-        store_attn_out(o1 * inv, oi + 1, out, out_lo);
+        store_attn_out(o0 * inv, oi, out);
+        store_attn_out(o1 * inv, oi + 1, out);
     }
 }
 
 int launch_dec_self_attn(const float* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* tokens,
-                         const int* step_base,
-                         int step_off, const int* finished, __nv_bfloat16* out, __nv_bfloat16* out_lo, int n_lines,
+                         const int* step_base, int step_off, const int* finished, float* out, int n_lines,
                          cudaStream_t stream) {
-    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, step_base, step_off, finished, out,
-                                                      out_lo);
+    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, step_base, step_off, finished, out);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -599,8 +593,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
                                                              const int* __restrict__ line_tok_off,
                                                              const int* __restrict__ line_T, int max_T,
                                                              const int* __restrict__ finished,
-                                                             __nv_bfloat16* __restrict__ out,
-                                                             __nv_bfloat16* __restrict__ out_lo) {
+                                                             float* __restrict__ out) {
     extern __shared__ __align__(16) float s_dyn[];       // [8 heads][max_T] scores | [8 warps][384] partial outputs
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (finished[l]) return;
@@ -701,13 +694,13 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
         float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) acc += s_o[w * D_MODEL + d];
-        store_attn_out(acc * s_inv[d / HEAD_DIM], (long)l * D_MODEL + d, out, out_lo);
+        store_attn_out(acc * s_inv[d / HEAD_DIM], (long)l * D_MODEL + d, out);
     }
 }
 
 int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
-                          const int* line_T, int max_T, const int* finished, __nv_bfloat16* out,
-                          __nv_bfloat16* out_lo, int n_lines, cudaStream_t stream) {
+                          const int* line_T, int max_T, const int* finished, float* out, int n_lines,
+                          cudaStream_t stream) {
     const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);
     KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
     static bool attr_set = false;
@@ -715,8 +708,7 @@ int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, co
         KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, finished, out,
-                                                          out_lo);
+    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, finished, out);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,7 +10,8 @@ What the packing does:
   * nn.Linear / in_proj weights are already [N][K] K-major: bf16 cast only
   * LSTM: W_ih of both directions stacked [1536][384]; b = b_ih + b_hh; W_hh re-laid out for the
     2-CTA persistent kernel as bf16x2 [dir][rank][k-pair][row]               (se_model.py:228-234)
-  * decoder cross-attention K/V projections of both layers stacked [1536][384]
+  * decoder projections / FFN / out_proj: fp32 pre-rounded to TF32 (the decoder GEMMs run in TF32)
+  * decoder cross-attention K/V projections of both layers stacked [1536][384] (bf16)
   * out_proj padded from 124 to 128 rows (pad logits are never read by the argmax)
 bf16 conversion is round-to-nearest-even, identical to __float2bfloat16_rn.
 """
@@ -36,6 +37,13 @@ def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
     if nan.any():
         out[nan] = 0x7FC0
     return out
+
+
+def round_to_tf32(x: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest TF32 (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32), kept as fp32."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u.astype(np.uint64) + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return r.view(np.float32).reshape(np.shape(x))
 
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
@@ -102,6 +110,9 @@ def pack_tensors(sd: dict) -> dict:
     def bf16(name, a):
         t[name] = (DT_BF16, f32_to_bf16_bits(np.ascontiguousarray(a, dtype=np.float32)))
 
+    def tf32(name, a):          # decoder GEMM operands stay fp32 (consumed as TF32 by the tensor cores)
+        t[name] = (DT_F32, round_to_tf32(np.ascontiguousarray(a, dtype=np.float32)))
+
     t["meta"] = (DT_I32, np.asarray([0 if se else 1, D, max_len, dec_max, vocab, 0, 0, 0], np.int32))
     for i in range(1, 7):
         p = f"cnn.conv{i}"
@@ -156,21 +167,21 @@ def pack_tensors(sd: dict) -> dict:
     kv_w, kv_b = [], []
     for l in range(2):
         p = f"dec.decoder.layers.{l}."
-        bf16(f"dec{l}.sa_in_w", sd[p + "self_attn.in_proj_weight"]); f32(f"dec{l}.sa_in_b", sd[p + "self_attn.in_proj_bias"])
-        bf16(f"dec{l}.sa_out_w", sd[p + "self_attn.out_proj.weight"]); f32(f"dec{l}.sa_out_b", sd[p + "self_attn.out_proj.bias"])
+        tf32(f"dec{l}.sa_in_w", sd[p + "self_attn.in_proj_weight"]); f32(f"dec{l}.sa_in_b", sd[p + "self_attn.in_proj_bias"])
+        tf32(f"dec{l}.sa_out_w", sd[p + "self_attn.out_proj.weight"]); f32(f"dec{l}.sa_out_b", sd[p + "self_attn.out_proj.bias"])
         cw, cb = sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"]
-        bf16(f"dec{l}.ca_q_w", cw[:D]); f32(f"dec{l}.ca_q_b", cb[:D])
+        tf32(f"dec{l}.ca_q_w", cw[:D]); f32(f"dec{l}.ca_q_b", cb[:D])
         kv_w.append(cw[D:]); kv_b.append(cb[D:])                   # rows: K (D) then V (D)
-        bf16(f"dec{l}.ca_out_w", sd[p + "multihead_attn.out_proj.weight"]); f32(f"dec{l}.ca_out_b", sd[p + "multihead_attn.out_proj.bias"])
-        bf16(f"dec{l}.l1_w", sd[p + "linear1.weight"]); f32(f"dec{l}.l1_b", sd[p + "linear1.bias"])
-        bf16(f"dec{l}.l2_w", sd[p + "linear2.weight"]); f32(f"dec{l}.l2_b", sd[p + "linear2.bias"])
+        tf32(f"dec{l}.ca_out_w", sd[p + "multihead_attn.out_proj.weight"]); f32(f"dec{l}.ca_out_b", sd[p + "multihead_attn.out_proj.bias"])
+        tf32(f"dec{l}.l1_w", sd[p + "linear1.weight"]); f32(f"dec{l}.l1_b", sd[p + "linear1.bias"])
+        tf32(f"dec{l}.l2_w", sd[p + "linear2.weight"]); f32(f"dec{l}.l2_b", sd[p + "linear2.bias"])
         for k in (1, 2, 3):
             f32(f"dec{l}.n{k}_g", sd[p + f"norm{k}.weight"]); f32(f"dec{l}.n{k}_b", sd[p + f"norm{k}.bias"])
     bf16("dec.ca_kv_w", np.concatenate(kv_w, 0))
     f32("dec.ca_kv_b", np.concatenate(kv_b, 0))
     ow = np.zeros((128, D), np.float32); ow[:vocab] = sd["dec.out_proj.weight"]
     ob = np.zeros(128, np.float32); ob[:vocab] = sd["dec.out_proj.bias"]
-    bf16("dec.out_w", ow)
+    tf32("dec.out_w", ow)
     f32("dec.out_b", ob)
     return t
 

@@ -78,3 +78,34 @@ def test_gemm_tcgen05_matches_check_kernel_and_numpy(M, N, taps, cin, relu, pl):
     # the bf16 output is the fp32 result rounded to nearest-even
     want16 = torch.from_numpy(tc32).to(torch.bfloat16).float().numpy()
     assert np.array_equal(tc16, want16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 1152, 384), (37, 128, 384), (256, 384, 1536), (300, 1536, 384)])
+def test_gemm_tf32_operands(M, N, K):
+    """kind::tf32 path used by the decoder: fp32 operands in global memory, read by the tensor core as TF32."""
+    import torch
+    from khmer_ocr_cnn_transformer_b200 import _native
+    from khmer_ocr_cnn_transformer_b200.weights import round_to_tf32
+    lib = _native.load_library()
+    rng = np.random.default_rng(M + N + K)
+    a_np = round_to_tf32(rng.standard_normal((M, K)).astype(np.float32))
+    w_np = round_to_tf32((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32))
+    bias = rng.standard_normal(N).astype(np.float32)
+    a, w, b = torch.from_numpy(a_np).cuda(), torch.from_numpy(w_np).cuda(), torch.from_numpy(bias).cuda()
+    out = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    to = np.zeros(1, np.int32)
+    _native.check(lib.kocr_test_gemm(2, a.data_ptr(), M, w.data_ptr(), M, N, 1, K, to.ctypes.data, b.data_ptr(), 0,
+                                     0, 0, out.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    ref = a_np.astype(np.float64) @ w_np.astype(np.float64).T + bias
+    err = np.abs(out.cpu().numpy() - ref).max()
+    assert err < 1e-4, f"tf32 GEMM with tf32-representable operands: max err {err}"
+    # un-rounded fp32 activations: the hardware drops the low mantissa bits (error ~2^-11 relative per element)
+    a2_np = rng.standard_normal((M, K)).astype(np.float32)
+    a2 = torch.from_numpy(a2_np).cuda()
+    _native.check(lib.kocr_test_gemm(2, a2.data_ptr(), M, w.data_ptr(), M, N, 1, K, to.ctypes.data, b.data_ptr(), 0,
+                                     0, 0, out.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    ref2 = a2_np.astype(np.float64) @ w_np.astype(np.float64).T + bias
+    rel = np.linalg.norm(out.cpu().numpy() - ref2) / np.linalg.norm(ref2)
+    assert rel < 1e-3, f"tf32 GEMM with fp32 activations: relative error {rel}"
