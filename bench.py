@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--straggler-threshold", type=int, default=8,
+                    help="a step returns once <= this many of its 256 lines are still decoding; they are pooled")
     ap.add_argument("--big-gemm-sms", type=int, default=0,
                     help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs)")
     ap.add_argument("--in-flight", type=int, default=4,
@@ -192,6 +194,7 @@ def main():
             self.tok_host = torch.zeros((LINES_PER_STEP, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
             self.len_host = torch.zeros(LINES_PER_STEP, dtype=torch.int32).pin_memory()
             self.tok_np, self.len_np = self.tok_host.numpy(), self.len_host.numpy()
+            self.pool, self.n_stragglers, self.n_flushes = [], 0, 0
             self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
             self.batch_host.__dict__.update(self.batch.__dict__)
             self.batch_host.pixels = self.pix_host.numpy()
@@ -199,12 +202,32 @@ def main():
                 self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
             self.n_chunks = int(self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr()).sum())
 
+        # Long tail: a step returns once <= 8 of the 256 lines are still decoding; those stragglers are pooled and
+        # decoded to the end in batches of up to 256 (flush), inside the timed region.  Same results, see predictor.py.
+        def _collect(self):
+            todo = np.nonzero(self.rec.unfinished(LINES_PER_STEP))[0]
+            self.pool.extend(self.imgs[i] for i in todo)
+            self.n_stragglers += len(todo)
+            if len(self.pool) >= LINES_PER_STEP:
+                self.flush()
+
+        def flush(self):
+            while self.pool:
+                part, self.pool = self.pool[:LINES_PER_STEP], self.pool[LINES_PER_STEP:]
+                self.rec.set_option("straggler_threshold", 0)
+                self.rec.recognize_lines(_native.LineBatch(part))
+                self.n_flushes += 1
+
         def step_resident(self):
+            self.rec.set_option("straggler_threshold", args.straggler_threshold)
             self.rec.recognize_lines(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr(), tokens_out=self.tok_np,
                                      lengths_out=self.len_np)
+            self._collect()
 
         def step_e2e(self):       # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
+            self.rec.set_option("straggler_threshold", args.straggler_threshold)
             self.rec.recognize_lines(self.batch_host, tokens_out=self.tok_np, lengths_out=self.len_np)
+            self._collect()
 
     workers = [Worker(w) for w in range(S)]
     n_chunks = workers[0].n_chunks
@@ -234,6 +257,7 @@ def main():
                             return
                         counter["next"] = i + 1
                     fn()
+                wk.flush()          # decode this worker's pooled stragglers to the end (inside the timed region)
             except Exception as e:  # surface worker failures instead of hanging
                 errors.append(e)
 
@@ -275,14 +299,17 @@ def main():
     ms_e2e, wall_e2e = timed("e2e", args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    mean_len = float(np.mean([wk.len_np.mean() for wk in workers]))
+    for wk in workers:          # one plain full-length step each for the length statistics
+        wk.rec.set_option("straggler_threshold", 0)
+    workers[0].rec.recognize_lines(workers[0].batch, tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
+    mean_len = float(workers[0].len_np.mean())
     decode_steps = int(rec.debug_read("last_steps"))
 
     # ---- single in-flight latency of one step (for context)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(3):
-        workers[0].step_e2e()
+    for _ in range(3):          # full-length decode of every line (no straggler hand-off)
+        workers[0].rec.recognize_lines(workers[0].batch_host, tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
     lat_ms = (time.perf_counter() - t0) * 1e3 / 3
 
     # ---- instrumented pass: CUDA events around every launch of stages 2-5a (roofline evidence),
@@ -325,6 +352,9 @@ def main():
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
                        "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S, "big_gemm_sms": args.big_gemm_sms,
+                       "straggler_threshold": args.straggler_threshold,
+                       "stragglers_pooled": int(sum(wk.n_stragglers for wk in workers)),
+                       "straggler_batches": int(sum(wk.n_flushes for wk in workers)),
                        "single_in_flight_e2e_ms_per_step": lat_ms, "wall_ms_resident": wall_res, "wall_ms_e2e": wall_e2e,
                        "l2": "per-step working set (~1.6 MB of activations per chunk, >3 GB per step) exceeds the 126 MB L2",
                        "parallelism": f"lines sharded over {world} GPU(s), no data-path collective"},

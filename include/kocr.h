@@ -84,8 +84,14 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
 /* Options (tests / parity tooling):
  *   "trace_logits"  1 -> decode_greedy records the last-position logits of every step
  *   "force_tokens"  1 -> decode_greedy feeds the ids set with kocr_set_forced_tokens instead of its argmax
+ *   "straggler_threshold" n -> see kocr_read_unfinished;  "lstm_impl" 0/1, "use_graphs" 0/1, "big_gemm_sms" n: tuning knobs
  *   "kernel_timing" 1 -> per-launch CUDA-event timing (see kocr_read_kernel_timing); setting it clears the totals */
 int kocr_set_option(kocr_handle* h, const char* name, int value);
+/* Long-tail handling.  With option "straggler_threshold" = n > 0, kocr_decode_greedy / kocr_recognize_lines return as
+ * soon as at most n lines are still decoding (checked every 8 positions).  flags_out[i] = 1 marks the lines whose
+ * row is incomplete; the caller re-submits those lines in a later batch (greedy decoding is deterministic, so the
+ * result is the same as decoding them to the end here).  Host int32 [n_lines]. */
+int kocr_read_unfinished(kocr_handle* h, int32_t* flags_out);
 /* With option "kernel_timing" = 1 every launch of the one-time stages (2-5a) is bracketed by CUDA events
  * on its stream.  This call synchronises and writes one line per launch site:
  * "<site> <total ms> <launches> <algorithmic FLOPs summed over those launches>\n". */

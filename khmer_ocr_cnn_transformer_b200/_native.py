@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished",
 ]
 
 _lib = None
@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.kocr_set_forced_tokens.argtypes = [vp, vp, i32]
     lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.kocr_read_unfinished.argtypes = [vp, vp]
+    lib.kocr_read_unfinished.restype = i32
     lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
     lib.kocr_read_kernel_timing.restype = i32
     lib.kocr_launch_count.restype = i64
@@ -178,6 +180,12 @@ class Recognizer:
         out = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
         check(self.lib.kocr_debug_read(self._h, name.encode(), _ptr(out), out.nbytes, C.byref(n)))
         return out
+
+    def unfinished(self, n_lines: int) -> np.ndarray:
+        """Flags of the lines left incomplete by an early return (option "straggler_threshold")."""
+        flags = np.zeros(max(n_lines, 1), np.int32)
+        check(self.lib.kocr_read_unfinished(self._h, _ptr(flags)))
+        return flags[:n_lines]
 
     def kernel_timing(self) -> dict:
         """{site: {"ms": total, "launches": n, "flops": algorithmic FLOPs over those launches}}"""

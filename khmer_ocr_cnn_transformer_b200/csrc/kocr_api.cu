@@ -65,6 +65,8 @@ struct kocr_handle {
     EncLayerW enc[2];
     const float* global_pos;
     const __nv_bfloat16 *lstm_w_ih, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
+    int straggler_threshold = 0; // >0: decode_greedy returns early once <= this many lines are still active;
+                                 // the caller re-submits those lines (kocr_read_unfinished) in a later batch
     int big_gemm_sms = 0;        // >0: persistent grid size of the stage 2-5a GEMMs (leave SMs to other streams)
     int lstm_impl = 1;           // 1 = tensor-core recurrence (mma fragments in registers), 0 = CUDA-core / SMEM weights
     const float *dec_tok_emb, *dec_pos;
@@ -80,6 +82,7 @@ struct kocr_handle {
     size_t staging_bytes = 0;
     cudaEvent_t staging_done = nullptr;
     int32_t* pinned_flag = nullptr;    // pinned int for early-exit polling
+    int32_t* fin_host = nullptr;       // pinned copy of the per-line finished flags of the last decode
     // batch state
     int n_lines = 0, n_chunks = 0, n_tok = 0, max_T = 0, n_groups = 0, max_new_w = 0;
     std::vector<int> line_T, line_first_chunk, line_n_chunks;
@@ -237,6 +240,7 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaMallocHost(&h->staging_host, h->staging_bytes));
     KOCR_CUDA(cudaMalloc(&h->staging_dev, h->staging_bytes));
     KOCR_CUDA(cudaMallocHost(&h->pinned_flag, 64));
+    KOCR_CUDA(cudaMallocHost(&h->fin_host, (size_t)h->max_lines * 4));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming));
     KOCR_CUDA(cudaStreamCreate(&h->own_stream));
     return 0;
@@ -572,6 +576,7 @@ int kocr_destroy(kocr_handle* h) {
     if (h->staging_host) cudaFreeHost(h->staging_host);
     if (h->staging_dev) cudaFree(h->staging_dev);
     if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
+    if (h->fin_host) cudaFreeHost(h->fin_host);
     if (h->staging_done) cudaEventDestroy(h->staging_done);
     for (auto& g : h->dec_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -739,12 +744,13 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         if (!forcing && done < max_steps) {
             KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
             KOCR_CUDA(cudaStreamSynchronize(s));
-            if (*h->pinned_flag == 0) break;     // every line has emitted <eos>
+            if (*h->pinned_flag <= h->straggler_threshold) break;     // every line (or all but a few stragglers) has emitted <eos>
         }
     }
     h->last_steps = done;
     if (tokens_out) KOCR_CUDA(cudaMemcpyAsync(tokens_out, tokens, (size_t)L * KOCR_TOKENS_LD * 4, cudaMemcpyDeviceToHost, s));
     if (lengths_out) KOCR_CUDA(cudaMemcpyAsync(lengths_out, buf<int>(h, "lengths"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(cudaMemcpyAsync(h->fin_host, buf<int>(h, "finished"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
@@ -766,6 +772,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
+    if (strcmp(name, "straggler_threshold") == 0) { h->straggler_threshold = value; return 0; }
     if (strcmp(name, "kernel_timing") == 0) {
         h->kernel_timing = value;
         if (value) { h->sites.clear(); }
@@ -781,6 +788,14 @@ int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens, int n_lines) {
     KOCR_CUDA(cudaSetDevice(h->device));
     KOCR_CUDA(cudaMemcpy(buf<int>(h, "forced"), tokens, (size_t)n_lines * KOCR_TOKENS_LD * 4, cudaMemcpyHostToDevice));
     h->have_forced = true;
+    return 0;
+}
+
+int kocr_read_unfinished(kocr_handle* h, int32_t* flags_out) {
+    KOCR_CHECK(h != nullptr && flags_out != nullptr, "kocr_read_unfinished: null argument");
+    // a line is unfinished if it neither emitted <eos> nor used up all decode positions (host-only: the flags
+    // were copied to pinned memory at the end of kocr_decode_greedy)
+    for (int i = 0; i < h->n_lines; ++i) flags_out[i] = (h->fin_host[i] == 0 && h->last_steps < h->dec_max_len) ? 1 : 0;
     return 0;
 }
 

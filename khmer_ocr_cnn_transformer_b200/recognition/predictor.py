@@ -49,14 +49,34 @@ class OCRPredictor:
         return [self.tokenizer.decode([int(t) for t in tokens[i, :lengths[i]]]) for i in range(tokens.shape[0])]
 
     def _recognize_gray(self, grays):
-        """Greedy recognition of grey uint8 lines, batched to the handle's capacity."""
+        """Greedy recognition of grey uint8 lines, batched to the handle's capacity.
+
+        Long tail: a batch returns as soon as only a few lines (<= 1/32 of the batch) are still decoding; those
+        stragglers are collected and decoded together in a final pass, so one looping line does not hold 255
+        finished ones for up to 256 positions.  Greedy decoding is deterministic: results are unchanged."""
         results = [None] * len(grays)
         from ..scheduling import plan_batches
-        for idxs in plan_batches([g.shape for g in grays], self._max_lines, self._max_chunks, self.cfg.max_seq_len):
-            batch = LineBatch([grays[i] for i in idxs])
-            tokens, lengths = self.model.recognize_lines(batch, max_steps=self.cfg.decode_max_len)
-            for i, text in zip(idxs, self._decode_ids(tokens, lengths)):
-                results[i] = text
+
+        def run(indices, threshold):
+            stragglers = []
+            for idxs in plan_batches([grays[i].shape for i in indices], self._max_lines, self._max_chunks,
+                                     self.cfg.max_seq_len):
+                idxs = [indices[j] for j in idxs]
+                batch = LineBatch([grays[i] for i in idxs])
+                self.model.set_option("straggler_threshold", threshold(len(idxs)))
+                tokens, lengths = self.model.recognize_lines(batch, max_steps=self.cfg.decode_max_len)
+                todo = self.model.unfinished(len(idxs))
+                for j, (i, text) in enumerate(zip(idxs, self._decode_ids(tokens, lengths))):
+                    if todo[j]:
+                        stragglers.append(i)
+                    else:
+                        results[i] = text
+            return stragglers
+
+        left = run(list(range(len(grays))), lambda n: n // 32)
+        if left:
+            left = run(left, lambda n: 0)
+        assert not left
         return results
 
     def predict(self, image_input, beam_width: int = 3) -> str:
