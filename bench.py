@@ -118,6 +118,11 @@ def run_reference(args, rank, world):
     reference cannot travel to the GPU box), all host threads numpy/BLAS can use, same workload."""
     if rank != 0:
         return
+    try:        # torchrun exports OMP_NUM_THREADS=1; give BLAS every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     sd, wname = load_state_dict()
     imgs = make_batch(0)
     per_step = 2
@@ -290,6 +295,9 @@ def main():
 
     run_steps("resident", max(args.warmup, S))
     run_steps("e2e", max(args.warmup, S))
+    if world > 1:       # NCCL creates its communicator lazily on the first collective: do that outside the timed region
+        dist.gather(workers[0].tok_host.cuda(non_blocking=True), gathered, dst=0)
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -339,6 +347,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1:
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
         v, dt = cpu_oracle_lines_per_s(sd, workers[0].imgs, args.cpu_lines)
         cpu = {"value": v, "unit": "lines/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"first {args.cpu_lines} lines of the c2 batch through the numpy oracle ({dt:.1f} s)"}
