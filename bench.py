@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch in the decode loop")
     ap.add_argument("--straggler-threshold", type=int, default=8,
                     help="a step returns once <= this many of its 256 lines are still decoding; they are pooled")
     ap.add_argument("--big-gemm-sms", type=int, default=0,
@@ -203,6 +204,8 @@ def main():
             self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
             self.batch_host.__dict__.update(self.batch.__dict__)
             self.batch_host.pixels = self.pix_host.numpy()
+            if args.no_pdl:
+                self.rec.set_option("use_pdl", 0)
             if args.big_gemm_sms > 0 and S > 1:
                 self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
             self.n_chunks = int(self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr()).sum())

@@ -106,7 +106,9 @@ class LineBatch:
 class Recognizer:
     """Thin owner of a `kocr_handle` (one per GPU, one host thread)."""
 
-    DEBUG_DTYPES = {"chunks": np.float32, "enc": np.float32, "memory": np.float32, "logits_trace": np.float32}
+    DEBUG_DTYPES = {"chunks": np.float32, "enc": np.float32, "memory": np.float32, "logits_trace": np.float32,
+                    "dx": np.float32, "dy": np.float32, "daof": np.float32, "dq": np.float32, "dqkv": np.float32,
+                    "dh": np.float32, "logits": np.float32}
 
     def __init__(self, weight_blob: bytes, device: int = 0, max_lines: int = 256, max_chunks: int = 4096):
         self.lib = load_library()

@@ -41,6 +41,29 @@ const char* get_error();
     } while (0)
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Inside the decode loop every kernel is launched with the
+// programmatic-stream-serialization attribute: it may start (prologue: barrier init, TMEM alloc, descriptor
+// prefetch, smem carve-up) while its predecessor is still running, and blocks in pdl_wait() until the
+// predecessor has completed and its writes are visible.  Every kernel that can be launched this way calls
+// pdl_trigger() first and pdl_wait() before touching global memory; both are no-ops for a normal launch.
+// ------------------------------------------------------------------------------------------
+bool pdl_active();               // true while the calling thread is enqueueing a PDL chain (decode step)
+void pdl_set_active(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_active() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // Geometry of a "padded-linear" NHWC activation:
 // per chunk (H+1) rows of pitch P = W+1 positions; position (h, w) with h == H or w == W is a
 // zero pad, shared by the neighbouring row / chunk, so that a 3x3 tap is a pure row shift.
@@ -56,6 +79,8 @@ __host__ __device__ inline PLGeom make_pl(int H, int W) {
 // Device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

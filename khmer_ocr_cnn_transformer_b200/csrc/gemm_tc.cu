@@ -21,7 +21,7 @@ template <int BN> struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = (BN == 256) ? 4 : 6;          // 192 KB of operands
+    static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);   // 192 KB of operands
     static constexpr int TMEM_COLS = 2 * BN;                    // 256 / 512
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -30,6 +30,7 @@ struct GemmKernelParams {
     int M, N, taps, cin_blocks;      // cin_blocks = cin / 64
     int tap_off[9];
     int num_m_tiles, num_n_tiles;
+    int split_k, kb_per_split;       // tile index = (m_tile * num_n_tiles + n_tile) * split_k + slice
     GemmEpilogue ep;
 };
 
@@ -50,6 +51,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();            // a dependent (PDL-launched) kernel may begin its own prologue now
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -63,19 +65,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();               // PDL: the producer of our operands (previous kernel in the stream) has completed
 
     constexpr int BKE = TF32 ? 32 : 64;           // K elements per 128-byte row
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int num_kb = p.taps * p.cin_blocks;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+    const int total_kb = p.taps * p.cin_blocks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.num_n_tiles) * BM;
-                const int n0 = (tile % p.num_n_tiles) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int mn = tile / p.split_k, sp = tile - mn * p.split_k;
+                const int m0 = (mn / p.num_n_tiles) * BM;
+                const int n0 = (mn % p.num_n_tiles) * BN;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     const int tap = kb / p.cin_blocks;
                     const int cb = kb - tap * p.cin_blocks;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -99,6 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
+            const int sp = tile % p.split_k;
+            const int kb0 = sp * p.kb_per_split, num_kb = min(total_kb, kb0 + p.kb_per_split) - kb0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -128,8 +135,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / p.num_n_tiles) * BM;
-            const int n0 = (tile % p.num_n_tiles) * BN;
+            const int mn = tile / p.split_k, sp = tile - mn * p.split_k;
+            const int m0 = (mn / p.num_n_tiles) * BM;
+            const int n0 = (mn % p.num_n_tiles) * BN;
             const long row = (long)m0 + row_in_tile;
             const bool in_range = row < p.M;
             bool valid = in_range;
@@ -167,18 +175,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (add_row) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(add_row + c * 32 + j));
+                        // .cg (L2) load: the addend may have been written by the immediately preceding kernel (PDL)
+                        const float4 a = __ldcg(reinterpret_cast<const float4*>(add_row + c * 32 + j));
                         f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
                     }
                 }
+                // activation: the (warp-uniform) mode is tested OUTSIDE the unrolled loops so that the sigmoid's
+                // MUFU work is not if-converted into every GEMM's epilogue
+                if (ep.relu == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (ep.relu == 1) f[j] = fmaxf(f[j], 0.f);
-                    else if (ep.relu == 2) f[j] = 1.f / (1.f + __expf(-f[j]));
-                    if (!valid) f[j] = 0.f;
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (ep.relu == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + __expf(-f[j]));
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
                 }
                 if (ep.out_f32) {
-                    float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + n0 + c * 32);
+                    float4* o = reinterpret_cast<float4*>(ep.out_f32 + ((long)sp * p.M + row) * ep.ld_f32 + n0 + c * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
@@ -310,6 +326,14 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     for (int i = 0; i < 9; ++i) kp.tap_off[i] = i < p.taps ? p.tap_off[i] : 0;
     kp.num_m_tiles = (p.M + BM - 1) / BM;
     kp.num_n_tiles = p.N / BN;
+    kp.split_k = p.split_k > 1 ? p.split_k : 1;
+    const int total_kb = kp.taps * kp.cin_blocks;
+    KOCR_CHECK(kp.split_k <= total_kb, "gemm: split_k %d exceeds the %d K blocks", kp.split_k, total_kb);
+    kp.kb_per_split = (total_kb + kp.split_k - 1) / kp.split_k;
+    KOCR_CHECK((kp.split_k - 1) * kp.kb_per_split < total_kb, "gemm: split_k %d leaves an empty K slice", kp.split_k);
+    if (kp.split_k > 1)
+        KOCR_CHECK(p.taps == 1 && p.ep.out_f32 && !p.ep.out_bf16 && !p.ep.bias && !p.ep.addend && !p.ep.relu && p.ep.pl_S == 0,
+                   "gemm: split-K writes raw fp32 partial sums only");
     kp.ep = p.ep;
     return 0;
 }
@@ -329,22 +353,26 @@ static int launch_impl(const void* a, long rowsA, const void* w, const GemmProbl
         KOCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = kp.num_m_tiles * kp.num_n_tiles;
+    const int tiles = kp.num_m_tiles * kp.num_n_tiles * kp.split_k;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<BN, TF32><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
-    KOCR_CUDA(cudaGetLastError());
+    KOCR_CUDA(launch_kernel(gemm_tc_kernel<BN, TF32>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, kp));
     ++g_gemm_launches;
     return 0;
 }
 
 int launch_gemm_tc(const void* a, long rowsA, const void* w, const GemmProblem& p, int num_sms,
                    cudaStream_t stream) {
+    const int bn = p.bn > 0 ? p.bn : (p.N % 256 == 0 ? 256 : 128);
     if (p.tf32) {
-        if (p.N % 256 == 0) return launch_impl<256, true>(a, rowsA, w, p, num_sms, stream);
-        return launch_impl<128, true>(a, rowsA, w, p, num_sms, stream);
+        if (bn == 256) return launch_impl<256, true>(a, rowsA, w, p, num_sms, stream);
+        if (bn == 128) return launch_impl<128, true>(a, rowsA, w, p, num_sms, stream);
+        if (bn == 64) return launch_impl<64, true>(a, rowsA, w, p, num_sms, stream);
+    } else {
+        if (bn == 256) return launch_impl<256, false>(a, rowsA, w, p, num_sms, stream);
+        if (bn == 128) return launch_impl<128, false>(a, rowsA, w, p, num_sms, stream);
     }
-    if (p.N % 256 == 0) return launch_impl<256, false>(a, rowsA, w, p, num_sms, stream);
-    return launch_impl<128, false>(a, rowsA, w, p, num_sms, stream);
+    KOCR_CHECK(false, "gemm: unsupported N tile %d", bn);
+    return 2;
 }
 
 int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p,

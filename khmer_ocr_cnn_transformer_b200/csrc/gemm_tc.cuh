@@ -35,6 +35,10 @@ struct GemmProblem {
     int taps;                 // 1 (linear) or 9 (3x3 conv)
     int cin;                  // K per tap in elements (multiple of 64 for bf16, of 32 for tf32)
     int tf32;                 // 0: bf16 operands (kind::f16), 1: fp32 operands consumed as TF32 (kind::tf32)
+    int split_k;              // <= 1: whole K per tile.  s > 1 (linear, fp32 output only): K is cut into s slices, slice i
+                              // writes its raw partial sums to out_f32 + i*M*ld_f32 (no bias/addend/activation: the
+                              // consumer adds the slices).  Used by the decode loop to spread tiny GEMMs over many SMs.
+    int bn;                   // N tile override (64, 128, 256); 0 = 256 if N % 256 == 0 else 128
     int tap_off[9];           // row shift per tap
     GemmEpilogue ep;
 };

@@ -51,9 +51,11 @@ int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_b
 // per-chunk 32-token, 8-head attention: qkv bf16 [M, 1152] -> out bf16 [M, 384].
 int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
 // LayerNorm over 384: y = LN(x)*g + b (+ pos[row_pos[row]]); writes f32 and/or bf16 (+ residual lo part).
+// Input row = sum of nsplit split-K partials (x + s*rows*384) + in_bias + resid (optional).
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
                      float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int nsplit = 1, const float* in_bias = nullptr,
+                     const float* resid = nullptr);
 // f32 [rows, 384] (+ pos[row_pos[row]]) -> f32 + bf16 copies (VGG merge path without LN).
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
                    __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream);
@@ -79,13 +81,14 @@ int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base,
                      cudaStream_t stream);
 int launch_dec_self_attn(const float* qkv /*[L,1152]*/, __nv_bfloat16* kcache,
                          __nv_bfloat16* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
-                         int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream);
+                         int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream,
+                         int nsplit, const float* bias);
 int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,
                           const int* line_tok_off, const int* line_T, int max_T, const int* finished,
-                          float* out, int n_lines, cudaStream_t stream);
+                          float* out, int n_lines, cudaStream_t stream, int nsplit, const float* bias);
 int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,
                       const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int nsplit, const float* bias);
 int launch_dec_bump(int* step_base, int n, cudaStream_t stream);
 
 }  // namespace kocr

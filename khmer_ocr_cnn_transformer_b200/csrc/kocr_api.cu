@@ -24,6 +24,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static thread_local bool g_pdl = false;
+bool pdl_active() { return g_pdl; }
+void pdl_set_active(bool on) { g_pdl = on; }
+
 static std::atomic<int64_t> g_launches{0};     // non-GEMM kernel launches (GEMM launches are counted in gemm_tc.cu)
 
 // ---- packed weight blob ---------------------------------------------------------------
@@ -96,6 +100,8 @@ struct kocr_handle {
     std::map<std::tuple<int, int, int, int>, DecGraph> dec_graphs;   // (n_lines, max_T bucket, trace, force)
     bool decode_warmed = false;
     int use_graphs = 1;
+    int use_pdl = 1;             // programmatic dependent launch inside the decode loop
+    int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
     // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
     int kernel_timing = 0;
     struct Site { std::string name; double flops = 0; double ms = 0; int count = 0; };
@@ -221,6 +227,7 @@ int carve_workspace(kocr_handle* h) {
         {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4}, {"step_base", 64},
         {"dx", L * D * 4}, {"dxb", L * D * 2}, {"dqkv", L * 3 * D * 4}, {"dao", L * D * 2}, {"dy", L * D * 4},
         {"dq", L * D * 4}, {"dh", L * 4 * D * 4}, {"daof", L * D * 4}, {"logits", L * VOCAB_PAD * 4},
+        {"dparts", 8 * L * 3 * D * 4},
         {"kcache", 2 * L * DEC_MAX * D * 2}, {"vcache", 2 * L * DEC_MAX * D * 2},
     };
     size_t total = 0;
@@ -411,55 +418,64 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
     return 0;
 }
 
+// Decoder GEMM for a handful of rows: TF32, 128x64 tiles and split-K so that ~50-100 CTAs each stream one
+// pipeline-fill of operands (the kernel is a latency chain, not a throughput problem); the slices are written
+// as raw partial sums [split][L][N] and added up (with bias / residual) by the consuming kernel.
+int gemm_dec(kocr_handle* h, const float* a, int L, const float* w, int N, int K, int split, float* parts,
+             cudaStream_t s) {
+    GemmProblem p;
+    memset(&p, 0, sizeof p);
+    p.M = L; p.N = N; p.taps = 1; p.cin = K; p.tf32 = 1; p.split_k = split; p.bn = 64;
+    p.ep.out_f32 = parts; p.ep.ld_f32 = N;
+    return launch_gemm_tc(a, L, w, p, h->num_sms, s);
+}
+
 // One generated position for every line of the batch; the position is *step_base + off (device side).
 // Decoder GEMMs run on the tensor cores in TF32 (fp32 operands): with bf16 operands ~7 % of the lines of the
 // fixture batch decode to a different sequence than the fp32 reference, with TF32 the flips disappear.
 int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     const int L = h->n_lines;
     const int D = D_MODEL;
+    int n_launched = 0;
+#define DSTEP(call) do { if (h->debug_stop <= 0 || n_launched < h->debug_stop) { KOCR_TRY(call); } ++n_launched; } while (0)
     int* tokens = buf<int>(h, "tokens");
     const int* sb = buf<int>(h, "step_base");
     const int* fin = buf<int>(h, "finished");
-    float* dx = buf<float>(h, "dx"); float* dy = buf<float>(h, "dy");
+    float* dx = buf<float>(h, "dx");
+    float* parts = buf<float>(h, "dparts");          // split-K partial results of the current projection
     float* dao = buf<float>(h, "daof");
     float* dh = buf<float>(h, "dh");
-    KOCR_TRY(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
+    const int S2 = 2, S8 = 8;                        // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8 slices
+    DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         __nv_bfloat16* kc = buf<__nv_bfloat16>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         __nv_bfloat16* vc = buf<__nv_bfloat16>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        GemmEpilogue e = ep_none();
-        e.bias = w.sa_in_b; e.out_f32 = buf<float>(h, "dqkv"); e.ld_f32 = 3 * D;
-        KOCR_TRY(gemm_linear(h, dx, L, w.sa_in_w, 3 * D, D, e, s, 1));
-        KOCR_TRY(launch_dec_self_attn(buf<float>(h, "dqkv"), kc, vc, tokens, sb, off, fin, dao, L, s)); ++g_launches;
-        e = ep_none();
-        e.bias = w.sa_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
-        KOCR_TRY(gemm_linear(h, dao, L, w.sa_out_w, D, D, e, s, 1));
-        KOCR_TRY(launch_layernorm(dy, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s)); ++g_launches;
-        e = ep_none();
-        e.bias = w.ca_q_b; e.out_f32 = buf<float>(h, "dq"); e.ld_f32 = D;
-        KOCR_TRY(gemm_linear(h, dx, L, w.ca_q_w, D, D, e, s, 1));
-        KOCR_TRY(launch_dec_cross_attn(buf<float>(h, "dq"), buf<__nv_bfloat16>(h, "kv"), l, h->d_line_tok_off,
-                                       h->d_line_T, max_T, fin, dao, L, s)); ++g_launches;
-        e = ep_none();
-        e.bias = w.ca_out_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
-        KOCR_TRY(gemm_linear(h, dao, L, w.ca_out_w, D, D, e, s, 1));
-        KOCR_TRY(launch_layernorm(dy, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s)); ++g_launches;
-        e = ep_none();
-        e.bias = w.l1_b; e.relu = 1; e.out_f32 = dh; e.ld_f32 = 4 * D;
-        KOCR_TRY(gemm_linear(h, dx, L, w.l1_w, 4 * D, D, e, s, 1));
-        e = ep_none();
-        e.bias = w.l2_b; e.addend = dx; e.ld_add = D; e.out_f32 = dy; e.ld_f32 = D;
-        KOCR_TRY(gemm_linear(h, dh, L, w.l2_w, D, 4 * D, e, s, 1));
-        KOCR_TRY(launch_layernorm(dy, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s)); ++g_launches;
+        DSTEP(gemm_dec(h, dx, L, w.sa_in_w, 3 * D, D, S2, parts, s));
+        DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches;
+        DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
+        DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx)); ++g_launches;
+        DSTEP(gemm_dec(h, dx, L, w.ca_q_w, D, D, S2, parts, s));
+        DSTEP(launch_dec_cross_attn(parts, buf<__nv_bfloat16>(h, "kv"), l, h->d_line_tok_off, h->d_line_T, max_T, fin,
+                                    dao, L, s, S2, w.ca_q_b)); ++g_launches;
+        DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s));
+        DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx)); ++g_launches;
+        {   // FFN1 keeps its ReLU epilogue (no split): N = 1536 already gives 48 CTAs
+            GemmProblem p;
+            memset(&p, 0, sizeof p);
+            p.M = L; p.N = 4 * D; p.taps = 1; p.cin = D; p.tf32 = 1; p.bn = 64;
+            p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D;
+            DSTEP(launch_gemm_tc(dx, L, w.l1_w, p, h->num_sms, s));
+        }
+        DSTEP(gemm_dec(h, dh, L, w.l2_w, D, 4 * D, S8, parts, s));
+        DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx)); ++g_launches;
     }
-    GemmEpilogue e = ep_none();
-    e.bias = h->dec_out_b; e.out_f32 = buf<float>(h, "logits"); e.ld_f32 = VOCAB_PAD;
-    KOCR_TRY(gemm_linear(h, dx, L, h->dec_out_w, VOCAB_PAD, D, e, s, 1));
+    DSTEP(gemm_dec(h, dx, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s));
     const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
     float* trace = h->trace_logits ? reinterpret_cast<float*>(h->trace.p) : nullptr;
-    KOCR_TRY(launch_dec_argmax(buf<float>(h, "logits"), tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"),
-                               buf<int>(h, "n_active"), sb, off, L, forced, trace, s)); ++g_launches;
+    DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,
+                            off, L, forced, trace, s, S2, h->dec_out_b)); ++g_launches;
+#undef DSTEP
     return 0;
 }
 
@@ -467,6 +483,7 @@ static const int DEC_GROUP = 8;     // positions per captured graph / per early-
 
 // `n` consecutive positions followed by the step_base bump, eagerly on stream s.
 int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
+    struct PdlScope { PdlScope(bool on) { pdl_set_active(on); } ~PdlScope() { pdl_set_active(false); } } scope(h->use_pdl != 0);
     for (int i = 0; i < n; ++i) KOCR_TRY(decode_step(h, i, max_T, s));
     KOCR_TRY(launch_dec_bump(buf<int>(h, "step_base"), n, s)); ++g_launches;
     return 0;
@@ -474,7 +491,7 @@ int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
 
 // The same 8 positions as one CUDA graph (captured once per (n_lines, max_T bucket, options)).
 int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
-    auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits, (h->force_tokens && h->have_forced) ? 1 : 0);
+    auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits * 2 + h->use_pdl, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
         const int64_t before = g_launches.load() + gemm_tc_launch_count();
@@ -770,6 +787,8 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "trace_logits") == 0) { h->trace_logits = value; return 0; }
     if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
+    if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
+    if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
     if (strcmp(name, "straggler_threshold") == 0) { h->straggler_threshold = value; return 0; }
@@ -842,6 +861,10 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
     else if (n == "patch_in") { src = h->named["patch_in"].p; bytes = M * 1024 * 2; }
     else if (n == "enc") { src = h->named["x"].p; bytes = M * D_MODEL * 4; }
     else if (n == "memory") { src = h->named[h->variant == 0 ? "mem" : "x"].p; bytes = M * D_MODEL * 4; }
+    else if (n == "dx" || n == "dy" || n == "daof" || n == "dq") { src = h->named[n].p; bytes = (size_t)h->n_lines * D_MODEL * 4; }
+    else if (n == "dqkv") { src = h->named[n].p; bytes = (size_t)h->n_lines * 3 * D_MODEL * 4; }
+    else if (n == "dh") { src = h->named[n].p; bytes = (size_t)h->n_lines * 4 * D_MODEL * 4; }
+    else if (n == "logits") { src = h->named[n].p; bytes = (size_t)h->n_lines * VOCAB_PAD * 4; }
     else if (n == "logits_trace") { src = h->trace.p; bytes = (size_t)h->n_lines * DEC_MAX * VOCAB_PAD * 4; }
     else if (n == "last_steps") { if (bytes_out) *bytes_out = (size_t)h->last_steps; return 0; }
     KOCR_CHECK(src != nullptr, "kocr_debug_read: unknown or empty buffer '%s'", name);

@@ -117,18 +117,37 @@ __device__ __forceinline__ void store_row_outputs(const float (&y)[12], long row
     }
 }
 
+// Input row = sum of `nsplit` split-K partial results (x + s*rows*384) + in_bias + residual (each optional).
 template <bool DO_LN>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ b, const float* __restrict__ pos,
                                                         const int* __restrict__ row_pos, float* out_f32,
-                                                        __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo, int rows) {
+                                                        __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo, int rows,
+                                                        int nsplit, const float* __restrict__ in_bias,
+                                                        const float* resid) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     float v[12];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const float4 a = *reinterpret_cast<const float4*>(x + row * D_MODEL + j * 128 + lane * 4);
+        // ld.global.cg: under PDL this kernel may be resident before its producer finishes, so data written by the
+        // producer must not be read through L1 / the non-coherent path (stale lines from an earlier step)
+        float4 a = __ldcg(reinterpret_cast<const float4*>(x + row * D_MODEL + j * 128 + lane * 4));
+        for (int sp = 1; sp < nsplit; ++sp) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(x + ((long)sp * rows + row) * D_MODEL + j * 128 + lane * 4));
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (in_bias) {
+            const float4 p = *reinterpret_cast<const float4*>(in_bias + j * 128 + lane * 4);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (resid) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(resid + row * D_MODEL + j * 128 + lane * 4));
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
         v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
     }
     if (DO_LN) {
@@ -163,17 +182,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
                      float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int nsplit, const float* in_bias, const float* resid) {
     if (rows == 0) return 0;
-    layernorm_kernel<true><<<(rows + 7) / 8, 256, 0, stream>>>(x, g, b, pos, row_pos, out_f32, out_bf16, out_bf16_lo, rows);
-    KOCR_CUDA(cudaGetLastError());
+    KOCR_CUDA(launch_kernel(layernorm_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, stream, x, g, b, pos, row_pos,
+                            out_f32, out_bf16, out_bf16_lo, rows, nsplit, in_bias, resid));
     return 0;
 }
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
                    __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream) {
     if (rows == 0) return 0;
     layernorm_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(x, nullptr, nullptr, pos, row_pos, out_f32, out_bf16,
-                                                                out_bf16_lo, rows);
+                                                                out_bf16_lo, rows, 1, nullptr, nullptr);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -481,10 +500,12 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __re
                                  const float* __restrict__ pos_emb, float* __restrict__ x,
                                  __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xb_lo, int n_lines) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // n_lines * 96 float4
+    pdl_trigger();
+    pdl_wait();
     if (idx >= n_lines * (D_MODEL / 4)) return;
     const int l = idx / (D_MODEL / 4), c4 = idx - l * (D_MODEL / 4);
-    const int t = *step_base + step_off;
-    const int tok = tokens[l * TOK_LD + t];
+    const int t = __ldcg(step_base) + step_off;
+    const int tok = __ldcg(tokens + l * TOK_LD + t);
     const float4 e = reinterpret_cast<const float4*>(tok_emb + (long)tok * D_MODEL)[c4];
     const float4 p = reinterpret_cast<const float4*>(pos_emb + (long)t * D_MODEL)[c4];
     const float4 v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
@@ -501,9 +522,8 @@ int launch_dec_embed(const int* tokens, const int* step_base, int step_off, cons
                      const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
                      cudaStream_t stream) {
     const int total = n_lines * (D_MODEL / 4);
-    dec_embed_kernel<<<(total + 255) / 256, 256, 0, stream>>>(tokens, step_base, step_off, tok_emb, pos_emb, x, xb,
-                                                              xb_lo, n_lines);
-    KOCR_CUDA(cudaGetLastError());
+    KOCR_CUDA(launch_kernel(dec_embed_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, tokens, step_base, step_off,
+                            tok_emb, pos_emb, x, xb, xb_lo, n_lines));
     return 0;
 }
 
@@ -517,19 +537,27 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
                                                             const int* __restrict__ tokens,
                                                             const int* __restrict__ step_base, int step_off,
                                                             const int* __restrict__ finished,
-                                                            float* __restrict__ out) {
+                                                            float* __restrict__ out, int nsplit, int n_lines,
+                                                            const float* __restrict__ bias) {
     __shared__ float s_q[D_MODEL];
     __shared__ float s_p[N_HEAD][DEC_MAX];
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (finished[l]) return;                      // line already emitted <eos>: nothing downstream reads it
-    const int t = *step_base + step_off;
+    pdl_trigger();
+    pdl_wait();
+    if (__ldcg(finished + l)) return;             // line already emitted <eos>: nothing downstream reads it
+    const int t = __ldcg(step_base) + step_off;
     const float* row = qkv + (long)l * 3 * D_MODEL;
     __nv_bfloat16* kc = kcache + (long)l * DEC_MAX * D_MODEL;
     __nv_bfloat16* vc = vcache + (long)l * DEC_MAX * D_MODEL;
     for (int i = tid; i < D_MODEL; i += blockDim.x) {
-        s_q[i] = row[i] * rsqrtf((float)HEAD_DIM);
-        kc[(long)t * D_MODEL + i] = __float2bfloat16_rn(row[D_MODEL + i]);
-        vc[(long)t * D_MODEL + i] = __float2bfloat16_rn(row[2 * D_MODEL + i]);
+        float qv = bias[i], kv_ = bias[D_MODEL + i], vv = bias[2 * D_MODEL + i];
+        for (int sp = 0; sp < nsplit; ++sp) {               // sum the split-K partial results of the QKV projection
+            const float* r = row + (long)sp * n_lines * 3 * D_MODEL;
+            qv += __ldcg(r + i); kv_ += __ldcg(r + D_MODEL + i); vv += __ldcg(r + 2 * D_MODEL + i);
+        }
+        s_q[i] = qv * rsqrtf((float)HEAD_DIM);
+        kc[(long)t * D_MODEL + i] = __float2bfloat16_rn(kv_);
+        vc[(long)t * D_MODEL + i] = __float2bfloat16_rn(vv);
     }
     __syncthreads();
     const int nk = t + 1;
@@ -537,12 +565,12 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     float mx = -INFINITY;
     for (int j = lane; j < nk; j += 32) {
         float acc = -INFINITY;
-        if (tokens[l * TOK_LD + j] != 0) {
+        if (__ldcg(tokens + l * TOK_LD + j) != 0) {
             const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)j * D_MODEL + warp * HEAD_DIM);
             acc = 0.f;
 #pragma unroll
             for (int i = 0; i < HEAD_DIM / 8; ++i) {
-                const uint4 k8 = kp[i];
+                const uint4 k8 = __ldcg(kp + i);
                 acc = fmaf(qh[8 * i], bf16_lo(k8.x), acc); acc = fmaf(qh[8 * i + 1], bf16_hi(k8.x), acc);
                 acc = fmaf(qh[8 * i + 2], bf16_lo(k8.y), acc); acc = fmaf(qh[8 * i + 3], bf16_hi(k8.y), acc);
                 acc = fmaf(qh[8 * i + 4], bf16_lo(k8.z), acc); acc = fmaf(qh[8 * i + 5], bf16_hi(k8.z), acc);
@@ -566,7 +594,7 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
         float o0 = 0.f, o1 = 0.f;
         const uint32_t* vp = reinterpret_cast<const uint32_t*>(vc + warp * HEAD_DIM) + lane;
         for (int j = 0; j < nk; ++j) {
-            const uint32_t v2 = vp[(long)j * (D_MODEL / 2)];
+            const uint32_t v2 = __ldcg(vp + (long)j * (D_MODEL / 2));
             o0 = fmaf(s_p[warp][j], bf16_lo(v2), o0);
             o1 = fmaf(s_p[warp][j], bf16_hi(v2), o1);
         }
@@ -578,9 +606,9 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
 
 int launch_dec_self_attn(const float* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* tokens,
                          const int* step_base, int step_off, const int* finished, float* out, int n_lines,
-                         cudaStream_t stream) {
-    dec_self_attn_kernel<<<n_lines, 256, 0, stream>>>(qkv, kcache, vcache, tokens, step_base, step_off, finished, out);
-    KOCR_CUDA(cudaGetLastError());
+                         cudaStream_t stream, int nsplit, const float* bias) {
+    KOCR_CUDA(launch_kernel(dec_self_attn_kernel, dim3(n_lines), dim3(256), 0, stream, qkv, kcache, vcache, tokens,
+                            step_base, step_off, finished, out, nsplit, n_lines, bias));
     return 0;
 }
 
@@ -593,10 +621,13 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
                                                              const int* __restrict__ line_tok_off,
                                                              const int* __restrict__ line_T, int max_T,
                                                              const int* __restrict__ finished,
-                                                             float* __restrict__ out) {
+                                                             float* __restrict__ out, int nsplit, int n_lines,
+                                                             const float* __restrict__ bias) {
     extern __shared__ __align__(16) float s_dyn[];       // [8 heads][max_T] scores | [8 warps][384] partial outputs
     const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (finished[l]) return;
+    pdl_trigger();
+    pdl_wait();
+    if (__ldcg(finished + l)) return;
     float* s_p = s_dyn;
     float* s_o = s_dyn + (long)N_HEAD * max_T;
     __shared__ float s_inv[N_HEAD];
@@ -609,7 +640,15 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
     {
         const float sc = rsqrtf((float)HEAD_DIM);
         const float4* qp = reinterpret_cast<const float4*>(q + (long)l * D_MODEL + lane * 12);
-        const float4 a = qp[0], b = qp[1], c = qp[2];
+        const float4* bp = reinterpret_cast<const float4*>(bias + lane * 12);
+        float4 a = bp[0], b = bp[1], c = bp[2];
+        for (int sp = 0; sp < nsplit; ++sp) {               // sum the split-K partial results of the Q projection
+            const float4* r = qp + (long)sp * n_lines * (D_MODEL / 4);
+            const float4 x = __ldcg(r), y = __ldcg(r + 1), z = __ldcg(r + 2);
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+            c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+        }
         qv[0] = a.x * sc; qv[1] = a.y * sc; qv[2] = a.z * sc; qv[3] = a.w * sc;
         qv[4] = b.x * sc; qv[5] = b.y * sc; qv[6] = b.z * sc; qv[7] = b.w * sc;
         qv[8] = c.x * sc; qv[9] = c.y * sc; qv[10] = c.z * sc; qv[11] = c.w * sc;
@@ -700,7 +739,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 
 int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
                           const int* line_T, int max_T, const int* finished, float* out, int n_lines,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int nsplit, const float* bias) {
     const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);
     KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
     static bool attr_set = false;
@@ -708,8 +747,8 @@ int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, co
         KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dec_cross_attn_kernel<<<n_lines, 256, smem, stream>>>(q, kv, layer, line_tok_off, line_T, max_T, finished, out);
-    KOCR_CUDA(cudaGetLastError());
+    KOCR_CUDA(launch_kernel(dec_cross_attn_kernel, dim3(n_lines), dim3(256), smem, stream, q, kv, layer, line_tok_off,
+                            line_T, max_T, finished, out, nsplit, n_lines, bias));
     return 0;
 }
 
@@ -720,12 +759,19 @@ __global__ void __launch_bounds__(128) dec_argmax_kernel(const float* __restrict
                                                          int* __restrict__ lengths, int* __restrict__ finished,
                                                          int* __restrict__ n_active, const int* __restrict__ step_base,
                                                          int step_off, int n_lines, const int* __restrict__ forced,
-                                                         float* __restrict__ trace) {
+                                                         float* __restrict__ trace, int nsplit,
+                                                         const float* __restrict__ bias) {
     const int l = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (l >= n_lines) return;
-    if (finished[l]) return;
-    const int t = *step_base + step_off;
-    const float4 v4 = reinterpret_cast<const float4*>(logits + (long)l * VOCAB_PAD)[lane];
+    if (__ldcg(finished + l)) return;
+    const int t = __ldcg(step_base) + step_off;
+    float4 v4 = reinterpret_cast<const float4*>(bias)[lane];
+    for (int sp = 0; sp < nsplit; ++sp) {                   // sum the split-K partial results of out_proj
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(logits + ((long)sp * n_lines + l) * VOCAB_PAD) + lane);
+        v4.x += p.x; v4.y += p.y; v4.z += p.z; v4.w += p.w;
+    }
     if (trace) reinterpret_cast<float4*>(trace + ((long)l * DEC_MAX + t) * VOCAB_PAD)[lane] = v4;
     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
     float best = -INFINITY;
@@ -758,17 +804,19 @@ __global__ void __launch_bounds__(128) dec_argmax_kernel(const float* __restrict
 
 int launch_dec_argmax(const float* logits, int* tokens, int* lengths, int* finished, int* n_active,
                       const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
-                      cudaStream_t stream) {
-    dec_argmax_kernel<<<(n_lines + 3) / 4, 128, 0, stream>>>(logits, tokens, lengths, finished, n_active, step_base,
-                                                             step_off, n_lines, forced, trace);
-    KOCR_CUDA(cudaGetLastError());
+                      cudaStream_t stream, int nsplit, const float* bias) {
+    KOCR_CUDA(launch_kernel(dec_argmax_kernel, dim3((n_lines + 3) / 4), dim3(128), 0, stream, logits, tokens, lengths,
+                            finished, n_active, step_base, step_off, n_lines, forced, trace, nsplit, bias));
     return 0;
 }
 
-__global__ void dec_bump_kernel(int* step_base, int n) { *step_base += n; }
+__global__ void dec_bump_kernel(int* step_base, int n) {
+    pdl_trigger();
+    pdl_wait();
+    *step_base = __ldcg(step_base) + n;
+}
 int launch_dec_bump(int* step_base, int n, cudaStream_t stream) {
-    dec_bump_kernel<<<1, 1, 0, stream>>>(step_base, n);
-    KOCR_CUDA(cudaGetLastError());
+    KOCR_CUDA(launch_kernel(dec_bump_kernel, dim3(1), dim3(1), 0, stream, step_base, n));
     return 0;
 }
 
