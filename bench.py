@@ -155,12 +155,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--dec-wide", type=int, default=-1,
+                    help="decode GEMM shape: 1 = split-K over many CTAs (latency), 0 = few CTAs (throughput), -1 = auto")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch in the decode loop")
     ap.add_argument("--straggler-threshold", type=int, default=8,
                     help="a step returns once <= this many of its 256 lines are still decoding; they are pooled")
-    ap.add_argument("--big-gemm-sms", type=int, default=0,
+    ap.add_argument("--big-gemm-sms", type=int, default=132,
                     help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs)")
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--in-flight", type=int, default=12,
                     help="batches in flight per GPU (one handle + stream + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +206,7 @@ def main():
             self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
             self.batch_host.__dict__.update(self.batch.__dict__)
             self.batch_host.pixels = self.pix_host.numpy()
+            self.rec.set_option("dec_wide", 1 if (args.dec_wide == 1 or (args.dec_wide < 0 and S <= 4)) else 0)
             if args.no_pdl:
                 self.rec.set_option("use_pdl", 0)
             if args.big_gemm_sms > 0 and S > 1:

@@ -101,6 +101,8 @@ struct kocr_handle {
     bool decode_warmed = false;
     int use_graphs = 1;
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
+    int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
+                                 // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
     // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
     int kernel_timing = 0;
@@ -425,7 +427,7 @@ int gemm_dec(kocr_handle* h, const float* a, int L, const float* w, int N, int K
              cudaStream_t s) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
-    p.M = L; p.N = N; p.taps = 1; p.cin = K; p.tf32 = 1; p.split_k = split; p.bn = 64;
+    p.M = L; p.N = N; p.taps = 1; p.cin = K; p.tf32 = 1; p.split_k = split; p.bn = h->dec_wide ? 64 : 128;
     p.ep.out_f32 = parts; p.ep.ld_f32 = N;
     return launch_gemm_tc(a, L, w, p, h->num_sms, s);
 }
@@ -445,7 +447,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     float* parts = buf<float>(h, "dparts");          // split-K partial results of the current projection
     float* dao = buf<float>(h, "daof");
     float* dh = buf<float>(h, "dh");
-    const int S2 = 2, S8 = 8;                        // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8 slices
+    const int S2 = h->dec_wide ? 2 : 1, S8 = h->dec_wide ? 8 : 1;   // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8
     DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
@@ -463,7 +465,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
         {   // FFN1 keeps its ReLU epilogue (no split): N = 1536 already gives 48 CTAs
             GemmProblem p;
             memset(&p, 0, sizeof p);
-            p.M = L; p.N = 4 * D; p.taps = 1; p.cin = D; p.tf32 = 1; p.bn = 64;
+            p.M = L; p.N = 4 * D; p.taps = 1; p.cin = D; p.tf32 = 1; p.bn = h->dec_wide ? 64 : 256;
             p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D;
             DSTEP(launch_gemm_tc(dx, L, w.l1_w, p, h->num_sms, s));
         }
@@ -491,7 +493,7 @@ int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
 
 // The same 8 positions as one CUDA graph (captured once per (n_lines, max_T bucket, options)).
 int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
-    auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits * 2 + h->use_pdl, (h->force_tokens && h->have_forced) ? 1 : 0);
+    auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
         const int64_t before = g_launches.load() + gemm_tc_launch_count();
@@ -789,6 +791,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
+    if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
     if (strcmp(name, "straggler_threshold") == 0) { h->straggler_threshold = value; return 0; }
