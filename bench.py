@@ -336,6 +336,15 @@ def main():
     peaks = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     dom = kt.get("conv6", {"ms": 0.0, "launches": 0, "flops": 0.0})
+    traffic, traffic_note = None, None
+    try:        # DRAM bytes of this launch from the committed `ncu --set full` capture of the same workload
+        cap = json.loads((REPO / "profiles" / "r01" / "conv6_ncu_v2.json").read_text())
+        if cap.get("chunks") == n_chunks:
+            traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * 1e6
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, " + cap["source"] +
+                            "; algorithmic bytes per launch = chunks * (2 * 182*512*2 B activations) + 4.7 MB weights")
+    except Exception:
+        pass
     achieved_tf = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
     gemm_sites = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "patch_proj", "enc_qkv", "enc_out_proj",
                   "enc_ffn1", "enc_ffn2"]
@@ -384,7 +393,9 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256> @ conv6 (implicit GEMM, M=chunks*182, N=512, K=4608)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_unit": "bytes", "traffic_source": traffic_note,
+                         "algorithmic_bytes": n_chunks * 2 * 182 * 512 * 2 + 512 * 4608 * 2,
                          "peak_source": peaks["_source"] + " (sustained figure: kernel timed inside a long step)",
                          "launches_timed": dom["launches"], "ms_per_launch": dom["ms"] / max(dom["launches"], 1)},
             "sevgg_encoder_stage": {"chunks_per_s": stage_chunks_per_s, "ms_per_step": stage_ms,
