@@ -36,8 +36,17 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
 
     const int rows_here = C1_BAND + (band == 3 ? 1 : 0);   // last band also writes the shared pad row
     const int items = rows_here * g.P * 8;
+    // 256 % 8 == 0: a thread always works on the same group of 8 output channels, so its 72 folded weights and
+    // 8 biases live in registers for all of its pixels (shared memory then only serves the 4x4 input patches).
+    const int cg = threadIdx.x & 7;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[t][j] = s_w[t][cg * 8 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] = s_b[cg * 8 + j];
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int cg = it & 7;
         const int pos = it >> 3;
         const int pr = pos / g.P, pw = pos - pr * g.P;
         const int oh = band * C1_BAND + pr;
@@ -51,19 +60,18 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
             float res[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int ch = cg * 8 + j;
                 float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float wv = s_w[r * 3 + c][ch];
+                        const float wv = wr[r * 3 + c][j];
                         a00 = fmaf(in[r][c], wv, a00);
                         a01 = fmaf(in[r][c + 1], wv, a01);
                         a10 = fmaf(in[r + 1][c], wv, a10);
                         a11 = fmaf(in[r + 1][c + 1], wv, a11);
                     }
-                res[j] = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + s_b[ch], 0.f);
+                res[j] = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + br[j], 0.f);
             }
             o = make_uint4(pack_bf16(res[0], res[1]), pack_bf16(res[2], res[3]), pack_bf16(res[4], res[5]),
                            pack_bf16(res[6], res[7]));

@@ -346,6 +346,16 @@ static constexpr int LM_THREADS = 384;
 
 size_t bilstm_whh_mma_elems() { return (size_t)2 * 2 * 12 * 2 * 12 * 32 * 8; }   // bf16 elements
 
+// Fast gate non-linearities for the tensor-core recurrence: ex2/rcp and tanh.approx MUFU ops (relative error
+// ~2^-11, far below the bf16 rounding of the memory that feeds the decoder); the accurate expf/tanhf sequences
+// were the longest part of a recurrence step.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -448,13 +458,13 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
         for (int c = 0; c < 4; ++c) {
             if (s < cell_T[c]) {
                 const int nt = c >> 1, e = c & 1;
-                const float ig = sigmoid_acc(acc[0][nt][e] + gsrc[(c * 4 + 0) * LM_THREADS]);
-                const float fg = sigmoid_acc(acc[0][nt][2 + e] + gsrc[(c * 4 + 1) * LM_THREADS]);
-                const float gg = tanhf(acc[1][nt][e] + gsrc[(c * 4 + 2) * LM_THREADS]);
-                const float og = sigmoid_acc(acc[1][nt][2 + e] + gsrc[(c * 4 + 3) * LM_THREADS]);
+                const float ig = sigmoid_fast(acc[0][nt][e] + gsrc[(c * 4 + 0) * LM_THREADS]);
+                const float fg = sigmoid_fast(acc[0][nt][2 + e] + gsrc[(c * 4 + 1) * LM_THREADS]);
+                const float gg = tanh_fast(acc[1][nt][e] + gsrc[(c * 4 + 2) * LM_THREADS]);
+                const float og = sigmoid_fast(acc[1][nt][2 + e] + gsrc[(c * 4 + 3) * LM_THREADS]);
                 const float cc = fg * c_state[c] + ig * gg;
                 c_state[c] = cc;
-                const float h = og * tanhf(cc);
+                const float h = og * tanh_fast(cc);
                 const __nv_bfloat16 hb = __float2bfloat16_rn(h);
                 const __nv_bfloat16 lb = __float2bfloat16_rn(h - __bfloat162float(hb));
                 const int line = nt * 8 + 2 * tig + e;
