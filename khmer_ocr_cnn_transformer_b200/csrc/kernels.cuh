@@ -79,8 +79,8 @@ size_t bilstm_whh_mma_elems();
 int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base, int step_off, const float* tok_emb,
                      const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
                      cudaStream_t stream);
-int launch_dec_self_attn(const float* qkv /*[L,1152]*/, __nv_bfloat16* kcache,
-                         __nv_bfloat16* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
+int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache,
+                         float* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
                          int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream,
                          int nsplit, const float* bias);
 int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,

@@ -230,7 +230,7 @@ int carve_workspace(kocr_handle* h) {
         {"dx", L * D * 4}, {"dxb", L * D * 2}, {"dqkv", L * 3 * D * 4}, {"dao", L * D * 2}, {"dy", L * D * 4},
         {"dq", L * D * 4}, {"dh", L * 4 * D * 4}, {"daof", L * D * 4}, {"logits", L * VOCAB_PAD * 4},
         {"dparts", 8 * L * 3 * D * 4},
-        {"kcache", 2 * L * DEC_MAX * D * 2}, {"vcache", 2 * L * DEC_MAX * D * 2},
+        {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
     };
     size_t total = 0;
     for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -451,8 +451,8 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
-        __nv_bfloat16* kc = buf<__nv_bfloat16>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        __nv_bfloat16* vc = buf<__nv_bfloat16>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        float* kc = buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        float* vc = buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         DSTEP(gemm_dec(h, dx, L, w.sa_in_w, 3 * D, D, S2, parts, s));
         DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
