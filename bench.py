@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
+    ap.add_argument("--phased", type=int, default=0,
+                    help="1: all in-flight batches run stages 1-5a, then all decode together (phase-separated schedule)")
     ap.add_argument("--dec-wide", type=int, default=-1,
                     help="decode GEMM shape: 1 = split-K over many CTAs (latency), 0 = few CTAs (throughput), -1 = auto")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch in the decode loop")
@@ -229,6 +231,21 @@ def main():
                 self.rec.recognize_lines(_native.LineBatch(part))
                 self.n_flushes += 1
 
+        # The same step as two calls (stages 1-5a, then the decode loop) for the phased schedule below.
+        def step_heavy(self, host):
+            self.rec.set_option("straggler_threshold", args.straggler_threshold)
+            if host:
+                self.rec.gather_chunks(self.batch_host)
+            else:
+                self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr())
+            self.rec.sevgg_encoder_forward()
+            self.rec.merge_bilstm_forward()
+
+        def step_decode(self):
+            check = _native.check
+            check(self.rec.lib.kocr_decode_greedy(self.rec._h, 0, self.tok_np.ctypes.data, self.len_np.ctypes.data, None))
+            self._collect()
+
         def step_resident(self):
             self.rec.set_option("straggler_threshold", args.straggler_threshold)
             self.rec.recognize_lines(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr(), tokens_out=self.tok_np,
@@ -251,8 +268,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps_phased(kind, steps):
+        """Phased schedule: all in-flight batches run stages 1-5a (tensor-pipe bound), then all run their decode
+        loops together (latency / HBM bound), so the two kinds of kernels do not fight for SMs."""
+        n_workers = min(S, steps)
+        barrier_t = threading.Barrier(n_workers)
+        errors = []
+        rounds = (steps + n_workers - 1) // n_workers
+
+        def loop(wi, wk):
+            try:
+                torch.cuda.set_device(local_rank)
+                for r in range(rounds):
+                    active = r * n_workers + wi < steps
+                    if active:
+                        wk.step_heavy(kind == "e2e")
+                    barrier_t.wait()
+                    if active:
+                        wk.step_decode()
+                    barrier_t.wait()
+                wk.flush()
+            except Exception as e:
+                errors.append(e)
+                barrier_t.abort()
+
+        threads = [threading.Thread(target=loop, args=(i, wk)) for i, wk in enumerate(workers[:n_workers])]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
     def run_steps(kind, steps):
         """`steps` passes over a 256-line batch, at most S in flight (one host thread per in-flight batch)."""
+        if args.phased and S > 1:
+            return run_steps_phased(kind, steps)
         counter = {"next": 0}
         lock = threading.Lock()
         errors = []
@@ -379,7 +430,7 @@ def main():
             "config": {"workload": f"c2: {LINES_PER_STEP} synthetic Khmer text lines per GPU, resized width "
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
-                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S, "big_gemm_sms": args.big_gemm_sms,
+                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S, "big_gemm_sms": args.big_gemm_sms, "phased_schedule": args.phased,
                        "straggler_threshold": args.straggler_threshold,
                        "stragglers_pooled": int(sum(wk.n_stragglers for wk in workers)),
                        "straggler_batches": int(sum(wk.n_flushes for wk in workers)),
