@@ -87,6 +87,15 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
  *   "straggler_threshold" n -> see kocr_read_unfinished;  "lstm_impl" 0/1, "use_graphs" 0/1, "big_gemm_sms" n: tuning knobs
  *   "kernel_timing" 1 -> per-launch CUDA-event timing (see kocr_read_kernel_timing); setting it clears the totals */
 int kocr_set_option(kocr_handle* h, const char* name, int value);
+/* Beam search support - OCRPredictor._beam_search (predictor.py:101-136).  After kocr_gather_chunks /
+ * kocr_sevgg_encoder_forward / kocr_merge_bilstm_forward on a batch, runs ONE decoder position for n_rows (<= 8)
+ * hypotheses of line `line`: prefixes = host int32 [n_rows, t+1] (token ids of positions 0..t of each hypothesis),
+ * parents[r] = row of the previous call whose cache hypothesis r continues (ignored for t = 0).
+ * logits_out = host fp32 [n_rows, 128] (first 124 valid) for position t+1.  The beam bookkeeping (log-softmax,
+ * top-k, stable sort, pruning, length normalisation) stays on the host, identical to the reference's Python. */
+int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
+                   float* logits_out, void* stream);
+
 /* Long-tail handling.  With option "straggler_threshold" = n > 0, kocr_decode_greedy / kocr_recognize_lines return as
  * soon as at most n lines are still decoding (checked every 8 positions).  flags_out[i] = 1 marks the lines whose
  * row is incomplete; the caller re-submits those lines in a later batch (greedy decoding is deterministic, so the

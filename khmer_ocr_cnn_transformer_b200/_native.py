@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step",
 ]
 
 _lib = None
@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.kocr_set_forced_tokens.argtypes = [vp, vp, i32]
     lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.kocr_beam_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp]
+    lib.kocr_beam_step.restype = i32
     lib.kocr_read_unfinished.argtypes = [vp, vp]
     lib.kocr_read_unfinished.restype = i32
     lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
@@ -182,6 +184,16 @@ class Recognizer:
         out = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
         check(self.lib.kocr_debug_read(self._h, name.encode(), _ptr(out), out.nbytes, C.byref(n)))
         return out
+
+    def beam_step(self, line: int, prefixes: np.ndarray, parents, t: int) -> np.ndarray:
+        """One decoder position for the hypotheses `prefixes` [n_rows, t+1] of `line`; returns logits [n_rows, 124]."""
+        prefixes = np.ascontiguousarray(prefixes, np.int32)
+        n_rows = prefixes.shape[0]
+        assert prefixes.shape[1] == t + 1
+        par = np.ascontiguousarray(parents if parents is not None else np.zeros(n_rows), np.int32)
+        logits = np.zeros((n_rows, 128), np.float32)
+        check(self.lib.kocr_beam_step(self._h, line, n_rows, _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
+        return logits[:, :124]
 
     def unfinished(self, n_lines: int) -> np.ndarray:
         """Flags of the lines left incomplete by an early return (option "straggler_threshold")."""

@@ -261,4 +261,218 @@ int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_b
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused 1D-SE block (SequenceSE.forward, se_model.py:19-30, + the pooling that follows it, :69-78):
+// ONE CTA per chunk does squeeze (column means) -> FC1+ReLU -> FC2+sigmoid -> gate * x -> pool.
+// The chunk's activations (150 KB) are read twice by the same CTA, a few microseconds apart: the second read is an
+// L2 hit, so HBM sees one read of the conv output and one write of the pooled output (225 KB per chunk instead of
+// the ~580 KB of the four-kernel version with its bf16 means / fp32 gate round trips).
+// The two 1x1 Conv1d layers are [25 columns -> 32] x C x C/16 contractions: far below a tcgen05 tile, so they
+// run on mma.sync.m16n8k16 (bf16, fp32 accumulate) with the column means / hidden vector as A operands in shared
+// memory and the weights read straight from L2 as B fragments.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+static constexpr int SE_W = 25;            // columns of every SE stage (100 / 4)
+static constexpr int SE_THREADS = 256;
+
+template <int C> struct SeSmem {
+    static constexpr int R = C / 16;                       // reduced width (se_model.py:9,13)
+    static constexpr int LDA = C + 8;                      // bf16 elements per row of the means (conflict-free frags)
+    static constexpr int LDZ = R + 8;
+    static constexpr size_t A_BYTES = 32 * LDA * 2;
+    static constexpr size_t Z_BYTES = 32 * LDZ * 2;
+    static constexpr size_t G_BYTES = (size_t)SE_W * C * 4;
+    static constexpr size_t BYTES = A_BYTES + Z_BYTES + G_BYTES;
+};
+
+// FINAL = false: (2,1) max-pool -> padded-linear (H/2, 25, C);  FINAL = true: AdaptiveAvgPool2d((2,32)) -> patch operand.
+template <int C, int H, bool FINAL>
+__global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              const __nv_bfloat16* __restrict__ w0p /*[128][C]*/,
+                                                              const float* __restrict__ b0p,
+                                                              const __nv_bfloat16* __restrict__ w2p /*[C][128]*/,
+                                                              const float* __restrict__ b2,
+                                                              __nv_bfloat16* __restrict__ out) {
+    using S = SeSmem<C>;
+    constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8, TPG = SE_THREADS / CG;
+    extern __shared__ __align__(16) uint8_t se_smem[];
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(se_smem);
+    __nv_bfloat16* sZ = reinterpret_cast<__nv_bfloat16*>(se_smem + S::A_BYTES);
+    float* sG = reinterpret_cast<float*>(se_smem + S::A_BYTES + S::Z_BYTES);
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const PLGeom gi = make_pl(H, SE_W);
+    const uint4* src = reinterpret_cast<const uint4*>(in + (long)n * gi.S * C);
+
+    // ---- squeeze: mean over H of every (column, channel) -> bf16 A operand [32][C] (rows 25..31 zero) ----
+    {
+        const int cg = tid % CG, sub = tid / CG;
+        const float inv = 1.f / (float)H;
+        // H is a compile-time constant: all H loads of a column (and two columns when H <= 6) are in flight at once
+#pragma unroll(H <= 6 ? 2 : 1)
+        for (int w = sub; w < 32; w += TPG) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (w < SE_W) {
+                uint4 v[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) v[h] = __ldg(src + (long)(h * gi.P + w) * CG + cg);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const uint4 a = v[h];
+                    acc[0] += bf16_lo(a.x); acc[1] += bf16_hi(a.x); acc[2] += bf16_lo(a.y); acc[3] += bf16_hi(a.y);
+                    acc[4] += bf16_lo(a.z); acc[5] += bf16_hi(a.z); acc[6] += bf16_lo(a.w); acc[7] += bf16_hi(a.w);
+                }
+            }
+            *reinterpret_cast<uint4*>(sA + w * LDA + cg * 8) =
+                make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
+                           pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+        }
+    }
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    // ---- FC1 + ReLU: Z[32][R] = relu(A[32][C] * W0^T + b0); one (m-tile, n-tile) pair per warp ----
+    {
+        constexpr int NT = R / 8;                          // 2 or 4 n-tiles; 2 m-tiles
+        if (warp < 2 * NT) {
+            const int mt = warp / NT, nt = warp % NT;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const __nv_bfloat16* arow0 = sA + (mt * 16 + g) * LDA + 2 * t;
+            const __nv_bfloat16* wrow = w0p + (long)(nt * 8 + g) * C + 2 * t;
+#pragma unroll 8
+            for (int k = 0; k < C; k += 16) {
+                uint32_t a[4];
+                a[0] = *reinterpret_cast<const uint32_t*>(arow0 + k);
+                a[1] = *reinterpret_cast<const uint32_t*>(arow0 + 8 * LDA + k);
+                a[2] = *reinterpret_cast<const uint32_t*>(arow0 + k + 8);
+                a[3] = *reinterpret_cast<const uint32_t*>(arow0 + 8 * LDA + k + 8);
+                const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k));
+                const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8));
+                mma_bf16_16816(d, a, b0, b1);
+            }
+            const int col = nt * 8 + 2 * t;
+            const float bb0 = __ldg(b0p + col), bb1 = __ldg(b0p + col + 1);
+            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g) * LDZ + col) = pack_bf16(fmaxf(d[0] + bb0, 0.f), fmaxf(d[1] + bb1, 0.f));
+            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g + 8) * LDZ + col) = pack_bf16(fmaxf(d[2] + bb0, 0.f), fmaxf(d[3] + bb1, 0.f));
+        }
+    }
+    __syncthreads();
+    // ---- FC2 + sigmoid: G[25][C] = sigmoid(Z[32][R] * W2^T + b2); each warp owns C/8 channels ----
+    {
+        constexpr int KS = R / 16;                         // 1 or 2 k-steps
+        uint32_t a[2][KS][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const __nv_bfloat16* zr = sZ + (mt * 16 + g) * LDZ + ks * 16 + 2 * t;
+                a[mt][ks][0] = *reinterpret_cast<const uint32_t*>(zr);
+                a[mt][ks][1] = *reinterpret_cast<const uint32_t*>(zr + 8 * LDZ);
+                a[mt][ks][2] = *reinterpret_cast<const uint32_t*>(zr + 8);
+                a[mt][ks][3] = *reinterpret_cast<const uint32_t*>(zr + 8 * LDZ + 8);
+            }
+        constexpr int NT_PER_WARP = C / 8 / 8;             // n-tiles of 8 channels per warp
+#pragma unroll 4
+        for (int i = 0; i < NT_PER_WARP; ++i) {
+            const int c0 = (warp * NT_PER_WARP + i) * 8;
+            const __nv_bfloat16* wrow = w2p + (long)(c0 + g) * 128 + 2 * t;
+            uint32_t b[KS][2];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                b[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16));
+                b[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8));
+            }
+            const int col = c0 + 2 * t;
+            const float bb0 = __ldg(b2 + col), bb1 = __ldg(b2 + col + 1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) mma_bf16_16816(d, a[mt][ks], b[ks][0], b[ks][1]);
+                const int r0 = mt * 16 + g, r1 = r0 + 8;
+                if (r0 < SE_W)
+                    *reinterpret_cast<float2*>(sG + r0 * C + col) =
+                        make_float2(1.f / (1.f + __expf(-(d[0] + bb0))), 1.f / (1.f + __expf(-(d[1] + bb1))));
+                if (r1 < SE_W)
+                    *reinterpret_cast<float2*>(sG + r1 * C + col) =
+                        make_float2(1.f / (1.f + __expf(-(d[2] + bb0))), 1.f / (1.f + __expf(-(d[3] + bb1))));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- excite + pool (second read of the chunk: L2 hits) ----
+    if (!FINAL) {
+        const PLGeom go = make_pl(H / 2, SE_W);
+        uint4* dst = reinterpret_cast<uint4*>(out + (long)n * go.S * C);
+#pragma unroll 4
+        for (int idx = tid; idx < go.S * CG; idx += SE_THREADS) {
+            const int cg = idx % CG, pos = idx / CG;
+            const int oh = pos / go.P, ow = pos - oh * go.P;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (oh < go.H && ow < go.W) {
+                const uint4* p = src + (long)(2 * oh * gi.P + ow) * CG + cg;
+                o = max4(__ldg(p), __ldg(p + (long)gi.P * CG));
+                const float4 ga = *reinterpret_cast<const float4*>(sG + ow * C + cg * 8);
+                const float4 gb = *reinterpret_cast<const float4*>(sG + ow * C + cg * 8 + 4);
+                o = make_uint4(pack_bf16(bf16_lo(o.x) * ga.x, bf16_hi(o.x) * ga.y),
+                               pack_bf16(bf16_lo(o.y) * ga.z, bf16_hi(o.y) * ga.w),
+                               pack_bf16(bf16_lo(o.z) * gb.x, bf16_hi(o.z) * gb.y),
+                               pack_bf16(bf16_lo(o.w) * gb.z, bf16_hi(o.w) * gb.w));
+            }
+            dst[idx] = o;
+        }
+    } else {
+        uint4* dst = reinterpret_cast<uint4*>(out + (long)n * TOK_PER_CHUNK * 2 * C);
+#pragma unroll 4
+        for (int idx = tid; idx < TOK_PER_CHUNK * 2 * CG; idx += SE_THREADS) {
+            const int cg = idx % CG, kh = (idx / CG) & 1, k = idx / (2 * CG);
+            const int h0 = (kh * H) / 2, h1 = ((kh + 1) * H + 1) / 2;
+            const int w0 = (k * SE_W) / TOK_PER_CHUNK, w1 = ((k + 1) * SE_W + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int w = w0; w < w1; ++w) {
+                const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
+                const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
+                for (int h = h0; h < h1; ++h) {
+                    const uint4 a = __ldg(src + (long)(h * gi.P + w) * CG + cg);
+                    acc[0] += bf16_lo(a.x) * ga.x; acc[1] += bf16_hi(a.x) * ga.y;
+                    acc[2] += bf16_lo(a.y) * ga.z; acc[3] += bf16_hi(a.y) * ga.w;
+                    acc[4] += bf16_lo(a.z) * gb.x; acc[5] += bf16_hi(a.z) * gb.y;
+                    acc[6] += bf16_lo(a.w) * gb.z; acc[7] += bf16_hi(a.w) * gb.w;
+                }
+            }
+            const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+            dst[idx] = make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
+                                  pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+        }
+    }
+}
+
+template <int C, int H, bool FINAL>
+static int launch_se_fused_impl(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks,
+                                cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        KOCR_CUDA(cudaFuncSetAttribute(se_fused_kernel<C, H, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SeSmem<C>::BYTES));
+        attr_set = true;
+    }
+    se_fused_kernel<C, H, FINAL><<<n_chunks, SE_THREADS, SeSmem<C>::BYTES, stream>>>(in, w.w0p, w.b0p, w.w2p, w.b2, out);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The three SE sites of the backbone (se_model.py:47,53,59): (C, H) = (256, 12), (512, 6) and (512, 3) + final pool.
+int launch_se_fused(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+                    bool final_pool, cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    if (W == SE_W && C == 256 && H == 12 && !final_pool) return launch_se_fused_impl<256, 12, false>(in, w, out, n_chunks, stream);
+    if (W == SE_W && C == 512 && H == 6 && !final_pool) return launch_se_fused_impl<512, 6, false>(in, w, out, n_chunks, stream);
+    if (W == SE_W && C == 512 && H == 3 && final_pool) return launch_se_fused_impl<512, 3, true>(in, w, out, n_chunks, stream);
+    KOCR_CHECK(false, "se_fused: unsupported geometry H=%d W=%d C=%d final=%d", H, W, C, (int)final_pool);
+    return 2;
+}
+
 }  // namespace kocr

@@ -23,7 +23,7 @@ template <int BN> struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);   // 192 KB of operands
     static constexpr int TMEM_COLS = 2 * BN;                    // 256 / 512
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 8192 /*epilogue staging: 2 x 4 KB per warp*/;
 };
 
 struct GemmKernelParams {
@@ -128,9 +128,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         // ===================== epilogue warps (2..5) =====================
+        // Thread = one accumulator row (TMEM lane).  Global traffic goes through a per-warp 32 x 128-byte staging tile
+        // in shared memory so that every global access instruction covers whole 64/128-byte row segments (4-8 rows
+        // per instruction) instead of 32 scattered 16-byte pieces: the short-K GEMMs are paced by their epilogue.
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
         const GemmEpilogue& ep = p.ep;
+        // two 4 KB buffers per warp: the addend block of chunk c+1 streams in (cp.async) while chunk c is processed
+        const uint32_t stg_base = smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES + 256 + quad * 8192);
+        // staging addressing (16-byte pieces, XOR-swizzled so that both the row-wise and the piece-wise access
+        // patterns are bank-conflict free): fp32 rows of 8 pieces, bf16 rows of 4 pieces
+        const uint32_t own32 = lane * 128, own16 = lane * 64;     // offsets inside a staging buffer
+        const int sw32 = lane & 7, sw16 = (lane >> 1) & 3;
+        const int r32 = lane >> 3, p32 = lane & 7;     // cooperative fp32 access: 4 rows x 8 pieces per instruction
+        const int r16 = lane >> 2, p16 = lane & 3;     // cooperative bf16 access: 8 rows x 4 pieces per instruction
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -138,47 +149,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int mn = tile / p.split_k, sp = tile - mn * p.split_k;
             const int m0 = (mn / p.num_n_tiles) * BM;
             const int n0 = (mn % p.num_n_tiles) * BN;
-            const long row = (long)m0 + row_in_tile;
-            const bool in_range = row < p.M;
-            bool valid = in_range;
+            const long row0 = (long)m0 + quad * 32;    // first row of this warp
+            const long row = row0 + lane;
+            bool valid = row < p.M;
             if (ep.pl_S > 0) {
                 const int r = (int)(row % ep.pl_S);
                 const int h = r / ep.pl_P, w = r - h * ep.pl_P;
                 valid = valid && (h < ep.pl_H) && (w < ep.pl_W);
             }
-            const float* add_row = nullptr;
-            if (ep.addend != nullptr && in_range) {
-                const long ar = ep.add_period > 0 ? (row % ep.add_period) : row;
-                add_row = ep.addend + ar * ep.ld_add + n0;
+            const int rows_here = (int)min((long)32, (long)p.M - row0);     // rows of this warp inside the matrix (may be <= 0)
+            // addend rows this lane fetches for the warp (4 rows x 8 pieces per instruction); element offsets fit 32 bits
+            uint32_t add_off[8];
+            if (ep.addend) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t gr = (uint32_t)row0 + i * 4 + r32;
+                    const uint32_t ar = ep.add_period > 0 ? gr % (uint32_t)ep.add_period : gr;
+                    add_off[i] = ar * (uint32_t)ep.ld_add + n0 + p32 * 4;
+                }
             }
+            auto fetch_addend = [&](int c) {           // async copy of the 32 x 32 fp32 addend block of chunk c (L2 path)
+                const uint32_t dstb = stg_base + (c & 1) * 4096;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + r32;
+                    if (rr < rows_here) cp_async_16(dstb + rr * 128 + ((p32 ^ (rr & 7)) << 4), ep.addend + add_off[i] + c * 32);
+                }
+                cp_async_commit();
+            };
+            if (ep.addend) fetch_addend(0);            // overlaps the wait for the accumulator
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c * 32, v);
-                tmem_ld_wait();
-                if (c == BN / 32 - 1) {
-                    // all TMEM reads of this accumulator stage are done -> release it to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(&tmem_empty[acc]);
-                }
-                if (!in_range) continue;
+
+            auto process = [&](const uint32_t (&v)[32], int c) {
+                const int nc = n0 + c * 32;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (ep.bias) x += __ldg(ep.bias + n0 + c * 32 + j);
-                    f[j] = x;
-                }
-                if (add_row) {
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (ep.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        // .cg (L2) load: the addend may have been written by the immediately preceding kernel (PDL)
-                        const float4 a = __ldcg(reinterpret_cast<const float4*>(add_row + c * 32 + j));
-                        f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nc + j));
+                        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
                     }
+                }
+                const uint32_t stg_u32 = stg_base + (c & 1) * 4096;
+                if (ep.addend) {
+                    // the block of this chunk was requested one chunk ago; request the next one before waiting
+                    if (c + 1 < BN / 32) { fetch_addend(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = ld_shared_v4(stg_u32 + own32 + ((j ^ sw32) << 4));
+                        f[4 * j] += a.x; f[4 * j + 1] += a.y; f[4 * j + 2] += a.z; f[4 * j + 3] += a.w;
+                    }
+                    __syncwarp();
                 }
                 // activation: the (warp-uniform) mode is tested OUTSIDE the unrolled loops so that the sigmoid's
                 // MUFU work is not if-converted into every GEMM's epilogue
@@ -194,18 +220,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     for (int j = 0; j < 32; ++j) f[j] = 0.f;
                 }
                 if (ep.out_f32) {
-                    float4* o = reinterpret_cast<float4*>(ep.out_f32 + ((long)sp * p.M + row) * ep.ld_f32 + n0 + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg_u32 + own32 + ((j ^ sw32) << 4), make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    __syncwarp();
+                    float* o = ep.out_f32 + ((long)sp * p.M + row0) * ep.ld_f32 + nc + p32 * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + r32;
+                        const float4 a = ld_shared_v4(stg_u32 + rr * 128 + ((p32 ^ (rr & 7)) << 4));
+                        if (rr < rows_here) *reinterpret_cast<float4*>(o + (long)rr * ep.ld_f32) = a;
+                    }
+                    __syncwarp();
                 }
                 if (ep.out_bf16) {
-                    uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + row * ep.ld_bf16 + n0 + c * 32);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        o[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-                    if (ep.out_bf16_lo) {
-                        uint4* ol = reinterpret_cast<uint4*>(ep.out_bf16_lo + row * ep.ld_bf16 + n0 + c * 32);
+                        st_shared_v4u(stg_u32 + own16 + ((j ^ sw16) << 4),
+                                      make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7])));
+                    __syncwarp();
+                    __nv_bfloat16* o = ep.out_bf16 + row0 * ep.ld_bf16 + nc + p16 * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + r16;
+                        const uint4 a = ld_shared_v4u(stg_u32 + rr * 64 + ((p16 ^ ((rr >> 1) & 3)) << 4));
+                        if (rr < rows_here) *reinterpret_cast<uint4*>(o + (long)rr * ep.ld_bf16) = a;
+                    }
+                    __syncwarp();
+                    if (ep.out_bf16_lo && row < p.M) {
+                        uint4* ol = reinterpret_cast<uint4*>(ep.out_bf16_lo + row * ep.ld_bf16 + nc);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
 #pragma unroll
@@ -214,6 +258,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
+            };
+
+            // TMEM reads are double-buffered in registers: the load of chunk c+1 is in flight while chunk c is
+            // processed; the accumulator stage is released as soon as its last chunk is in registers.
+            constexpr int NCH = BN / 32;
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
+#pragma unroll 1
+            for (int c = 0; c < NCH; c += 2) {
+                tmem_ld_wait();
+                tmem_ld32(t_row + (c + 1) * 32, vb);
+                if (rows_here > 0) process(va, c);
+                tmem_ld_wait();
+                if (c + 2 < NCH) {
+                    tmem_ld32(t_row + (c + 2) * 32, va);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[acc]);
+                }
+                if (rows_here > 0) process(vb, c + 1);
             }
         }
     }

@@ -40,6 +40,9 @@ int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, in
 // gate fp32 [n*W + w][C] (null = no SE) * (2,1) max-pool -> padded-linear (H/2, W, C), or
 // gate * x -> AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n*32 + k][kh*C + c].
 struct SEWeights { const __nv_bfloat16* w0p; const float* b0p; const __nv_bfloat16* w2p; const float* b2; };
+// Fused SE block: squeeze + FC1/ReLU + FC2/sigmoid + gate*x + pool in one kernel, one CTA per chunk (W = 25).
+int launch_se_fused(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+                    bool final_pool, cudaStream_t stream);
 int launch_se_col_mean(const __nv_bfloat16* in, __nv_bfloat16* means, int n_chunks, int H, int W, int C,
                        cudaStream_t stream);
 int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H, int W,

@@ -101,6 +101,10 @@ struct kocr_handle {
     bool decode_warmed = false;
     int use_graphs = 1;
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
+    int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
+    static const int BEAM_MAX = 8;
+    Buf beam_cache;              // [2 ping-pong][K,V][2 layers][BEAM_MAX][DEC_MAX][384] fp32, allocated on first use
+    int beam_cur = 0;
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
@@ -352,16 +356,26 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
     TIMED("conv4", cf(12, 25, 256, 256), gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
     const float* gate = nullptr;
+    const bool fused = se && h->se_fused;     // one kernel per SE block (squeeze + FCs + gate + pool)
+    if (fused) { TIMED("se3_fused_pool3", 4.0 * nc * 25 * 256 * 16, launch_se_fused(B("conv4"), h->se[0], B("pool3"), NC, 12, 25, 256, false, s)); ++g_launches; }
+    else {
     if (se) KOCR_TRY(se_gate(h, B("conv4"), NC, 12, 25, 256, h->se[0], "se3", &gate, s));
     TIMED("se3_apply_pool3", 0, launch_se_apply_pool(B("conv4"), gate, B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
+    }
     TIMED("conv5", cf(6, 25, 256, 512), gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
     TIMED("conv6", cf(6, 25, 512, 512), gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
+    if (fused) { TIMED("se4_fused_pool4", 4.0 * nc * 25 * 512 * 32, launch_se_fused(B("conv6"), h->se[1], B("pool4"), NC, 6, 25, 512, false, s)); ++g_launches; }
+    else {
     if (se) KOCR_TRY(se_gate(h, B("conv6"), NC, 6, 25, 512, h->se[1], "se4", &gate, s));
     TIMED("se4_apply_pool4", 0, launch_se_apply_pool(B("conv6"), gate, B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
+    }
     // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
     TIMED("conv7", cf(3, 25, 512, 512), gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
+    if (fused) { TIMED("se5_fused_finalpool", 4.0 * nc * 25 * 512 * 32, launch_se_fused(B("conv7"), h->se[2], B("patch_in"), NC, 3, 25, 512, true, s)); ++g_launches; }
+    else {
     if (se) KOCR_TRY(se_gate(h, B("conv7"), NC, 3, 25, 512, h->se[2], "se5", &gate, s));
     TIMED("se5_apply_finalpool", 0, launch_se_apply_finalpool(B("conv7"), gate, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
+    }
 
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");
@@ -435,8 +449,17 @@ int gemm_dec(kocr_handle* h, const float* a, int L, const float* w, int N, int K
 // One generated position for every line of the batch; the position is *step_base + off (device side).
 // Decoder GEMMs run on the tensor cores in TF32 (fp32 operands): with bf16 operands ~7 % of the lines of the
 // fixture batch decode to a different sequence than the fp32 reference, with TF32 the flips disappear.
-int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
-    const int L = h->n_lines;
+// Optional override: the rows are `n_rows` hypotheses (beams) that share the memory of ONE line and use a private,
+// small self-attention cache.
+struct DecRows {
+    int n_rows;
+    float *kcache, *vcache;          // [2 layers][BEAM_MAX][DEC_MAX][384]
+    size_t layer_stride;
+    const int *tok_off, *T;          // device arrays [n_rows]
+};
+
+int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRows* rows = nullptr) {
+    const int L = rows ? rows->n_rows : h->n_lines;
     const int D = D_MODEL;
     int n_launched = 0;
 #define DSTEP(call) do { if (h->debug_stop <= 0 || n_launched < h->debug_stop) { KOCR_TRY(call); } ++n_launched; } while (0)
@@ -451,14 +474,15 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
-        float* kc = buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        float* vc = buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        float* kc = rows ? rows->kcache + l * rows->layer_stride : buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
+        float* vc = rows ? rows->vcache + l * rows->layer_stride : buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         DSTEP(gemm_dec(h, dx, L, w.sa_in_w, 3 * D, D, S2, parts, s));
         DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
         DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx)); ++g_launches;
         DSTEP(gemm_dec(h, dx, L, w.ca_q_w, D, D, S2, parts, s));
-        DSTEP(launch_dec_cross_attn(parts, buf<__nv_bfloat16>(h, "kv"), l, h->d_line_tok_off, h->d_line_T, max_T, fin,
+        DSTEP(launch_dec_cross_attn(parts, buf<__nv_bfloat16>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
+                                    rows ? rows->T : h->d_line_T, max_T, fin,
                                     dao, L, s, S2, w.ca_q_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s));
         DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx)); ++g_launches;
@@ -474,7 +498,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s) {
     }
     DSTEP(gemm_dec(h, dx, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s));
     const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
-    float* trace = h->trace_logits ? reinterpret_cast<float*>(h->trace.p) : nullptr;
+    float* trace = (h->trace_logits || rows) ? reinterpret_cast<float*>(h->trace.p) : nullptr;
     DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,
                             off, L, forced, trace, s, S2, h->dec_out_b)); ++g_launches;
 #undef DSTEP
@@ -592,6 +616,7 @@ int kocr_destroy(kocr_handle* h) {
     if (h->pixels_dev.p) cudaFree(h->pixels_dev.p);
     if (h->mid_dev.p) cudaFree(h->mid_dev.p);
     if (h->trace.p) cudaFree(h->trace.p);
+    if (h->beam_cache.p) cudaFree(h->beam_cache.p);
     if (h->staging_host) cudaFreeHost(h->staging_host);
     if (h->staging_dev) cudaFree(h->staging_dev);
     if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
@@ -790,6 +815,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
+    if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
@@ -810,6 +836,79 @@ int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens, int n_lines) {
     KOCR_CUDA(cudaSetDevice(h->device));
     KOCR_CUDA(cudaMemcpy(buf<int>(h, "forced"), tokens, (size_t)n_lines * KOCR_TOKENS_LD * 4, cudaMemcpyHostToDevice));
     h->have_forced = true;
+    return 0;
+}
+
+// ---- beam search support (OCRPredictor._beam_search, predictor.py:101-136) ---------------------------------
+// One decoder position for `n_rows` hypotheses of line `line`.  The host owns the beam bookkeeping (scores, pruning,
+// tie order - identical to the reference's Python); the device keeps one self-attention cache row per hypothesis.
+namespace {
+__global__ void beam_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ parents,
+                                    int n_rows, int t, size_t layer_stride, size_t kv_stride) {
+    // grid = (n_rows, 2 layers, 2 {K,V}); copies positions [0, t) of the parent's cache row
+    const int r = blockIdx.x, layer = blockIdx.y, kv = blockIdx.z;
+    const float4* s4 = reinterpret_cast<const float4*>(src + kv * kv_stride + layer * layer_stride + (size_t)parents[r] * DEC_MAX * D_MODEL);
+    float4* d4 = reinterpret_cast<float4*>(dst + kv * kv_stride + layer * layer_stride + (size_t)r * DEC_MAX * D_MODEL);
+    for (int i = threadIdx.x; i < t * (D_MODEL / 4); i += blockDim.x) d4[i] = s4[i];
+}
+}  // namespace
+
+int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
+                   float* logits_out, void* stream) {
+    KOCR_CHECK(h != nullptr && prefixes != nullptr && logits_out != nullptr, "kocr_beam_step: null argument");
+    KOCR_CHECK(line >= 0 && line < h->n_lines, "kocr_beam_step: line %d outside the current batch of %d", line, h->n_lines);
+    KOCR_CHECK(n_rows >= 1 && n_rows <= kocr_handle::BEAM_MAX, "kocr_beam_step: %d hypotheses (max %d)", n_rows, kocr_handle::BEAM_MAX);
+    KOCR_CHECK(t >= 0 && t < h->dec_max_len, "kocr_beam_step: position %d out of range", t);
+    KOCR_CHECK(t == 0 || parents != nullptr, "kocr_beam_step: parents required for t > 0");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    const size_t row = (size_t)DEC_MAX * D_MODEL, layer_stride = kocr_handle::BEAM_MAX * row, kv_stride = 2 * layer_stride,
+                 buf_stride = 2 * kv_stride;
+    KOCR_TRY(ensure(h->beam_cache, 2 * buf_stride * sizeof(float)));
+    KOCR_TRY(ensure(h->trace, (size_t)h->max_lines * DEC_MAX * VOCAB_PAD * 4));
+    float* base = reinterpret_cast<float*>(h->beam_cache.p);
+    int* tokens = buf<int>(h, "tokens");
+    int* scratch = buf<int>(h, "forced");             // [0, 8): parents, [8, 16): tok_off, [16, 24): T
+    int32_t host_tab[24];
+    for (int r = 0; r < kocr_handle::BEAM_MAX; ++r) {
+        host_tab[r] = (t > 0 && r < n_rows) ? parents[r] : 0;
+        KOCR_CHECK(host_tab[r] >= 0 && host_tab[r] < kocr_handle::BEAM_MAX, "kocr_beam_step: bad parent index");
+        host_tab[8 + r] = h->line_first_chunk[line] * TOK_PER_CHUNK;
+        host_tab[16 + r] = h->line_T[line];
+    }
+    KOCR_CUDA(cudaMemcpyAsync(scratch, host_tab, sizeof host_tab, cudaMemcpyHostToDevice, s));
+    // token prefixes of all hypotheses (positions 0..t): row r of `prefixes` is [t + 1] ints
+    KOCR_CUDA(cudaMemcpy2DAsync(tokens, KOCR_TOKENS_LD * 4, prefixes, (size_t)(t + 1) * 4, (size_t)(t + 1) * 4, n_rows,
+                                cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "finished"), 0, (size_t)kocr_handle::BEAM_MAX * 4, s));
+    const int32_t step = t;
+    KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "step_base"), &step, 4, cudaMemcpyHostToDevice, s));
+    if (t == 0) h->beam_cur = 0;
+    if (t > 0) {
+        const int nxt = h->beam_cur ^ 1;
+        beam_reorder_kernel<<<dim3(n_rows, 2, 2), 256, 0, s>>>(base + h->beam_cur * buf_stride, base + nxt * buf_stride, scratch,
+                                                              n_rows, t, row * kocr_handle::BEAM_MAX, kv_stride);
+        KOCR_CUDA(cudaGetLastError());
+        ++g_launches;
+        h->beam_cur = nxt;
+    }
+    DecRows rows;
+    rows.n_rows = n_rows;
+    rows.kcache = base + h->beam_cur * buf_stride;
+    rows.vcache = rows.kcache + kv_stride;
+    rows.layer_stride = layer_stride;
+    rows.tok_off = scratch + 8;
+    rows.T = scratch + 16;
+    const int max_T = (h->line_T[line] + 127) / 128 * 128;
+    const int saved_force = h->force_tokens;
+    h->force_tokens = 0;
+    int rc = decode_step(h, 0, max_T, s, &rows);
+    h->force_tokens = saved_force;
+    if (rc) return rc;
+    // the argmax kernel wrote the (bias-added, slice-summed) logits of position t into the trace rows
+    KOCR_CUDA(cudaMemcpy2DAsync(logits_out, VOCAB_PAD * 4, reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
+                                (size_t)DEC_MAX * VOCAB_PAD * 4, VOCAB_PAD * 4, n_rows, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -3,7 +3,9 @@ signatures (reference: netra_ocr/recognition/predictor.py:12-199), running on li
 
 Differences that do not change results: chunks of many lines are batched on the GPU regardless of
 `batch_size` (lines are independent, predictor.py:150-193), BiLSTM/decoding are batched across lines
-with a KV cache instead of one line and one full-prefix pass per token.  There is no CPU path."""
+with a KV cache instead of one line and one full-prefix pass per token.  Beam search (beam_width > 1) keeps the
+reference's bookkeeping on the host and runs each decoder position for all hypotheses on the GPU.
+There is no CPU path."""
 import logging
 from pathlib import Path
 
@@ -79,14 +81,65 @@ class OCRPredictor:
         assert not left
         return results
 
+    # ------------------------------------------------------------------------------------
+    def _beam_search_line(self, line: int, beam_width: int) -> str:
+        """`OCRPredictor._beam_search` (reference predictor.py:101-136) for line `line` of the batch whose stages 1-5a
+        have just run: same candidate generation, stable sort, pruning and length normalisation; the decoder
+        positions run on the GPU (kocr_beam_step), one call per position."""
+        import torch
+        import torch.nn.functional as F
+        sos, eos = self.tokenizer.sos_idx, self.tokenizer.eos_idx
+        beams = [(0.0, [sos])]
+        completed = []
+        parents = None
+        for t in range(self.cfg.decode_max_len):
+            k_curr = len(beams)
+            prefixes = np.asarray([b[1] for b in beams], np.int32)
+            logits = self.model.beam_step(line, prefixes, parents, t)
+            log_probs = F.log_softmax(torch.from_numpy(logits.copy()), dim=-1)
+            candidates = []
+            for i in range(k_curr):
+                score, seq = beams[i]
+                top_probs, top_idxs = log_probs[i].topk(beam_width)
+                for k in range(beam_width):
+                    candidates.append((score + top_probs[k].item(), seq + [top_idxs[k].item()], i))
+            candidates.sort(key=lambda x: x[0], reverse=True)
+            next_beams, next_parents = [], []
+            for s, seq, parent in candidates:
+                if seq[-1] == eos:
+                    completed.append((s / len(seq), seq))
+                elif len(next_beams) < beam_width:
+                    next_beams.append((s, seq))
+                    next_parents.append(parent)
+            beams, parents = next_beams, next_parents
+            if not beams:
+                break
+        best_seq = sorted(completed, key=lambda x: x[0], reverse=True)[0][1] if completed else beams[0][1]
+        return self.tokenizer.decode(best_seq)
+
+    def _beam_gray(self, grays, beam_width: int):
+        if beam_width > 8:
+            raise ValueError("beam_width > 8 is not supported by the CUDA path")
+        results = [None] * len(grays)
+        from ..scheduling import plan_batches
+        for idxs in plan_batches([g.shape for g in grays], self._max_lines, self._max_chunks, self.cfg.max_seq_len):
+            self.model.gather_chunks(LineBatch([grays[i] for i in idxs]))
+            self.model.sevgg_encoder_forward()
+            self.model.merge_bilstm_forward()
+            for j, i in enumerate(idxs):
+                results[i] = self._beam_search_line(j, beam_width)
+        return results
+
     def predict(self, image_input, beam_width: int = 3) -> str:
-        if beam_width > 1:
-            logger.warning("beam search is not implemented on the CUDA path yet; decoding greedily")
-        return self._recognize_gray([ImagePreprocessor.to_gray(image_input)])[0]
+        gray = ImagePreprocessor.to_gray(image_input)
+        if beam_width <= 1:
+            return self._recognize_gray([gray])[0]
+        return self._beam_gray([gray], beam_width)[0]
 
     def predict_batch(self, image_list: list, beam_width: int = 1, batch_size: int = 8) -> list:
         if not image_list:
             return []
-        if beam_width > 1:
-            logger.warning("beam search is not implemented on the CUDA path yet; decoding greedily")
-        return self._recognize_gray([ImagePreprocessor.to_gray(im) for im in image_list])
+        grays = [ImagePreprocessor.to_gray(im) for im in image_list]
+        if beam_width <= 1:
+            return self._recognize_gray(grays)
+        return self._beam_gray(grays, beam_width)

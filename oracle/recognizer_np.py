@@ -418,6 +418,44 @@ def greedy_decode(sd, memory, max_len=256, return_logits=False):
     return generated
 
 
+def log_softmax(x):
+    """F.log_softmax(x, dim=-1) in fp32 (predictor.py:115)."""
+    x = np.asarray(x, F32)
+    z = x - x.max(axis=-1, keepdims=True)
+    return (z - np.log(np.exp(z).sum(axis=-1, keepdims=True, dtype=F32))).astype(F32)
+
+
+def beam_search(sd, memory, beam_width=3, max_len=256):
+    """OCRPredictor._beam_search (predictor.py:101-136).  Scores are Python floats (sums of `.item()` values);
+    candidates = top-`beam_width` tokens of every live hypothesis, sorted by score with Python's STABLE sort
+    (ties keep hypothesis order, then top-k rank); a candidate ending in eos is moved to `completed` with its
+    score divided by len(seq) INCLUDING sos (:127) wherever it ranks, the first `beam_width` others survive;
+    result = best completed hypothesis, else the first live one.  Returns the id list (sos first, eos last if
+    completed) that the reference passes to Tokenizer.decode."""
+    beams = [(0.0, [SOS])]
+    completed = []
+    for _ in range(max_len):
+        logp = np.stack([log_softmax(decoder_forward(sd, seq, memory)[-1]) for _, seq in beams])
+        candidates = []
+        for i, (score, seq) in enumerate(beams):
+            order = np.argsort(-logp[i], kind="stable")[:beam_width]          # topk: descending values
+            for k in order:
+                candidates.append((score + float(logp[i, k]), seq + [int(k)]))
+        candidates.sort(key=lambda c: c[0], reverse=True)
+        nxt = []
+        for s, seq in candidates:
+            if seq[-1] == EOS:
+                completed.append((s / len(seq), seq))
+            elif len(nxt) < beam_width:
+                nxt.append((s, seq))
+        beams = nxt
+        if not beams:
+            break
+    if completed:
+        return sorted(completed, key=lambda c: c[0], reverse=True)[0][1]
+    return beams[0][1]
+
+
 def tokens_to_text(ids, idx2char):
     """Tokenizer.decode, tokenizer.py:26-35."""
     out = []

@@ -263,6 +263,12 @@ def stage_golden(args):
     batch_texts = pred.predict_batch([Image.fromarray(i) for i in imgs], beam_width=1, batch_size=8)
     assert batch_texts == texts
     g["texts"] = np.asarray(texts)
+    # beam search (OCRPredictor._beam_search, the default of `recognize`): widths 3 and 2 through both entry points
+    beam3 = [pred.predict(Image.fromarray(i), beam_width=3) for i in imgs]
+    assert pred.predict_batch([Image.fromarray(i) for i in imgs], beam_width=3, batch_size=4) == beam3
+    g["beam3_texts"] = np.asarray(beam3)
+    g["beam2_texts"] = np.asarray([pred.predict(Image.fromarray(i), beam_width=2) for i in imgs[:4]])
+    print("beam3 differs from greedy on", sum(a != b for a, b in zip(beam3, texts)), "of", len(texts), "lines", flush=True)
     np.savez_compressed(HERE / "golden_se.npz", **g)
 
     # ---- (3) VGG baseline (config 5) with the seeded init (no SE, no BiLSTM, bare conv7)

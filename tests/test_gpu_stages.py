@@ -234,3 +234,23 @@ def test_greedy_decode_semantics_seeded(rec_seeded_se):
             assert ids[t + 1] == int(np.argmax(trace[i, t, :124]))
         if ln[i] < 41:
             assert int(np.argmax(trace[i, ln[i] - 1, :124])) == 3      # stopped because of <eos>
+
+
+def test_se_fused_kernel_agrees_with_unfused_path(rec_seeded_se):
+    """The one-kernel SE block (squeeze + FCs on mma.sync + gate + pool) against the four-kernel version
+    (column means / two tcgen05 GEMMs / apply+pool): same bf16 roundings, so the pooled outputs agree to bf16 ulps."""
+    from khmer_ocr_cnn_transformer_b200 import _native
+    rec, _ = rec_seeded_se
+    imgs = _lines(6, 100, 1200, seed=21)
+    got = {}
+    try:
+        for mode in (0, 1):
+            rec.set_option("se_fused", mode)
+            rec.gather_chunks(_native.LineBatch(imgs))
+            rec.sevgg_encoder_forward()
+            got[mode] = {k: bf16_u16_to_f32(rec.debug_read(k)).copy() for k in ("pool3", "pool4", "patch_in")}
+    finally:
+        rec.set_option("se_fused", 1)
+    errs = {k: rel_err(got[1][k], got[0][k]) for k in got[0]}
+    _report("se_fused_vs_unfused_rel_err", errs)
+    assert max(errs.values()) < 5e-3, errs

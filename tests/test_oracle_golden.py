@@ -61,6 +61,22 @@ def test_se_model_stages_against_reference_outputs():
             assert max_err(logits, z[f"step_logits{i}"]) < 1e-3
 
 
+def test_beam_search_against_reference_outputs():
+    """oracle.beam_search == OCRPredictor._beam_search (predictor.py:101-136) on the reference's own memory."""
+    from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import build_vocab
+    z = _need("golden_se.npz")
+    if "beam3_texts" not in z.files:
+        pytest.skip("golden_se.npz predates the beam-search goldens")
+    idx2char = {v: k for k, v in build_vocab().items()}
+    sd = load_fixture_ckpt()
+    for i in (0, 1, 6):
+        assert O.tokens_to_text(O.beam_search(sd, z[f"mem{i}"], 3), idx2char) == str(z["beam3_texts"][i])
+    assert O.tokens_to_text(O.beam_search(sd, z["mem2"], 2), idx2char) == str(z["beam2_texts"][2])
+    # width 1 degenerates to the greedy loop
+    assert O.beam_search(sd, z["mem3"], 1)[:-1] == [int(t) for t in z["tokens3"]] or \
+        O.beam_search(sd, z["mem3"], 1) == [int(t) for t in z["tokens3"]]
+
+
 def test_vgg_baseline_against_reference_outputs():
     from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict
     z = _need("golden_vgg.npz")
