@@ -53,6 +53,7 @@ int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_b
 // ---- stage 4/5 helpers -----------------------------------------------------------------
 // per-chunk 32-token, 8-head attention: qkv bf16 [M, 1152] -> out bf16 [M, 384].
 int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
+void set_chunk_attention_impl(int impl);   // 1 = mma.sync kernel (default), 0 = CUDA-core kernel (A/B tests)
 // LayerNorm over 384: y = LN(x)*g + b (+ pos[row_pos[row]]); writes f32 and/or bf16 (+ residual lo part).
 // Input row = sum of nsplit split-K partials (x + s*rows*384) + in_bias + resid (optional).
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,

@@ -816,6 +816,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
+    if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }

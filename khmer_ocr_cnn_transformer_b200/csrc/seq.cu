@@ -81,7 +81,140 @@ __global__ void __launch_bounds__(256) chunk_attention_kernel(const __nv_bfloat1
                             pack_bf16(o[i * 8 + 4], o[i * 8 + 5]), pack_bf16(o[i * 8 + 6], o[i * 8 + 7]));
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core version: one CTA per chunk, warp = head.  The chunk's [32][1152] bf16 QKV block is copied to shared
+// memory with coalesced 16-byte loads (it is contiguous in HBM), every head then runs S = Q K^T (m16n8k16, fp32
+// accumulators), a register softmax (quad shuffles), and O = P V with the probabilities re-used directly as A
+// fragments (accumulator layout of S == A layout of the next MMA) and V read through ldmatrix.trans.  The output is
+// staged in the head's dead Q columns and written back as whole 768-byte rows.
+// 32 x 32 x 48 per head is far below a tcgen05 tile (M = 128), hence mma.sync here.
+// ------------------------------------------------------------------------------------------
+static constexpr int CA_LD = 3 * D_MODEL + 8;      // bf16 elements per smem row: 2320 B = odd multiple of 16 B
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                     __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t ca_smem[];
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(ca_smem);          // [32][CA_LD]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (long)blockIdx.x * TOK_PER_CHUNK * 3 * D_MODEL);
+    constexpr int ROW_U4 = 3 * D_MODEL / 8;        // 144 16-byte pieces per row
+#pragma unroll 6
+    for (int i = tid; i < TOK_PER_CHUNK * ROW_U4; i += 256) {
+        const int r = i / ROW_U4, c = i - r * ROW_U4;
+        *reinterpret_cast<uint4*>(sm + r * CA_LD + c * 8) = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint32_t sbase = smem_u32(sm);
+    const int qc = warp * HEAD_DIM, kc = D_MODEL + warp * HEAD_DIM, vc = 2 * D_MODEL + warp * HEAD_DIM;
+    const int g = lane >> 2, t = lane & 3;
+    // ldmatrix row addresses: x4 (A operand): lane -> matrix lane/8 = {rows 0-7 | rows 8-15} x {k 0-7 | k 8-15};
+    // x2 (B operand): lanes 0-7 -> rows at k0, lanes 8-15 -> rows at k0 + 8 (other lanes' addresses are ignored)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+    const int b_row = lane & 7, b_col = ((lane >> 3) & 1) * 8;
+    const float scale_log2 = rsqrtf((float)HEAD_DIM) * 1.4426950408889634f;    // softmax in base 2
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        // ---- S = Q K^T for 16 queries x 32 keys ----
+        float sacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < HEAD_DIM / 16; ++ks) {
+            uint32_t a[4];
+            ldsm_x4(a, sbase + ((mt * 16 + a_row) * CA_LD + qc + ks * 16 + a_col) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t b0, b1;
+                ldsm_x2(b0, b1, sbase + ((j * 8 + b_row) * CA_LD + kc + ks * 16 + b_col) * 2);
+                mma16816(sacc[j], a, b0, b1);
+            }
+        }
+        // ---- softmax over the 32 keys of rows g and g + 8 (values spread over the 4 lanes of a quad) ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        uint32_t pa[2][4];                           // P as A fragments of the two 16-key k-steps
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = pack_bf16(exp2f((sacc[j][0] - m0) * scale_log2), exp2f((sacc[j][1] - m0) * scale_log2));
+            const uint32_t hi = pack_bf16(exp2f((sacc[j][2] - m1) * scale_log2), exp2f((sacc[j][3] - m1) * scale_log2));
+            s0 += bf16_lo(lo) + bf16_hi(lo);         // sums of the ROUNDED weights: the applied weights add up to 1
+            s1 += bf16_lo(hi) + bf16_hi(hi);
+            pa[j >> 1][(j & 1) * 2] = lo;
+            pa[j >> 1][(j & 1) * 2 + 1] = hi;
+        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float inv0 = 1.f / s0, inv1 = 1.f / s1;
+        // ---- O = P V: 16 queries x 48 dims, K = 32 keys ----
+        float oacc[HEAD_DIM / 8][4];
+#pragma unroll
+        for (int j = 0; j < HEAD_DIM / 8; ++j) { oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int j = 0; j < HEAD_DIM / 8; ++j) {
+                uint32_t b0, b1;
+                // V[key][d] row-major, keys = K dimension: transposed 8x8 loads give B[k = 2t, 2t+1][n = g]
+                ldsm_x2_trans(b0, b1, sbase + ((ks * 16 + b_row + b_col) * CA_LD + vc + j * 8) * 2);
+                mma16816(oacc[j], pa[ks], b0, b1);
+            }
+        }
+        // ---- stage the output in this head's Q columns (rows of this m-tile: no other warp reads them) ----
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < HEAD_DIM / 8; ++j) {
+            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g) * CA_LD + qc + j * 8 + 2 * t) = pack_bf16(oacc[j][0] * inv0, oacc[j][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g + 8) * CA_LD + qc + j * 8 + 2 * t) = pack_bf16(oacc[j][2] * inv1, oacc[j][3] * inv1);
+        }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + (long)blockIdx.x * TOK_PER_CHUNK * D_MODEL);
+    constexpr int OUT_U4 = D_MODEL / 8;            // 48 pieces per output row
+#pragma unroll 2
+    for (int i = tid; i < TOK_PER_CHUNK * OUT_U4; i += 256) {
+        const int r = i / OUT_U4, c = i - r * OUT_U4;
+        dst[i] = *reinterpret_cast<const uint4*>(sm + r * CA_LD + c * 8);
+    }
+}
+
+static int g_chunk_attn_impl = 1;      // 1: mma.sync kernel, 0: CUDA-core kernel (kept for A/B tests)
+void set_chunk_attention_impl(int impl) { g_chunk_attn_impl = impl; }
+
 int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream) {
+    if (n_chunks > 0 && g_chunk_attn_impl == 1) {
+        const size_t smem_mma = (size_t)TOK_PER_CHUNK * CA_LD * 2;
+        static bool attr_set_mma = false;
+        if (!attr_set_mma) {
+            KOCR_CUDA(cudaFuncSetAttribute(chunk_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+            attr_set_mma = true;
+        }
+        chunk_attention_mma_kernel<<<n_chunks, 256, smem_mma, stream>>>(qkv, out);
+        KOCR_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (n_chunks == 0) return 0;
     const size_t smem = 8 * 2 * 32 * HEAD_DIM * sizeof(float);
     static bool attr_set = false;

@@ -254,3 +254,23 @@ def test_se_fused_kernel_agrees_with_unfused_path(rec_seeded_se):
     errs = {k: rel_err(got[1][k], got[0][k]) for k in got[0]}
     _report("se_fused_vs_unfused_rel_err", errs)
     assert max(errs.values()) < 5e-3, errs
+
+
+def test_chunk_attention_mma_agrees_with_cuda_core_kernel(rec_seeded_se):
+    """Per-chunk encoder attention on mma.sync (bf16 probabilities, fp32 accumulation) against the fp32 CUDA-core
+    kernel: encoder outputs agree far inside the parity tolerance."""
+    from khmer_ocr_cnn_transformer_b200 import _native
+    rec, _ = rec_seeded_se
+    imgs = _lines(6, 100, 1200, seed=22)
+    got = {}
+    try:
+        for mode in (0, 1):
+            rec.set_option("chunk_attn_impl", mode)
+            rec.gather_chunks(_native.LineBatch(imgs))
+            rec.sevgg_encoder_forward()
+            got[mode] = rec.debug_read("enc").copy()
+    finally:
+        rec.set_option("chunk_attn_impl", 1)
+    err = rel_err(got[1], got[0])
+    _report("chunk_attention_mma_vs_fp32_rel_err", err)
+    assert err < 5e-3, err

@@ -1,9 +1,11 @@
-"""Token-level parity of the CUDA path against the CPU oracle on the WHOLE c2 batch (256 lines), with a margin
-analysis of every mismatch.
+"""Token-level parity of the CUDA path against the CPU oracle on whole workloads, with a margin analysis of every
+mismatch and the CER of both sides against the ground-truth labels.
 
-  GPU box :  python tools/parity_c2.py dump      -> gpurun_out/c2_tokens.npz  (tokens + lengths from the CUDA path)
-  anywhere:  python tools/parity_c2.py oracle    -> profiles/r01/c2_oracle_tokens.npz (numpy oracle, host cores)
-  anywhere:  python tools/parity_c2.py compare   -> profiles/r01/parity_c2.json
+  workloads: c2 = the 256-line bench batch (widths 400-800, seed 0); c3 = 1024 lines of the mixed-width config
+             (widths 200-1600, seed 3)
+  GPU box :  python tools/parity_c2.py dump [c2|c3]    -> gpurun_out/<w>_tokens.npz  (tokens + lengths, CUDA path)
+  anywhere:  python tools/parity_c2.py oracle [c2|c3]  -> profiles/r01/<w>_oracle_tokens.npz (numpy oracle, host cores)
+  anywhere:  python tools/parity_c2.py compare [c2|c3] -> profiles/r01/parity_<w>.json
 """
 import json, sys, time, os
 from pathlib import Path
@@ -11,8 +13,10 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np
 
-ORACLE_NPZ = ROOT / "profiles" / "r01" / "c2_oracle_tokens.npz"
-GPU_NPZ = ROOT / "gpurun_out" / "c2_tokens.npz"
+WL = sys.argv[2] if len(sys.argv) > 2 else "c2"
+SPEC = {"c2": (256, 400, 800, 0), "c3": (1024, 200, 1600, 3)}[WL]
+ORACLE_NPZ = ROOT / "profiles" / "r01" / f"{WL}_oracle_tokens.npz"
+GPU_NPZ = ROOT / "gpurun_out" / f"{WL}_tokens.npz"
 
 
 def _oracle_line(img):
@@ -31,17 +35,23 @@ def _oracle_line(img):
     return toks, (top[:, 0] - top[:, 1]).astype(np.float32)
 
 
-def lines():
+def lines(with_labels=False):
     from khmer_ocr_cnn_transformer_b200 import synth
-    return synth.make_lines(256, 400, 800, seed=0)[0]
+    imgs, labels = synth.make_lines(SPEC[0], SPEC[1], SPEC[2], seed=SPEC[3])
+    return (imgs, labels) if with_labels else imgs
 
 
 def dump():
     from khmer_ocr_cnn_transformer_b200 import _native, weights
     from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
     sd = load_checkpoint(ROOT / "tests/golden/fixture_se_ckpt.npz")
-    rec = _native.Recognizer(weights.pack_blob(sd), max_lines=256, max_chunks=2816)
-    tok, ln = rec.recognize_lines(_native.LineBatch(lines()))
+    rec = _native.Recognizer(weights.pack_blob(sd), max_lines=256, max_chunks=5120)
+    imgs = lines()
+    toks, lns = [], []
+    for i in range(0, len(imgs), 256):
+        t, l = rec.recognize_lines(_native.LineBatch(imgs[i:i + 256]))
+        toks.append(t.copy()); lns.append(l.copy())
+    tok, ln = np.concatenate(toks), np.concatenate(lns)
     rec.close()
     GPU_NPZ.parent.mkdir(exist_ok=True)
     np.savez_compressed(GPU_NPZ, tokens=tok, lengths=ln)
@@ -53,9 +63,10 @@ def oracle():
     t0 = time.time()
     with Pool(int(os.environ.get("ORACLE_PROCS", "8"))) as pool:
         res = pool.map(_oracle_line, lines(), chunksize=1)
-    tokens = np.zeros((256, 257), np.int32)
-    lengths = np.zeros(256, np.int32)
-    gaps = np.zeros((256, 256), np.float32)
+    n = SPEC[0]
+    tokens = np.zeros((n, 257), np.int32)
+    lengths = np.zeros(n, np.int32)
+    gaps = np.zeros((n, 256), np.float32)
     for i, (t, g) in enumerate(res):
         tokens[i, :len(t)] = t
         lengths[i] = len(t)
@@ -70,9 +81,15 @@ def compare():
     g, o = np.load(GPU_NPZ), np.load(ORACLE_NPZ)
     idx2char = {v: k for k, v in build_vocab().items()}
     same, mism, cer_sum = 0, [], 0.0
-    for i in range(256):
+    n = SPEC[0]
+    labels = lines(with_labels=True)[1]
+    cer_gpu = cer_orc = 0.0
+    for i in range(n):
         a = [int(t) for t in g["tokens"][i, :g["lengths"][i]]]
         b = [int(t) for t in o["tokens"][i, :o["lengths"][i]]]
+        truth = O.tokens_to_text([int(t) for t in labels[i]], idx2char)
+        cer_gpu += O.cer(O.tokens_to_text(a, idx2char), truth)
+        cer_orc += O.cer(O.tokens_to_text(b, idx2char), truth)
         if a == b:
             same += 1
             continue
@@ -82,10 +99,12 @@ def compare():
         mism.append({"line": i, "first_diff_pos": k, "len_gpu": len(a), "len_oracle": len(b),
                      "oracle_top1_top2_gap_at_diff": float(o["gaps"][i, k - 1]) if k >= 1 else None, "cer_between": c})
     gaps = o["gaps"][o["gaps"] > 0]
-    out = {"workload": "c2 batch: 256 synthetic lines, fixture checkpoint", "identical": same, "of": 256,
-           "identity_rate": same / 256, "mean_cer_gpu_vs_oracle_all_lines": cer_sum / 256, "mismatches": mism,
+    out = {"workload": f"{WL}: {n} synthetic lines, resized width {SPEC[1]}-{SPEC[2]}, fixture checkpoint", "identical": same, "of": n,
+           "identity_rate": same / n, "mean_cer_gpu_vs_oracle_all_lines": cer_sum / n,
+           "mean_cer_vs_labels": {"cuda": cer_gpu / n, "oracle": cer_orc / n},
+           "mean_decoded_len": {"cuda": float(g["lengths"].mean()), "oracle": float(o["lengths"].mean())}, "mismatches": mism,
            "oracle_margin_percentiles": {p: float(np.percentile(gaps, p)) for p in (0.1, 1, 5, 50)}}
-    (ROOT / "profiles" / "r01" / "parity_c2.json").write_text(json.dumps(out, indent=1))
+    (ROOT / "profiles" / "r01" / f"parity_{WL}.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out, indent=1))
 
 
