@@ -399,8 +399,10 @@ def main():
     achieved_tf = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
     gemm_sites = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "patch_proj", "enc_qkv", "enc_out_proj",
                   "enc_ffn1", "enc_ffn2"]
-    stage_sites = gemm_sites + ["conv1_pool1", "pool2", "se3_pool3", "se4_pool4", "se5_finalpool", "enc_attention",
-                                "enc_layernorm"]
+    # every launch of stages 2-4: the GEMMs, conv1, the pools, the SE blocks (fused kernels, or - VGG baseline / A-B
+    # option - the squeeze / FC / apply kernels), per-chunk attention and LayerNorm
+    stage_sites = gemm_sites + ["conv1_pool1", "pool2", "enc_attention", "enc_layernorm"] + \
+        [s for s in kt if s.startswith("se")]
     stage_ms = sum(kt[s]["ms"] for s in stage_sites if s in kt) / max(args.steps, 1)
     stage_chunks_per_s = n_chunks / (stage_ms * 1e-3) if stage_ms > 0 else 0.0
     per_site = {s: {"ms_per_step": kt[s]["ms"] / args.steps,
