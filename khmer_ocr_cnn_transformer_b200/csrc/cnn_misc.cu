@@ -3,7 +3,7 @@
 //   2x2 max-pool after conv2                                                 se_model.py:43,65
 //   SequenceSE gate (mean over H -> FC -> ReLU -> FC -> sigmoid) + (2,1) pool  se_model.py:19-30,48-49,53-54
 //   SequenceSE gate + AdaptiveAvgPool2d((2,32)) -> patch-projection operand  se_model.py:59-61,76-78
-// All activations are bf16 in the padded-linear NHWC layout (common.cuh PLGeom); SE math is fp32.
+// All activations are a16 in the padded-linear NHWC layout (common.cuh PLGeom); SE math is fp32.
 #include "kernels.cuh"
 
 namespace kocr {
@@ -17,7 +17,7 @@ static constexpr int C1_IN_COLS = CHUNK_W + 2;
 
 __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict__ chunks,
                                                          const float* __restrict__ w, const float* __restrict__ b,
-                                                         __nv_bfloat16* __restrict__ out) {
+                                                         act16_t* __restrict__ out) {
     __shared__ float s_in[C1_IN_ROWS][C1_IN_COLS];
     __shared__ float s_w[9][64];
     __shared__ float s_b[64];
@@ -73,15 +73,15 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
                     }
                 res[j] = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + br[j], 0.f);
             }
-            o = make_uint4(pack_bf16(res[0], res[1]), pack_bf16(res[2], res[3]), pack_bf16(res[4], res[5]),
-                           pack_bf16(res[6], res[7]));
+            o = make_uint4(pack_a16(res[0], res[1]), pack_a16(res[2], res[3]), pack_a16(res[4], res[5]),
+                           pack_a16(res[6], res[7]));
         }
         const long q = (long)n * g.S + (long)oh * g.P + pw;
         reinterpret_cast<uint4*>(out + q * 64)[cg] = o;
     }
 }
 
-int launch_conv1_pool(const float* d_chunks, const float* w, const float* b, __nv_bfloat16* out, int n_chunks,
+int launch_conv1_pool(const float* d_chunks, const float* w, const float* b, act16_t* out, int n_chunks,
                       cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     conv1_pool_kernel<<<dim3(4, n_chunks), 256, 0, stream>>>(d_chunks, w, b, out);
@@ -92,16 +92,12 @@ int launch_conv1_pool(const float* d_chunks, const float* w, const float* b, __n
 // ------------------------------------------------------------------------------------------
 // 2x2 max-pool between padded-linear layouts.  One thread per (output position, 8 channels).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
 __device__ __forceinline__ uint4 max4(uint4 a, uint4 b) {
-    return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+    return make_uint4(a16x2_max(a.x, b.x), a16x2_max(a.y, b.y), a16x2_max(a.z, b.z), a16x2_max(a.w, b.w));
 }
 
-__global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __restrict__ in,
-                                                      __nv_bfloat16* __restrict__ out, long total, int H, int W,
+__global__ void __launch_bounds__(256) pool2x2_kernel(const act16_t* __restrict__ in,
+                                                      act16_t* __restrict__ out, long total, int H, int W,
                                                       int C) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -123,7 +119,7 @@ __global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __res
     reinterpret_cast<uint4*>(out)[idx] = o;
 }
 
-int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+int launch_pool2x2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C,
                    cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     const PLGeom go = make_pl(H / 2, W / 2);
@@ -138,9 +134,9 @@ int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, in
 // HBM-bound elementwise kernels; the two 1x1 Conv1d layers of the excitation are real contractions
 // over channels and run on the tcgen05 GEMM (reduced width padded to 128), see kocr_api.cu.
 // ------------------------------------------------------------------------------------------
-// squeeze: padded-linear (H, W, C) bf16 -> column means [n*W + w][C] bf16.  Thread per (n, w, 8 channels).
-__global__ void __launch_bounds__(256) se_col_mean_kernel(const __nv_bfloat16* __restrict__ in,
-                                                          __nv_bfloat16* __restrict__ means, long total, int H,
+// squeeze: padded-linear (H, W, C) a16 -> column means [n*W + w][C] a16.  Thread per (n, w, 8 channels).
+__global__ void __launch_bounds__(256) se_col_mean_kernel(const act16_t* __restrict__ in,
+                                                          act16_t* __restrict__ means, long total, int H,
                                                           int W, int C) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -153,16 +149,16 @@ __global__ void __launch_bounds__(256) se_col_mean_kernel(const __nv_bfloat16* _
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int h = 0; h < H; ++h) {
         const uint4 a = __ldg(p + (long)h * gi.P * cgs);
-        acc[0] += bf16_lo(a.x); acc[1] += bf16_hi(a.x); acc[2] += bf16_lo(a.y); acc[3] += bf16_hi(a.y);
-        acc[4] += bf16_lo(a.z); acc[5] += bf16_hi(a.z); acc[6] += bf16_lo(a.w); acc[7] += bf16_hi(a.w);
+        acc[0] += a16_lo(a.x); acc[1] += a16_hi(a.x); acc[2] += a16_lo(a.y); acc[3] += a16_hi(a.y);
+        acc[4] += a16_lo(a.z); acc[5] += a16_hi(a.z); acc[6] += a16_lo(a.w); acc[7] += a16_hi(a.w);
     }
     const float inv = 1.f / (float)H;
     reinterpret_cast<uint4*>(means)[idx] =
-        make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                   pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+        make_uint4(pack_a16(acc[0] * inv, acc[1] * inv), pack_a16(acc[2] * inv, acc[3] * inv),
+                   pack_a16(acc[4] * inv, acc[5] * inv), pack_a16(acc[6] * inv, acc[7] * inv));
 }
 
-int launch_se_col_mean(const __nv_bfloat16* in, __nv_bfloat16* means, int n_chunks, int H, int W, int C,
+int launch_se_col_mean(const act16_t* in, act16_t* means, int n_chunks, int H, int W, int C,
                        cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     const long total = (long)n_chunks * W * (C / 8);
@@ -179,9 +175,9 @@ __device__ __forceinline__ void load_gate8(const float* __restrict__ gate, long 
 
 // gate (optional, fp32 [n*W + w][C], already sigmoid-ed) * max over row pairs -> padded-linear (H/2, W, C).
 // The gate is positive, so max(x1*g, x2*g) == g*max(x1, x2) exactly (se_model.py:30,49).
-__global__ void __launch_bounds__(256) se_apply_pool_kernel(const __nv_bfloat16* __restrict__ in,
+__global__ void __launch_bounds__(256) se_apply_pool_kernel(const act16_t* __restrict__ in,
                                                             const float* __restrict__ gate,
-                                                            __nv_bfloat16* __restrict__ out, long total, int H,
+                                                            act16_t* __restrict__ out, long total, int H,
                                                             int W, int C) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -199,16 +195,16 @@ __global__ void __launch_bounds__(256) se_apply_pool_kernel(const __nv_bfloat16*
         if (gate) {
             float g[8];
             load_gate8(gate, ((long)n * W + ow) * C + cg * 8, g);
-            o = make_uint4(pack_bf16(bf16_lo(o.x) * g[0], bf16_hi(o.x) * g[1]),
-                           pack_bf16(bf16_lo(o.y) * g[2], bf16_hi(o.y) * g[3]),
-                           pack_bf16(bf16_lo(o.z) * g[4], bf16_hi(o.z) * g[5]),
-                           pack_bf16(bf16_lo(o.w) * g[6], bf16_hi(o.w) * g[7]));
+            o = make_uint4(pack_a16(a16_lo(o.x) * g[0], a16_hi(o.x) * g[1]),
+                           pack_a16(a16_lo(o.y) * g[2], a16_hi(o.y) * g[3]),
+                           pack_a16(a16_lo(o.z) * g[4], a16_hi(o.z) * g[5]),
+                           pack_a16(a16_lo(o.w) * g[6], a16_hi(o.w) * g[7]));
         }
     }
     reinterpret_cast<uint4*>(out)[idx] = o;
 }
 
-int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H, int W,
+int launch_se_apply_pool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H, int W,
                          int C, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     const PLGeom go = make_pl(H / 2, W);
@@ -220,9 +216,9 @@ int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat
 
 // gate (optional) * x, then AdaptiveAvgPool2d((2, 32)) -> patch-projection operand
 // out[n*32 + k][kh*C + c] (se_model.py:61,78: bin k covers columns [floor(k*W/32), ceil((k+1)*W/32))).
-__global__ void __launch_bounds__(256) se_apply_finalpool_kernel(const __nv_bfloat16* __restrict__ in,
+__global__ void __launch_bounds__(256) se_apply_finalpool_kernel(const act16_t* __restrict__ in,
                                                                  const float* __restrict__ gate,
-                                                                 __nv_bfloat16* __restrict__ out, long total, int H,
+                                                                 act16_t* __restrict__ out, long total, int H,
                                                                  int W, int C) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -240,19 +236,19 @@ __global__ void __launch_bounds__(256) se_apply_finalpool_kernel(const __nv_bflo
         if (gate) load_gate8(gate, ((long)n * W + w) * C + cg * 8, g);
         for (int h = h0; h < h1; ++h) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + ((long)n * gi.S + (long)h * gi.P + w) * C) + cg);
-            acc[0] += bf16_lo(a.x) * g[0]; acc[1] += bf16_hi(a.x) * g[1];
-            acc[2] += bf16_lo(a.y) * g[2]; acc[3] += bf16_hi(a.y) * g[3];
-            acc[4] += bf16_lo(a.z) * g[4]; acc[5] += bf16_hi(a.z) * g[5];
-            acc[6] += bf16_lo(a.w) * g[6]; acc[7] += bf16_hi(a.w) * g[7];
+            acc[0] += a16_lo(a.x) * g[0]; acc[1] += a16_hi(a.x) * g[1];
+            acc[2] += a16_lo(a.y) * g[2]; acc[3] += a16_hi(a.y) * g[3];
+            acc[4] += a16_lo(a.z) * g[4]; acc[5] += a16_hi(a.z) * g[5];
+            acc[6] += a16_lo(a.w) * g[6]; acc[7] += a16_hi(a.w) * g[7];
         }
     }
     const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
     reinterpret_cast<uint4*>(out)[idx] =
-        make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                   pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+        make_uint4(pack_a16(acc[0] * inv, acc[1] * inv), pack_a16(acc[2] * inv, acc[3] * inv),
+                   pack_a16(acc[4] * inv, acc[5] * inv), pack_a16(acc[6] * inv, acc[7] * inv));
 }
 
-int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H,
+int launch_se_apply_finalpool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H,
                               int W, int C, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     const long total = (long)n_chunks * TOK_PER_CHUNK * 2 * (C / 8);
@@ -266,13 +262,13 @@ int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_b
 // ONE CTA per chunk does squeeze (column means) -> FC1+ReLU -> FC2+sigmoid -> gate * x -> pool.
 // The chunk's activations (150 KB) are read twice by the same CTA, a few microseconds apart: the second read is an
 // L2 hit, so HBM sees one read of the conv output and one write of the pooled output (225 KB per chunk instead of
-// the ~580 KB of the four-kernel version with its bf16 means / fp32 gate round trips).
+// the ~580 KB of the four-kernel version with its a16 means / fp32 gate round trips).
 // The two 1x1 Conv1d layers are [25 columns -> 32] x C x C/16 contractions: far below a tcgen05 tile, so they
-// run on mma.sync.m16n8k16 (bf16, fp32 accumulate) with the column means / hidden vector as A operands in shared
+// run on mma.sync.m16n8k16 (a16, fp32 accumulate) with the column means / hidden vector as A operands in shared
 // memory and the weights read straight from L2 as B fragments.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_a16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." KOCR_MMA_A16 "." KOCR_MMA_A16 ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -282,7 +278,7 @@ static constexpr int SE_THREADS = 256;
 
 template <int C> struct SeSmem {
     static constexpr int R = C / 16;                       // reduced width (se_model.py:9,13)
-    static constexpr int LDA = C + 8;                      // bf16 elements per row of the means (conflict-free frags)
+    static constexpr int LDA = C + 8;                      // a16 elements per row of the means (conflict-free frags)
     static constexpr int LDZ = R + 8;
     static constexpr size_t A_BYTES = 32 * LDA * 2;
     static constexpr size_t Z_BYTES = 32 * LDZ * 2;
@@ -292,23 +288,23 @@ template <int C> struct SeSmem {
 
 // FINAL = false: (2,1) max-pool -> padded-linear (H/2, 25, C);  FINAL = true: AdaptiveAvgPool2d((2,32)) -> patch operand.
 template <int C, int H, bool FINAL>
-__global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bfloat16* __restrict__ in,
-                                                              const __nv_bfloat16* __restrict__ w0p /*[128][C]*/,
+__global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const act16_t* __restrict__ in,
+                                                              const act16_t* __restrict__ w0p /*[128][C]*/,
                                                               const float* __restrict__ b0p,
-                                                              const __nv_bfloat16* __restrict__ w2p /*[C][128]*/,
+                                                              const act16_t* __restrict__ w2p /*[C][128]*/,
                                                               const float* __restrict__ b2,
-                                                              __nv_bfloat16* __restrict__ out) {
+                                                              act16_t* __restrict__ out) {
     using S = SeSmem<C>;
     constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8, TPG = SE_THREADS / CG;
     extern __shared__ __align__(16) uint8_t se_smem[];
-    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(se_smem);
-    __nv_bfloat16* sZ = reinterpret_cast<__nv_bfloat16*>(se_smem + S::A_BYTES);
+    act16_t* sA = reinterpret_cast<act16_t*>(se_smem);
+    act16_t* sZ = reinterpret_cast<act16_t*>(se_smem + S::A_BYTES);
     float* sG = reinterpret_cast<float*>(se_smem + S::A_BYTES + S::Z_BYTES);
     const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const PLGeom gi = make_pl(H, SE_W);
     const uint4* src = reinterpret_cast<const uint4*>(in + (long)n * gi.S * C);
 
-    // ---- squeeze: mean over H of every (column, channel) -> bf16 A operand [32][C] (rows 25..31 zero) ----
+    // ---- squeeze: mean over H of every (column, channel) -> a16 A operand [32][C] (rows 25..31 zero) ----
     {
         const int cg = tid % CG, sub = tid / CG;
         const float inv = 1.f / (float)H;
@@ -323,13 +319,13 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     const uint4 a = v[h];
-                    acc[0] += bf16_lo(a.x); acc[1] += bf16_hi(a.x); acc[2] += bf16_lo(a.y); acc[3] += bf16_hi(a.y);
-                    acc[4] += bf16_lo(a.z); acc[5] += bf16_hi(a.z); acc[6] += bf16_lo(a.w); acc[7] += bf16_hi(a.w);
+                    acc[0] += a16_lo(a.x); acc[1] += a16_hi(a.x); acc[2] += a16_lo(a.y); acc[3] += a16_hi(a.y);
+                    acc[4] += a16_lo(a.z); acc[5] += a16_hi(a.z); acc[6] += a16_lo(a.w); acc[7] += a16_hi(a.w);
                 }
             }
             *reinterpret_cast<uint4*>(sA + w * LDA + cg * 8) =
-                make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                           pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+                make_uint4(pack_a16(acc[0] * inv, acc[1] * inv), pack_a16(acc[2] * inv, acc[3] * inv),
+                           pack_a16(acc[4] * inv, acc[5] * inv), pack_a16(acc[6] * inv, acc[7] * inv));
         }
     }
     __syncthreads();
@@ -340,8 +336,8 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
         if (warp < 2 * NT) {
             const int mt = warp / NT, nt = warp % NT;
             float d[4] = {0.f, 0.f, 0.f, 0.f};
-            const __nv_bfloat16* arow0 = sA + (mt * 16 + g) * LDA + 2 * t;
-            const __nv_bfloat16* wrow = w0p + (long)(nt * 8 + g) * C + 2 * t;
+            const act16_t* arow0 = sA + (mt * 16 + g) * LDA + 2 * t;
+            const act16_t* wrow = w0p + (long)(nt * 8 + g) * C + 2 * t;
 #pragma unroll 8
             for (int k = 0; k < C; k += 16) {
                 uint32_t a[4];
@@ -351,12 +347,12 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
                 a[3] = *reinterpret_cast<const uint32_t*>(arow0 + 8 * LDA + k + 8);
                 const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k));
                 const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8));
-                mma_bf16_16816(d, a, b0, b1);
+                mma_a16_16816(d, a, b0, b1);
             }
             const int col = nt * 8 + 2 * t;
             const float bb0 = __ldg(b0p + col), bb1 = __ldg(b0p + col + 1);
-            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g) * LDZ + col) = pack_bf16(fmaxf(d[0] + bb0, 0.f), fmaxf(d[1] + bb1, 0.f));
-            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g + 8) * LDZ + col) = pack_bf16(fmaxf(d[2] + bb0, 0.f), fmaxf(d[3] + bb1, 0.f));
+            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g) * LDZ + col) = pack_a16(fmaxf(d[0] + bb0, 0.f), fmaxf(d[1] + bb1, 0.f));
+            *reinterpret_cast<uint32_t*>(sZ + (mt * 16 + g + 8) * LDZ + col) = pack_a16(fmaxf(d[2] + bb0, 0.f), fmaxf(d[3] + bb1, 0.f));
         }
     }
     __syncthreads();
@@ -368,7 +364,7 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const __nv_bfloat16* zr = sZ + (mt * 16 + g) * LDZ + ks * 16 + 2 * t;
+                const act16_t* zr = sZ + (mt * 16 + g) * LDZ + ks * 16 + 2 * t;
                 a[mt][ks][0] = *reinterpret_cast<const uint32_t*>(zr);
                 a[mt][ks][1] = *reinterpret_cast<const uint32_t*>(zr + 8 * LDZ);
                 a[mt][ks][2] = *reinterpret_cast<const uint32_t*>(zr + 8);
@@ -378,7 +374,7 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
 #pragma unroll 4
         for (int i = 0; i < NT_PER_WARP; ++i) {
             const int c0 = (warp * NT_PER_WARP + i) * 8;
-            const __nv_bfloat16* wrow = w2p + (long)(c0 + g) * 128 + 2 * t;
+            const act16_t* wrow = w2p + (long)(c0 + g) * 128 + 2 * t;
             uint32_t b[KS][2];
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
@@ -391,7 +387,7 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
             for (int mt = 0; mt < 2; ++mt) {
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) mma_bf16_16816(d, a[mt][ks], b[ks][0], b[ks][1]);
+                for (int ks = 0; ks < KS; ++ks) mma_a16_16816(d, a[mt][ks], b[ks][0], b[ks][1]);
                 const int r0 = mt * 16 + g, r1 = r0 + 8;
                 if (r0 < SE_W)
                     *reinterpret_cast<float2*>(sG + r0 * C + col) =
@@ -417,10 +413,10 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
                 o = max4(__ldg(p), __ldg(p + (long)gi.P * CG));
                 const float4 ga = *reinterpret_cast<const float4*>(sG + ow * C + cg * 8);
                 const float4 gb = *reinterpret_cast<const float4*>(sG + ow * C + cg * 8 + 4);
-                o = make_uint4(pack_bf16(bf16_lo(o.x) * ga.x, bf16_hi(o.x) * ga.y),
-                               pack_bf16(bf16_lo(o.y) * ga.z, bf16_hi(o.y) * ga.w),
-                               pack_bf16(bf16_lo(o.z) * gb.x, bf16_hi(o.z) * gb.y),
-                               pack_bf16(bf16_lo(o.w) * gb.z, bf16_hi(o.w) * gb.w));
+                o = make_uint4(pack_a16(a16_lo(o.x) * ga.x, a16_hi(o.x) * ga.y),
+                               pack_a16(a16_lo(o.y) * ga.z, a16_hi(o.y) * ga.w),
+                               pack_a16(a16_lo(o.z) * gb.x, a16_hi(o.z) * gb.y),
+                               pack_a16(a16_lo(o.w) * gb.z, a16_hi(o.w) * gb.w));
             }
             dst[idx] = o;
         }
@@ -437,21 +433,21 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const __nv_bflo
                 const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
                 for (int h = h0; h < h1; ++h) {
                     const uint4 a = __ldg(src + (long)(h * gi.P + w) * CG + cg);
-                    acc[0] += bf16_lo(a.x) * ga.x; acc[1] += bf16_hi(a.x) * ga.y;
-                    acc[2] += bf16_lo(a.y) * ga.z; acc[3] += bf16_hi(a.y) * ga.w;
-                    acc[4] += bf16_lo(a.z) * gb.x; acc[5] += bf16_hi(a.z) * gb.y;
-                    acc[6] += bf16_lo(a.w) * gb.z; acc[7] += bf16_hi(a.w) * gb.w;
+                    acc[0] += a16_lo(a.x) * ga.x; acc[1] += a16_hi(a.x) * ga.y;
+                    acc[2] += a16_lo(a.y) * ga.z; acc[3] += a16_hi(a.y) * ga.w;
+                    acc[4] += a16_lo(a.z) * gb.x; acc[5] += a16_hi(a.z) * gb.y;
+                    acc[6] += a16_lo(a.w) * gb.z; acc[7] += a16_hi(a.w) * gb.w;
                 }
             }
             const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
-            dst[idx] = make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                                  pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
+            dst[idx] = make_uint4(pack_a16(acc[0] * inv, acc[1] * inv), pack_a16(acc[2] * inv, acc[3] * inv),
+                                  pack_a16(acc[4] * inv, acc[5] * inv), pack_a16(acc[6] * inv, acc[7] * inv));
         }
     }
 }
 
 template <int C, int H, bool FINAL>
-static int launch_se_fused_impl(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks,
+static int launch_se_fused_impl(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks,
                                 cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -465,7 +461,7 @@ static int launch_se_fused_impl(const __nv_bfloat16* in, const SEWeights& w, __n
 }
 
 // The three SE sites of the backbone (se_model.py:47,53,59): (C, H) = (256, 12), (512, 6) and (512, 3) + final pool.
-int launch_se_fused(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+int launch_se_fused(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks, int H, int W, int C,
                     bool final_pool, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     if (W == SE_W && C == 256 && H == 12 && !final_pool) return launch_se_fused_impl<256, 12, false>(in, w, out, n_chunks, stream);

@@ -1,14 +1,35 @@
-// Shared helpers for the sm_100a kernels: error plumbing, bf16 packing, PTX wrappers for
+// Shared helpers for the sm_100a kernels: error plumbing, a16 packing, PTX wrappers for
 // mbarrier / TMA / tcgen05 (TMEM + UMMA).  Compile with -gencode arch=compute_100a,code=sm_100a.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 namespace kocr {
+
+// ------------------------------------------------------------------------------------------
+// "a16" = the 16-bit storage format of activations and tensor-core operands on stages 2-5a.
+// Default: IEEE fp16 (11 significant bits).  The tensor pipe runs fp16 and bf16 at the same rate
+// (tcgen05.mma.kind::f16 takes either), HBM traffic is identical, and the 8x finer rounding is what gets
+// greedy-decoded token sequences to agree with the fp32 reference (with bf16 storage 2 of
+// 256 lines of the c2 batch flip a near-tie).  Every layer on this path is BatchNorm/LayerNorm-bounded;
+// conversions saturate to +-65504 instead of overflowing to inf.  -DKOCR_A16_BF16 builds the bf16 variant.
+// ------------------------------------------------------------------------------------------
+#ifdef KOCR_A16_BF16
+typedef __nv_bfloat16 act16_t;
+typedef __nv_bfloat162 act16x2_t;
+#define KOCR_A16_FORMAT 0
+#define KOCR_MMA_A16 "bf16"
+#else
+typedef __half act16_t;
+typedef __half2 act16x2_t;
+#define KOCR_A16_FORMAT 1
+#define KOCR_MMA_A16 "f16"
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Host-side error plumbing: every C-ABI entry returns int (0 ok); the message is thread-local.
@@ -84,12 +105,30 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+#ifdef KOCR_A16_BF16
+__device__ __forceinline__ uint32_t pack_a16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float a16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float a16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ act16_t to_a16(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float from_a16(act16_t x) { return __bfloat162float(x); }
+#else
+__device__ __forceinline__ uint32_t pack_a16(float lo, float hi) {      // round to nearest even, saturating
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float a16_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float a16_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ act16_t to_a16(float x) { return __ushort_as_half((unsigned short)(pack_a16(x, 0.f) & 0xffffu)); }
+__device__ __forceinline__ float from_a16(act16_t x) { return __half2float(x); }
+#endif
+__device__ __forceinline__ uint32_t a16x2_max(uint32_t a, uint32_t b) {
+    act16x2_t r = __hmax2(*reinterpret_cast<act16x2_t*>(&a), *reinterpret_cast<act16x2_t*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -193,7 +232,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B (64 bf16), 8-row
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B (64 a16), 8-row
 // atoms 1024 B apart (SBO), LBO unused.  bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version = 1 (sm_100), [49,52) base offset, [61,64) layout (2 = SWIZZLE_128B).
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
@@ -206,15 +245,16 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor, A and B K-major, D = f32, M x N tile.  fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32).
+// Instruction descriptor, A and B K-major, D = f32, M x N tile.  fmt (A and B operand format): 0 = F16, 1 = BF16 (both kind::f16), 2 = TF32 (kind::tf32).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return make_idesc(M, N, 1u); }
+static constexpr uint32_t IDESC_FMT_A16 = KOCR_A16_FORMAT == 1 ? 0u : 1u;
+__host__ __device__ constexpr uint32_t make_idesc_a16(int M, int N) { return make_idesc(M, N, IDESC_FMT_A16); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+__device__ __forceinline__ void umma_a16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

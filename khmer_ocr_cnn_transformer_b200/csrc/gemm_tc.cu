@@ -2,7 +2,7 @@
 //
 // CTA = 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
 // (one lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
-// Tile = 128 (M) x BN (N, 128 or 256), K step 64 bf16 = one 128-byte swizzle atom per row.
+// Tile = 128 (M) x BN (N, 128 or 256), K step 64 a16 = one 128-byte swizzle atom per row.
 // Accumulators: 2 stages x BN fp32 columns in TMEM so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Operands: NSTAGE-deep ring of {A 16 KB, B BN*128 B} in shared memory.
 #include "gemm_tc.cuh"
@@ -34,7 +34,7 @@ struct GemmKernelParams {
     GemmEpilogue ep;
 };
 
-// BK is 128 bytes of K per row in both precisions: 64 bf16 or 32 fp32 (TF32) elements.
+// BK is 128 bytes of K per row in both precisions: 64 a16 or 32 fp32 (TF32) elements.
 template <int BN, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -95,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(BM, BN, TF32 ? 2u : 1u);
+        constexpr uint32_t idesc = make_idesc(BM, BN, TF32 ? 2u : IDESC_FMT_A16);
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -115,9 +115,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t db = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        // one MMA consumes 32 B of K (16 bf16 / 8 tf32) inside the 128 B swizzle row: +2 (16-byte units)
+                        // one MMA consumes 32 B of K (16 a16 / 8 tf32) inside the 128 B swizzle row: +2 (16-byte units)
                         if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_a16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem slot
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator ready
@@ -137,11 +137,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // two 4 KB buffers per warp: the addend block of chunk c+1 streams in (cp.async) while chunk c is processed
         const uint32_t stg_base = smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES + 256 + quad * 8192);
         // staging addressing (16-byte pieces, XOR-swizzled so that both the row-wise and the piece-wise access
-        // patterns are bank-conflict free): fp32 rows of 8 pieces, bf16 rows of 4 pieces
+        // patterns are bank-conflict free): fp32 rows of 8 pieces, a16 rows of 4 pieces
         const uint32_t own32 = lane * 128, own16 = lane * 64;     // offsets inside a staging buffer
         const int sw32 = lane & 7, sw16 = (lane >> 1) & 3;
         const int r32 = lane >> 3, p32 = lane & 7;     // cooperative fp32 access: 4 rows x 8 pieces per instruction
-        const int r16 = lane >> 2, p16 = lane & 3;     // cooperative bf16 access: 8 rows x 4 pieces per instruction
+        const int r16 = lane >> 2, p16 = lane & 3;     // cooperative a16 access: 8 rows x 4 pieces per instruction
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -233,29 +233,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     __syncwarp();
                 }
-                if (ep.out_bf16) {
+                if (ep.out_a16) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         st_shared_v4u(stg_u32 + own16 + ((j ^ sw16) << 4),
-                                      make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7])));
+                                      make_uint4(pack_a16(f[8 * j], f[8 * j + 1]), pack_a16(f[8 * j + 2], f[8 * j + 3]),
+                                                 pack_a16(f[8 * j + 4], f[8 * j + 5]), pack_a16(f[8 * j + 6], f[8 * j + 7])));
                     __syncwarp();
-                    __nv_bfloat16* o = ep.out_bf16 + row0 * ep.ld_bf16 + nc + p16 * 8;
+                    act16_t* o = ep.out_a16 + row0 * ep.ld_a16 + nc + p16 * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + r16;
                         const uint4 a = ld_shared_v4u(stg_u32 + rr * 64 + ((p16 ^ ((rr >> 1) & 3)) << 4));
-                        if (rr < rows_here) *reinterpret_cast<uint4*>(o + (long)rr * ep.ld_bf16) = a;
+                        if (rr < rows_here) *reinterpret_cast<uint4*>(o + (long)rr * ep.ld_a16) = a;
                     }
                     __syncwarp();
-                    if (ep.out_bf16_lo && row < p.M) {
-                        uint4* ol = reinterpret_cast<uint4*>(ep.out_bf16_lo + row * ep.ld_bf16 + nc);
+                    if (ep.out_a16_lo && row < p.M) {
+                        uint4* ol = reinterpret_cast<uint4*>(ep.out_a16_lo + row * ep.ld_a16 + nc);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
+                        for (int j = 0; j < 32; ++j) f[j] -= from_a16(to_a16(f[j]));
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            ol[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                            ol[j] = make_uint4(pack_a16(f[8 * j], f[8 * j + 1]), pack_a16(f[8 * j + 2], f[8 * j + 3]),
+                                               pack_a16(f[8 * j + 4], f[8 * j + 5]), pack_a16(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
             };
@@ -290,8 +290,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // CUDA-core check kernel (tests only): one thread per output element, fp32 accumulation.
 // ------------------------------------------------------------------------------------------
-__global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ a, long rowsA,
-                                       const __nv_bfloat16* __restrict__ w, GemmKernelParams p) {
+__global__ void gemm_simt_check_kernel(const act16_t* __restrict__ a, long rowsA,
+                                       const act16_t* __restrict__ w, GemmKernelParams p) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)p.M * p.N) return;
     const long row = idx / p.N;
@@ -302,9 +302,9 @@ __global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ a, long
     for (int t = 0; t < p.taps; ++t) {
         const long ar = row + p.tap_off[t];
         if (ar < 0 || ar >= rowsA) continue;
-        const __nv_bfloat16* ap = a + ar * cin;
-        const __nv_bfloat16* wp = w + (long)n * p.taps * cin + (long)t * cin;
-        for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(ap[c]), __bfloat162float(wp[c]), acc);
+        const act16_t* ap = a + ar * cin;
+        const act16_t* wp = w + (long)n * p.taps * cin + (long)t * cin;
+        for (int c = 0; c < cin; ++c) acc = fmaf(from_a16(ap[c]), from_a16(wp[c]), acc);
     }
     if (ep.bias) acc += ep.bias[n];
     if (ep.addend) {
@@ -319,11 +319,11 @@ __global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ a, long
         if (!(h < ep.pl_H && ww < ep.pl_W)) acc = 0.f;
     }
     if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + n] = acc;
-    if (ep.out_bf16) {
-        ep.out_bf16[row * ep.ld_bf16 + n] = __float2bfloat16_rn(acc);
-        if (ep.out_bf16_lo)
-            ep.out_bf16_lo[row * ep.ld_bf16 + n] =
-                __float2bfloat16_rn(acc - __bfloat162float(__float2bfloat16_rn(acc)));
+    if (ep.out_a16) {
+        ep.out_a16[row * ep.ld_a16 + n] = to_a16(acc);
+        if (ep.out_a16_lo)
+            ep.out_a16_lo[row * ep.ld_a16 + n] =
+                to_a16(acc - from_a16(to_a16(acc)));
     }
 }
 
@@ -347,7 +347,7 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// row-major [rows, cols] matrix of bf16 (esize 2) or fp32 (esize 4), box = {128 bytes of K, box_rows},
+// row-major [rows, cols] matrix of a16 (esize 2) or fp32 (esize 4), box = {128 bytes of K, box_rows},
 // 128-byte swizzle, zero OOB fill.
 static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esize) {
     typedef std::tuple<const void*, uint64_t, uint64_t, uint32_t, int> Key;
@@ -365,7 +365,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t 
     cuuint64_t gstride[1] = {cols * (uint64_t)esize};
     cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(out, esize == 2 ? (KOCR_A16_FORMAT == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(ptr), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -396,7 +396,7 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     kp.kb_per_split = (total_kb + kp.split_k - 1) / kp.split_k;
     KOCR_CHECK((kp.split_k - 1) * kp.kb_per_split < total_kb, "gemm: split_k %d leaves an empty K slice", kp.split_k);
     if (kp.split_k > 1)
-        KOCR_CHECK(p.taps == 1 && p.ep.out_f32 && !p.ep.out_bf16 && !p.ep.bias && !p.ep.addend && !p.ep.relu && p.ep.pl_S == 0,
+        KOCR_CHECK(p.taps == 1 && p.ep.out_f32 && !p.ep.out_a16 && !p.ep.bias && !p.ep.addend && !p.ep.relu && p.ep.pl_S == 0,
                    "gemm: split-K writes raw fp32 partial sums only");
     kp.ep = p.ep;
     return 0;
@@ -439,9 +439,9 @@ int launch_gemm_tc(const void* a, long rowsA, const void* w, const GemmProblem& 
     return 2;
 }
 
-int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w, const GemmProblem& p,
+int launch_gemm_simt_check(const act16_t* a, long rowsA, const act16_t* w, const GemmProblem& p,
                            cudaStream_t stream) {
-    KOCR_CHECK(!p.tf32, "gemm check kernel: bf16 operands only");
+    KOCR_CHECK(!p.tf32, "gemm check kernel: a16 operands only");
     GemmKernelParams kp;
     KOCR_TRY(fill_params(kp, p, 128));
     const long total = (long)p.M * p.N;

@@ -21,20 +21,20 @@ struct GemmEpilogue {
     int ld_add;
     int add_period;
     // outputs (either may be null)
-    __nv_bfloat16* out_bf16;
-    int ld_bf16;
+    act16_t* out_a16;
+    int ld_a16;
     float* out_f32;
     int ld_f32;
-    // optional second bf16 copy holding the rounding residual (x - bf16(x)) for split-precision
-    // ("bf16x3") consumers; written at out_bf16_lo with the same leading dimension.
-    __nv_bfloat16* out_bf16_lo;
+    // optional second a16 copy holding the rounding residual (x - a16(x)) for split-precision
+    // ("a16x3") consumers; written at out_a16_lo with the same leading dimension.
+    act16_t* out_a16_lo;
 };
 
 struct GemmProblem {
     int M, N;                 // output rows / cols (N multiple of the N tile)
     int taps;                 // 1 (linear) or 9 (3x3 conv)
-    int cin;                  // K per tap in elements (multiple of 64 for bf16, of 32 for tf32)
-    int tf32;                 // 0: bf16 operands (kind::f16), 1: fp32 operands consumed as TF32 (kind::tf32)
+    int cin;                  // K per tap in elements (multiple of 64 for a16, of 32 for tf32)
+    int tf32;                 // 0: a16 operands (kind::f16), 1: fp32 operands consumed as TF32 (kind::tf32)
     int split_k;              // <= 1: whole K per tile.  s > 1 (linear, fp32 output only): K is cut into s slices, slice i
                               // writes its raw partial sums to out_f32 + i*M*ld_f32 (no bias/addend/activation: the
                               // consumer adds the slices).  Used by the decode loop to spread tiny GEMMs over many SMs.
@@ -43,12 +43,12 @@ struct GemmProblem {
     GemmEpilogue ep;
 };
 
-// Host launchers (defined in gemm_tc.cu).  a: [rowsA, cin] row-major, w: [N, taps*cin] (bf16 unless p.tf32).
+// Host launchers (defined in gemm_tc.cu).  a: [rowsA, cin] row-major, w: [N, taps*cin] (a16 unless p.tf32).
 // With p.tf32 the operands are fp32 arrays (a: [rowsA, cin], w: [N, taps*cin]) read by the tensor core as TF32.
 int launch_gemm_tc(const void* a, long rowsA, const void* w,
                    const GemmProblem& p, int num_sms, cudaStream_t stream);
 // CUDA-core restatement of the same contract; used ONLY by tests to localise tcgen05 bugs.
-int launch_gemm_simt_check(const __nv_bfloat16* a, long rowsA, const __nv_bfloat16* w,
+int launch_gemm_simt_check(const act16_t* a, long rowsA, const act16_t* w,
                            const GemmProblem& p, cudaStream_t stream);
 long gemm_tc_launch_count();
 

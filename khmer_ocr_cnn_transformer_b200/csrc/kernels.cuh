@@ -31,63 +31,63 @@ int preprocess_vtab_ints_per_line();
 int preprocess_kmax();
 
 // ---- stage 2 helpers -------------------------------------------------------------------
-// conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool: f32 chunks -> bf16 padded-linear (24x50, 64).
+// conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool: f32 chunks -> a16 padded-linear (24x50, 64).
 int launch_conv1_pool(const float* d_chunks, const float* w /*[64][9]*/, const float* b /*[64]*/,
-                      __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
+                      act16_t* out, int n_chunks, cudaStream_t stream);
 // 2x2 max-pool between padded-linear layouts (C multiple of 8).
-int launch_pool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
-// 1D-SE: squeeze -> column means bf16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;
+int launch_pool2x2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
+// 1D-SE: squeeze -> column means a16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;
 // gate fp32 [n*W + w][C] (null = no SE) * (2,1) max-pool -> padded-linear (H/2, W, C), or
 // gate * x -> AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n*32 + k][kh*C + c].
-struct SEWeights { const __nv_bfloat16* w0p; const float* b0p; const __nv_bfloat16* w2p; const float* b2; };
+struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; const float* b2; };
 // Fused SE block: squeeze + FC1/ReLU + FC2/sigmoid + gate*x + pool in one kernel, one CTA per chunk (W = 25).
-int launch_se_fused(const __nv_bfloat16* in, const SEWeights& w, __nv_bfloat16* out, int n_chunks, int H, int W, int C,
+int launch_se_fused(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks, int H, int W, int C,
                     bool final_pool, cudaStream_t stream);
-int launch_se_col_mean(const __nv_bfloat16* in, __nv_bfloat16* means, int n_chunks, int H, int W, int C,
+int launch_se_col_mean(const act16_t* in, act16_t* means, int n_chunks, int H, int W, int C,
                        cudaStream_t stream);
-int launch_se_apply_pool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H, int W,
+int launch_se_apply_pool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H, int W,
                          int C, cudaStream_t stream);
-int launch_se_apply_finalpool(const __nv_bfloat16* in, const float* gate, __nv_bfloat16* out, int n_chunks, int H,
+int launch_se_apply_finalpool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H,
                               int W, int C, cudaStream_t stream);
 
 // ---- stage 4/5 helpers -----------------------------------------------------------------
-// per-chunk 32-token, 8-head attention: qkv bf16 [M, 1152] -> out bf16 [M, 384].
-int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream);
+// per-chunk 32-token, 8-head attention: qkv a16 [M, 1152] -> out a16 [M, 384].
+int launch_chunk_attention(const act16_t* qkv, act16_t* out, int n_chunks, cudaStream_t stream);
 void set_chunk_attention_impl(int impl);   // 1 = mma.sync kernel (default), 0 = CUDA-core kernel (A/B tests)
-// LayerNorm over 384: y = LN(x)*g + b (+ pos[row_pos[row]]); writes f32 and/or bf16 (+ residual lo part).
+// LayerNorm over 384: y = LN(x)*g + b (+ pos[row_pos[row]]); writes f32 and/or a16 (+ residual lo part).
 // Input row = sum of nsplit split-K partials (x + s*rows*384) + in_bias + resid (optional).
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
-                     float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
+                     float* out_f32, act16_t* out_a16, act16_t* out_a16_lo, int rows,
                      cudaStream_t stream, int nsplit = 1, const float* in_bias = nullptr,
                      const float* resid = nullptr);
-// f32 [rows, 384] (+ pos[row_pos[row]]) -> f32 + bf16 copies (VGG merge path without LN).
-int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
-                   __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream);
+// f32 [rows, 384] (+ pos[row_pos[row]]) -> f32 + a16 copies (VGG merge path without LN).
+int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
+                   act16_t* out_a16_lo, int rows, cudaStream_t stream);
 
 // BiLSTM recurrence (input projection already in gin): persistent 2-CTA cluster kernel.
 struct LstmGroup { int line[8]; };   // lines handled together by one cluster (-1 = unused)
-int launch_bilstm(const float* gin /*[Mtok,1536]*/, const __nv_bfloat16* whh_packed, const int* line_tok_off,
+int launch_bilstm(const float* gin /*[Mtok,1536]*/, const act16_t* whh_packed, const int* line_tok_off,
                   const int* line_T, const LstmGroup* groups, int n_groups, float* mem_f32,
-                  __nv_bfloat16* mem_bf16, __nv_bfloat16* mem_bf16_lo, cudaStream_t stream);
+                  act16_t* mem_a16, act16_t* mem_a16_lo, cudaStream_t stream);
 size_t bilstm_whh_packed_elems();
 // tensor-core version: groups of 16 lines, recurrent weights as register-resident mma.sync fragments
 struct LstmGroup16 { int line[16]; };
-int launch_bilstm_mma(const float* gin, const __nv_bfloat16* whh_mma, const int* line_tok_off, const int* line_T,
-                      const LstmGroup16* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
-                      __nv_bfloat16* mem_bf16_lo, cudaStream_t stream);
+int launch_bilstm_mma(const float* gin, const act16_t* whh_mma, const int* line_tok_off, const int* line_T,
+                      const LstmGroup16* groups, int n_groups, float* mem_f32, act16_t* mem_a16,
+                      act16_t* mem_a16_lo, cudaStream_t stream);
 size_t bilstm_whh_mma_elems();
 
 // ---- decoder step kernels ---------------------------------------------------------------
 // The generated position of a step is t = *step_base + step_off: step_base lives on the device so that a
 // captured CUDA graph of 8 steps can be replayed for every group of 8 positions.
 int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base, int step_off, const float* tok_emb,
-                     const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
+                     const float* pos_emb, float* x, act16_t* xb, act16_t* xb_lo, int n_lines,
                      cudaStream_t stream);
 int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache,
                          float* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
                          int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream,
                          int nsplit, const float* bias);
-int launch_dec_cross_attn(const float* q /*[L,384]*/, const __nv_bfloat16* kv /*[Mtok,1536]*/, int layer,
+int launch_dec_cross_attn(const float* q /*[L,384]*/, const act16_t* kv /*[Mtok,1536]*/, int layer,
                           const int* line_tok_off, const int* line_T, int max_T, const int* finished,
                           float* out, int n_lines, cudaStream_t stream, int nsplit, const float* bias);
 int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,

@@ -35,7 +35,7 @@ struct BlobHeader { char magic[8]; uint32_t n_entries; uint32_t reserved; };
 struct BlobEntry { char name[48]; uint32_t dtype; uint32_t pad; uint64_t offset; uint64_t nbytes; };
 
 struct EncLayerW {
-    const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;
+    const act16_t *in_w, *out_w, *l1_w, *l2_w;
     const float *in_b, *out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b;
 };
 struct DecLayerW {
@@ -62,20 +62,20 @@ struct kocr_handle {
     size_t blob_bytes = 0;
     std::map<std::string, std::pair<const void*, size_t>> w;
     const float *conv1_w, *conv1_b;
-    const __nv_bfloat16* conv_w[8];
+    const act16_t* conv_w[8];
     const float* conv_b[8];
     SEWeights se[3];
-    const __nv_bfloat16* patch_w; const float *patch_b, *patch_pos;
+    const act16_t* patch_w; const float *patch_b, *patch_pos;
     EncLayerW enc[2];
     const float* global_pos;
-    const __nv_bfloat16 *lstm_w_ih, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
+    const act16_t *lstm_w_ih, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
     int straggler_threshold = 0; // >0: decode_greedy returns early once <= this many lines are still active;
                                  // the caller re-submits those lines (kocr_read_unfinished) in a later batch
     int big_gemm_sms = 0;        // >0: persistent grid size of the stage 2-5a GEMMs (leave SMs to other streams)
     int lstm_impl = 1;           // 1 = tensor-core recurrence (mma fragments in registers), 0 = CUDA-core / SMEM weights
     const float *dec_tok_emb, *dec_pos;
     DecLayerW dec[2];
-    const __nv_bfloat16* dec_kv_w; const float* dec_out_w; const float *dec_kv_b, *dec_out_b;
+    const act16_t* dec_kv_w; const float* dec_out_w; const float *dec_kv_b, *dec_out_b;
     // workspace
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
@@ -134,7 +134,7 @@ int lookup(kocr_handle* h, const char* name, const void** out, size_t min_bytes)
     return 0;
 }
 #define W_F32(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 4))
-#define W_BF16(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 2))
+#define W_A16(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 2))
 
 int resolve_weights(kocr_handle* h) {
     const int D = D_MODEL;
@@ -144,35 +144,35 @@ int resolve_weights(kocr_handle* h) {
     W_F32(h->conv1_b, "conv1.b", 64);
     char nm[64];
     for (int i = 2; i <= 7; ++i) {
-        snprintf(nm, sizeof nm, "conv%d.w", i); W_BF16(h->conv_w[i], nm, (size_t)cout[i] * 9 * cin[i]);
+        snprintf(nm, sizeof nm, "conv%d.w", i); W_A16(h->conv_w[i], nm, (size_t)cout[i] * 9 * cin[i]);
         snprintf(nm, sizeof nm, "conv%d.b", i); W_F32(h->conv_b[i], nm, cout[i]);
     }
     if (h->variant == 0) {
         static const int sc[3] = {256, 512, 512};
         for (int i = 0; i < 3; ++i) {
             const int C = sc[i];
-            snprintf(nm, sizeof nm, "se%d.w0p", i + 3); W_BF16(h->se[i].w0p, nm, 128 * C);
+            snprintf(nm, sizeof nm, "se%d.w0p", i + 3); W_A16(h->se[i].w0p, nm, 128 * C);
             snprintf(nm, sizeof nm, "se%d.b0p", i + 3); W_F32(h->se[i].b0p, nm, 128);
-            snprintf(nm, sizeof nm, "se%d.w2p", i + 3); W_BF16(h->se[i].w2p, nm, C * 128);
+            snprintf(nm, sizeof nm, "se%d.w2p", i + 3); W_A16(h->se[i].w2p, nm, C * 128);
             snprintf(nm, sizeof nm, "se%d.b2", i + 3); W_F32(h->se[i].b2, nm, C);
         }
-        W_BF16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
+        W_A16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
         W_F32(h->lstm_b, "lstm.b", 8 * LSTM_H);
-        W_BF16(h->lstm_w_hh, "lstm.w_hh", bilstm_whh_packed_elems());
-        W_BF16(h->lstm_w_hh_mma, "lstm.w_hh_mma", bilstm_whh_mma_elems());
+        W_A16(h->lstm_w_hh, "lstm.w_hh", bilstm_whh_packed_elems());
+        W_A16(h->lstm_w_hh_mma, "lstm.w_hh_mma", bilstm_whh_mma_elems());
     }
-    W_BF16(h->patch_w, "patch.w", D * 1024);
+    W_A16(h->patch_w, "patch.w", D * 1024);
     W_F32(h->patch_b, "patch.b", D);
     W_F32(h->patch_pos, "patch.pos", 32 * D);
     for (int l = 0; l < 2; ++l) {
         EncLayerW& e = h->enc[l];
-        snprintf(nm, sizeof nm, "enc%d.in_w", l); W_BF16(e.in_w, nm, 3 * D * D);
+        snprintf(nm, sizeof nm, "enc%d.in_w", l); W_A16(e.in_w, nm, 3 * D * D);
         snprintf(nm, sizeof nm, "enc%d.in_b", l); W_F32(e.in_b, nm, 3 * D);
-        snprintf(nm, sizeof nm, "enc%d.out_w", l); W_BF16(e.out_w, nm, D * D);
+        snprintf(nm, sizeof nm, "enc%d.out_w", l); W_A16(e.out_w, nm, D * D);
         snprintf(nm, sizeof nm, "enc%d.out_b", l); W_F32(e.out_b, nm, D);
-        snprintf(nm, sizeof nm, "enc%d.l1_w", l); W_BF16(e.l1_w, nm, 1024 * D);
+        snprintf(nm, sizeof nm, "enc%d.l1_w", l); W_A16(e.l1_w, nm, 1024 * D);
         snprintf(nm, sizeof nm, "enc%d.l1_b", l); W_F32(e.l1_b, nm, 1024);
-        snprintf(nm, sizeof nm, "enc%d.l2_w", l); W_BF16(e.l2_w, nm, D * 1024);
+        snprintf(nm, sizeof nm, "enc%d.l2_w", l); W_A16(e.l2_w, nm, D * 1024);
         snprintf(nm, sizeof nm, "enc%d.l2_b", l); W_F32(e.l2_b, nm, D);
         snprintf(nm, sizeof nm, "enc%d.n1_g", l); W_F32(e.n1_g, nm, D);
         snprintf(nm, sizeof nm, "enc%d.n1_b", l); W_F32(e.n1_b, nm, D);
@@ -203,7 +203,7 @@ int resolve_weights(kocr_handle* h) {
         snprintf(nm, sizeof nm, "dec%d.n3_g", l); W_F32(d.n3_g, nm, D);
         snprintf(nm, sizeof nm, "dec%d.n3_b", l); W_F32(d.n3_b, nm, D);
     }
-    W_BF16(h->dec_kv_w, "dec.ca_kv_w", 4 * D * D);
+    W_A16(h->dec_kv_w, "dec.ca_kv_w", 4 * D * D);
     W_F32(h->dec_kv_b, "dec.ca_kv_b", 4 * D);
     W_F32(h->dec_out_w, "dec.out_w", VOCAB_PAD * D);
     W_F32(h->dec_out_b, "dec.out_b", VOCAB_PAD);
@@ -306,8 +306,8 @@ int gemm_linear(kocr_handle* h, const void* a, long rows, const void* w, int N, 
     return launch_gemm_tc(a, rows, w, p, sms, s);
 }
 
-int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n_chunks, const PLGeom& g, int Cin,
-              int Cout, const __nv_bfloat16* w, const float* b, int relu, cudaStream_t s) {
+int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, const PLGeom& g, int Cin,
+              int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = n_chunks * g.S; p.N = Cout; p.taps = 9; p.cin = Cin;
@@ -316,24 +316,24 @@ int gemm_conv(kocr_handle* h, const __nv_bfloat16* in, __nv_bfloat16* out, int n
     p.ep = ep_none();
     p.ep.bias = b; p.ep.relu = relu;
     p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W;
-    p.ep.out_bf16 = out; p.ep.ld_bf16 = Cout;
+    p.ep.out_a16 = out; p.ep.ld_a16 = Cout;
     const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
     return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, sms, s);
 }
 
 // SequenceSE excitation for every column of the batch: means -> FC1+ReLU (width padded to 128) -> FC2+sigmoid.
 // Returns the fp32 gate [n*W + w][C] in the workspace (null for the VGG baseline).
-int se_gate(kocr_handle* h, const __nv_bfloat16* act, int NC, int H, int W, int C, const SEWeights& w, const char* site,
+int se_gate(kocr_handle* h, const act16_t* act, int NC, int H, int W, int C, const SEWeights& w, const char* site,
             const float** gate_out, cudaStream_t s) {
-    __nv_bfloat16* means = buf<__nv_bfloat16>(h, "se_mean");
-    __nv_bfloat16* z = buf<__nv_bfloat16>(h, "se_z");
+    act16_t* means = buf<act16_t>(h, "se_mean");
+    act16_t* z = buf<act16_t>(h, "se_z");
     float* gate = buf<float>(h, "se_gate");
     const long rows = (long)NC * W;
     char nm[64];
     snprintf(nm, sizeof nm, "%s_squeeze", site);
     TIMED(nm, 0, launch_se_col_mean(act, means, NC, H, W, C, s)); ++g_launches;
     GemmEpilogue e = ep_none();
-    e.bias = w.b0p; e.relu = 1; e.out_bf16 = z; e.ld_bf16 = 128;
+    e.bias = w.b0p; e.relu = 1; e.out_a16 = z; e.ld_a16 = 128;
     snprintf(nm, sizeof nm, "%s_fc", site);
     TIMED(nm, 2.0 * rows * C * (C / 16), gemm_linear(h, means, rows, w.w0p, 128, C, e, s));
     e = ep_none();
@@ -347,7 +347,7 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     const int NC = h->n_chunks;
     if (NC == 0) return 0;
     const bool se = h->variant == 0;
-    auto B = [&](const char* n) { return buf<__nv_bfloat16>(h, n); };
+    auto B = [&](const char* n) { return buf<act16_t>(h, n); };
     const double nc = NC;
     auto cf = [&](int H, int W, int ci, int co) { return 2.0 * nc * H * W * 9.0 * ci * co; };   // algorithmic conv FLOPs
     TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s)); ++g_launches;
@@ -379,17 +379,17 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
 
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");
-    __nv_bfloat16* xb = B("xb");
+    act16_t* xb = B("xb");
     {   // patch projection + bias + local positional encoding (se_model.py:108-115)
         GemmEpilogue e = ep_none();
         e.bias = h->patch_b; e.addend = h->patch_pos; e.ld_add = D_MODEL; e.add_period = TOK_PER_CHUNK;
-        e.out_f32 = x; e.ld_f32 = D_MODEL; e.out_bf16 = xb; e.ld_bf16 = D_MODEL;
+        e.out_f32 = x; e.ld_f32 = D_MODEL; e.out_a16 = xb; e.ld_a16 = D_MODEL;
         TIMED("patch_proj", 2.0 * M * 1024 * D_MODEL, gemm_linear(h, B("patch_in"), M, h->patch_w, D_MODEL, 1024, e, s));
     }
     for (int l = 0; l < 2; ++l) {
         const EncLayerW& w = h->enc[l];
         GemmEpilogue e = ep_none();
-        e.bias = w.in_b; e.out_bf16 = B("qkv"); e.ld_bf16 = 3 * D_MODEL;
+        e.bias = w.in_b; e.out_a16 = B("qkv"); e.ld_a16 = 3 * D_MODEL;
         TIMED("enc_qkv", 2.0 * M * D_MODEL * 3 * D_MODEL, gemm_linear(h, xb, M, w.in_w, 3 * D_MODEL, D_MODEL, e, s));
         TIMED("enc_attention", 2.0 * 2.0 * M * 32 * D_MODEL, launch_chunk_attention(B("qkv"), B("ao"), NC, s)); ++g_launches;
         e = ep_none();
@@ -397,7 +397,7 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
         TIMED("enc_out_proj", 2.0 * M * D_MODEL * D_MODEL, gemm_linear(h, B("ao"), M, w.out_w, D_MODEL, D_MODEL, e, s));
         TIMED("enc_layernorm", 0, launch_layernorm(y, w.n1_g, w.n1_b, nullptr, nullptr, x, xb, nullptr, (int)M, s)); ++g_launches;
         e = ep_none();
-        e.bias = w.l1_b; e.relu = 1; e.out_bf16 = B("hff"); e.ld_bf16 = 1024;
+        e.bias = w.l1_b; e.relu = 1; e.out_a16 = B("hff"); e.ld_a16 = 1024;
         TIMED("enc_ffn1", 2.0 * M * D_MODEL * 1024, gemm_linear(h, xb, M, w.l1_w, 1024, D_MODEL, e, s));
         e = ep_none();
         e.bias = w.l2_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
@@ -413,23 +413,23 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
 int stage_memory(kocr_handle* h, cudaStream_t s) {
     const long M = h->n_tok;
     if (M == 0) return 0;
-    const __nv_bfloat16* memb = buf<__nv_bfloat16>(h, "xb");
+    const act16_t* memb = buf<act16_t>(h, "xb");
     if (h->variant == 0) {
         GemmEpilogue e = ep_none();
         e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
-        TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, buf<__nv_bfloat16>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
+        TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, buf<act16_t>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
         if (h->lstm_impl == 1)
             TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm_mma(buf<float>(h, "gin"), h->lstm_w_hh_mma, h->d_line_tok_off, h->d_line_T, h->d_groups16,
-                               h->n_groups16, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
+                               h->n_groups16, buf<float>(h, "mem"), buf<act16_t>(h, "memb"), nullptr, s));
         else
         TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm(buf<float>(h, "gin"), h->lstm_w_hh, h->d_line_tok_off, h->d_line_T, h->d_groups,
-                               h->n_groups, buf<float>(h, "mem"), buf<__nv_bfloat16>(h, "memb"), nullptr, s));
+                               h->n_groups, buf<float>(h, "mem"), buf<act16_t>(h, "memb"), nullptr, s));
         ++g_launches;
-        memb = buf<__nv_bfloat16>(h, "memb");
+        memb = buf<act16_t>(h, "memb");
     }
     // cross-attention K/V of both decoder layers, once per line (depends only on the memory)
     GemmEpilogue e = ep_none();
-    e.bias = h->dec_kv_b; e.out_bf16 = buf<__nv_bfloat16>(h, "kv"); e.ld_bf16 = 4 * D_MODEL;
+    e.bias = h->dec_kv_b; e.out_a16 = buf<act16_t>(h, "kv"); e.ld_a16 = 4 * D_MODEL;
     TIMED("cross_kv_proj", 2.0 * M * D_MODEL * 4 * D_MODEL, gemm_linear(h, memb, M, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
     return 0;
 }
@@ -447,7 +447,7 @@ int gemm_dec(kocr_handle* h, const float* a, int L, const float* w, int N, int K
 }
 
 // One generated position for every line of the batch; the position is *step_base + off (device side).
-// Decoder GEMMs run on the tensor cores in TF32 (fp32 operands): with bf16 operands ~7 % of the lines of the
+// Decoder GEMMs run on the tensor cores in TF32 (fp32 operands): with a16 operands ~7 % of the lines of the
 // fixture batch decode to a different sequence than the fp32 reference, with TF32 the flips disappear.
 // Optional override: the rows are `n_rows` hypotheses (beams) that share the memory of ONE line and use a private,
 // small self-attention cache.
@@ -481,7 +481,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
         DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
         DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx)); ++g_launches;
         DSTEP(gemm_dec(h, dx, L, w.ca_q_w, D, D, S2, parts, s));
-        DSTEP(launch_dec_cross_attn(parts, buf<__nv_bfloat16>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
+        DSTEP(launch_dec_cross_attn(parts, buf<act16_t>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
                                     rows ? rows->T : h->d_line_T, max_T, fin,
                                     dao, L, s, S2, w.ca_q_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s));
@@ -594,6 +594,11 @@ int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_
     }
     if (!meta) { set_error("kocr_create: blob lacks 'meta'"); return fail(2); }
     h->variant = meta[0]; h->emb_dim = meta[1]; h->max_seq_len = meta[2]; h->dec_max_len = meta[3]; h->vocab = meta[4];
+    if (meta[5] != KOCR_A16_FORMAT) {
+        set_error("kocr_create: weight blob packs 16-bit operands as %s but this library was built for %s",
+                  meta[5] == 1 ? "fp16" : "bf16", KOCR_A16_FORMAT == 1 ? "fp16" : "bf16");
+        return fail(2);
+    }
     if (h->emb_dim != D_MODEL || h->dec_max_len != DEC_MAX || h->vocab != VOCAB) {
         set_error("kocr_create: unsupported dims emb=%d dec_max=%d vocab=%d (kernels are specialised for 384/256/124)",
                   h->emb_dim, h->dec_max_len, h->vocab);
@@ -979,9 +984,9 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
     return 0;
 }
 
-int kocr_test_gemm(int impl, const void* a_bf16, int64_t rows_a, const void* w_bf16, int m, int n, int taps, int cin,
+int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a16, int m, int n, int taps, int cin,
                    const int32_t* tap_off, const float* bias, int relu, int pl_h, int pl_w, float* out_f32,
-                   void* out_bf16, void* stream) {
+                   void* out_a16, void* stream) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = m; p.N = n; p.taps = taps; p.cin = cin;
@@ -989,16 +994,16 @@ int kocr_test_gemm(int impl, const void* a_bf16, int64_t rows_a, const void* w_b
     p.ep.bias = bias; p.ep.relu = relu;
     if (pl_h > 0) { const PLGeom g = make_pl(pl_h, pl_w); p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W; }
     p.ep.out_f32 = out_f32; p.ep.ld_f32 = n;
-    p.ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ep.ld_bf16 = n;
+    p.ep.out_a16 = reinterpret_cast<act16_t*>(out_a16); p.ep.ld_a16 = n;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     p.tf32 = impl == 2 ? 1 : 0;          // impl 2: fp32 operands consumed as TF32
     if (impl == 1)
-        return launch_gemm_simt_check(reinterpret_cast<const __nv_bfloat16*>(a_bf16), rows_a,
-                                      reinterpret_cast<const __nv_bfloat16*>(w_bf16), p, s);
+        return launch_gemm_simt_check(reinterpret_cast<const act16_t*>(a_a16), rows_a,
+                                      reinterpret_cast<const act16_t*>(w_a16), p, s);
     int dev = 0, sms = 148;
     KOCR_CUDA(cudaGetDevice(&dev));
     KOCR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return launch_gemm_tc(a_bf16, rows_a, w_bf16, p, sms, s);
+    return launch_gemm_tc(a_a16, rows_a, w_a16, p, sms, s);
 }
 
 }  // extern "C"

@@ -16,14 +16,14 @@ namespace kocr {
 // Per-chunk attention: one CTA per chunk, warp = head, lane = query token.
 // K/V of the head live in shared memory (fp32), scores/softmax in registers.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) chunk_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                              __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) chunk_attention_kernel(const act16_t* __restrict__ qkv,
+                                                              act16_t* __restrict__ out) {
     extern __shared__ float s_kv[];                 // [8 warps][2][32][48]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sk = s_kv + warp * (2 * 32 * HEAD_DIM);
     float* sv = sk + 32 * HEAD_DIM;
     const long row = (long)blockIdx.x * TOK_PER_CHUNK + lane;
-    const __nv_bfloat16* base = qkv + row * (3 * D_MODEL) + warp * HEAD_DIM;
+    const act16_t* base = qkv + row * (3 * D_MODEL) + warp * HEAD_DIM;
     float q[HEAD_DIM];
     const float scale = rsqrtf((float)HEAD_DIM);
 #pragma unroll
@@ -34,12 +34,12 @@ __global__ void __launch_bounds__(256) chunk_attention_kernel(const __nv_bfloat1
         const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            q[i * 8 + 2 * j] = bf16_lo(av[j]) * scale;
-            q[i * 8 + 2 * j + 1] = bf16_hi(av[j]) * scale;
-            sk[lane * HEAD_DIM + i * 8 + 2 * j] = bf16_lo(bv[j]);
-            sk[lane * HEAD_DIM + i * 8 + 2 * j + 1] = bf16_hi(bv[j]);
-            sv[lane * HEAD_DIM + i * 8 + 2 * j] = bf16_lo(cv[j]);
-            sv[lane * HEAD_DIM + i * 8 + 2 * j + 1] = bf16_hi(cv[j]);
+            q[i * 8 + 2 * j] = a16_lo(av[j]) * scale;
+            q[i * 8 + 2 * j + 1] = a16_hi(av[j]) * scale;
+            sk[lane * HEAD_DIM + i * 8 + 2 * j] = a16_lo(bv[j]);
+            sk[lane * HEAD_DIM + i * 8 + 2 * j + 1] = a16_hi(bv[j]);
+            sv[lane * HEAD_DIM + i * 8 + 2 * j] = a16_lo(cv[j]);
+            sv[lane * HEAD_DIM + i * 8 + 2 * j + 1] = a16_hi(cv[j]);
         }
     }
     __syncwarp();
@@ -77,19 +77,19 @@ __global__ void __launch_bounds__(256) chunk_attention_kernel(const __nv_bfloat1
     uint4* dst = reinterpret_cast<uint4*>(out + row * D_MODEL + warp * HEAD_DIM);
 #pragma unroll
     for (int i = 0; i < HEAD_DIM / 8; ++i)
-        dst[i] = make_uint4(pack_bf16(o[i * 8], o[i * 8 + 1]), pack_bf16(o[i * 8 + 2], o[i * 8 + 3]),
-                            pack_bf16(o[i * 8 + 4], o[i * 8 + 5]), pack_bf16(o[i * 8 + 6], o[i * 8 + 7]));
+        dst[i] = make_uint4(pack_a16(o[i * 8], o[i * 8 + 1]), pack_a16(o[i * 8 + 2], o[i * 8 + 3]),
+                            pack_a16(o[i * 8 + 4], o[i * 8 + 5]), pack_a16(o[i * 8 + 6], o[i * 8 + 7]));
 }
 
 // ------------------------------------------------------------------------------------------
-// Tensor-core version: one CTA per chunk, warp = head.  The chunk's [32][1152] bf16 QKV block is copied to shared
+// Tensor-core version: one CTA per chunk, warp = head.  The chunk's [32][1152] a16 QKV block is copied to shared
 // memory with coalesced 16-byte loads (it is contiguous in HBM), every head then runs S = Q K^T (m16n8k16, fp32
 // accumulators), a register softmax (quad shuffles), and O = P V with the probabilities re-used directly as A
 // fragments (accumulator layout of S == A layout of the next MMA) and V read through ldmatrix.trans.  The output is
 // staged in the head's dead Q columns and written back as whole 768-byte rows.
 // 32 x 32 x 48 per head is far below a tcgen05 tile (M = 128), hence mma.sync here.
 // ------------------------------------------------------------------------------------------
-static constexpr int CA_LD = 3 * D_MODEL + 8;      // bf16 elements per smem row: 2320 B = odd multiple of 16 B
+static constexpr int CA_LD = 3 * D_MODEL + 8;      // a16 elements per smem row: 2320 B = odd multiple of 16 B
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -102,15 +102,15 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." KOCR_MMA_A16 "." KOCR_MMA_A16 ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                     __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const act16_t* __restrict__ qkv,
+                                                                     act16_t* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t ca_smem[];
-    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(ca_smem);          // [32][CA_LD]
+    act16_t* sm = reinterpret_cast<act16_t*>(ca_smem);          // [32][CA_LD]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint4* src = reinterpret_cast<const uint4*>(qkv + (long)blockIdx.x * TOK_PER_CHUNK * 3 * D_MODEL);
     constexpr int ROW_U4 = 3 * D_MODEL / 8;        // 144 16-byte pieces per row
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const __nv_
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t lo = pack_bf16(exp2f((sacc[j][0] - m0) * scale_log2), exp2f((sacc[j][1] - m0) * scale_log2));
-            const uint32_t hi = pack_bf16(exp2f((sacc[j][2] - m1) * scale_log2), exp2f((sacc[j][3] - m1) * scale_log2));
-            s0 += bf16_lo(lo) + bf16_hi(lo);         // sums of the ROUNDED weights: the applied weights add up to 1
-            s1 += bf16_lo(hi) + bf16_hi(hi);
+            const uint32_t lo = pack_a16(exp2f((sacc[j][0] - m0) * scale_log2), exp2f((sacc[j][1] - m0) * scale_log2));
+            const uint32_t hi = pack_a16(exp2f((sacc[j][2] - m1) * scale_log2), exp2f((sacc[j][3] - m1) * scale_log2));
+            s0 += a16_lo(lo) + a16_hi(lo);         // sums of the ROUNDED weights: the applied weights add up to 1
+            s1 += a16_lo(hi) + a16_hi(hi);
             pa[j >> 1][(j & 1) * 2] = lo;
             pa[j >> 1][(j & 1) * 2 + 1] = hi;
         }
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const __nv_
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < HEAD_DIM / 8; ++j) {
-            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g) * CA_LD + qc + j * 8 + 2 * t) = pack_bf16(oacc[j][0] * inv0, oacc[j][1] * inv0);
-            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g + 8) * CA_LD + qc + j * 8 + 2 * t) = pack_bf16(oacc[j][2] * inv1, oacc[j][3] * inv1);
+            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g) * CA_LD + qc + j * 8 + 2 * t) = pack_a16(oacc[j][0] * inv0, oacc[j][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sm + (mt * 16 + g + 8) * CA_LD + qc + j * 8 + 2 * t) = pack_a16(oacc[j][2] * inv1, oacc[j][3] * inv1);
         }
     }
     __syncthreads();
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256, 3) chunk_attention_mma_kernel(const __nv_
 static int g_chunk_attn_impl = 1;      // 1: mma.sync kernel, 0: CUDA-core kernel (kept for A/B tests)
 void set_chunk_attention_impl(int impl) { g_chunk_attn_impl = impl; }
 
-int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_chunks, cudaStream_t stream) {
+int launch_chunk_attention(const act16_t* qkv, act16_t* out, int n_chunks, cudaStream_t stream) {
     if (n_chunks > 0 && g_chunk_attn_impl == 1) {
         const size_t smem_mma = (size_t)TOK_PER_CHUNK * CA_LD * 2;
         static bool attr_set_mma = false;
@@ -231,19 +231,19 @@ int launch_chunk_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_c
 // LayerNorm / positional add over rows of 384.  Warp per row, 12 elements per lane.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_row_outputs(const float (&y)[12], long row, int lane, float* out_f32,
-                                                  __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo) {
+                                                  act16_t* out_a16, act16_t* out_lo) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const int col = j * 128 + lane * 4;
         if (out_f32)
             *reinterpret_cast<float4*>(out_f32 + row * D_MODEL + col) =
                 make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        if (out_bf16) {
-            const uint32_t p0 = pack_bf16(y[4 * j], y[4 * j + 1]), p1 = pack_bf16(y[4 * j + 2], y[4 * j + 3]);
-            *reinterpret_cast<uint2*>(out_bf16 + row * D_MODEL + col) = make_uint2(p0, p1);
+        if (out_a16) {
+            const uint32_t p0 = pack_a16(y[4 * j], y[4 * j + 1]), p1 = pack_a16(y[4 * j + 2], y[4 * j + 3]);
+            *reinterpret_cast<uint2*>(out_a16 + row * D_MODEL + col) = make_uint2(p0, p1);
             if (out_lo) {
-                const uint32_t l0 = pack_bf16(y[4 * j] - bf16_lo(p0), y[4 * j + 1] - bf16_hi(p0));
-                const uint32_t l1 = pack_bf16(y[4 * j + 2] - bf16_lo(p1), y[4 * j + 3] - bf16_hi(p1));
+                const uint32_t l0 = pack_a16(y[4 * j] - a16_lo(p0), y[4 * j + 1] - a16_hi(p0));
+                const uint32_t l1 = pack_a16(y[4 * j + 2] - a16_lo(p1), y[4 * j + 3] - a16_hi(p1));
                 *reinterpret_cast<uint2*>(out_lo + row * D_MODEL + col) = make_uint2(l0, l1);
             }
         }
@@ -255,7 +255,7 @@ template <bool DO_LN>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ b, const float* __restrict__ pos,
                                                         const int* __restrict__ row_pos, float* out_f32,
-                                                        __nv_bfloat16* out_bf16, __nv_bfloat16* out_lo, int rows,
+                                                        act16_t* out_a16, act16_t* out_lo, int rows,
                                                         int nsplit, const float* __restrict__ in_bias,
                                                         const float* resid) {
     const int lane = threadIdx.x & 31;
@@ -310,22 +310,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             v[4 * j] += pp.x; v[4 * j + 1] += pp.y; v[4 * j + 2] += pp.z; v[4 * j + 3] += pp.w;
         }
     }
-    store_row_outputs(v, row, lane, out_f32, out_bf16, out_lo);
+    store_row_outputs(v, row, lane, out_f32, out_a16, out_lo);
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
-                     float* out_f32, __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_lo, int rows,
+                     float* out_f32, act16_t* out_a16, act16_t* out_a16_lo, int rows,
                      cudaStream_t stream, int nsplit, const float* in_bias, const float* resid) {
     if (rows == 0) return 0;
     KOCR_CUDA(launch_kernel(layernorm_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, stream, x, g, b, pos, row_pos,
-                            out_f32, out_bf16, out_bf16_lo, rows, nsplit, in_bias, resid));
+                            out_f32, out_a16, out_a16_lo, rows, nsplit, in_bias, resid));
     return 0;
 }
-int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, __nv_bfloat16* out_bf16,
-                   __nv_bfloat16* out_bf16_lo, int rows, cudaStream_t stream) {
+int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
+                   act16_t* out_a16_lo, int rows, cudaStream_t stream) {
     if (rows == 0) return 0;
-    layernorm_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(x, nullptr, nullptr, pos, row_pos, out_f32, out_bf16,
-                                                                out_bf16_lo, rows, 1, nullptr, nullptr);
+    layernorm_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(x, nullptr, nullptr, pos, row_pos, out_f32, out_a16,
+                                                                out_a16_lo, rows, 1, nullptr, nullptr);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -333,24 +333,24 @@ int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* 
 // ------------------------------------------------------------------------------------------
 // BiLSTM recurrence.  Cluster of 2 CTAs per (group of <= 8 lines, direction); CTA `rank` owns hidden
 // units [rank*96, rank*96+96) i.e. 384 gate rows (i,f,g,o x 96), whose recurrent weights stay in
-// shared memory (bf16x2, k-pair major) for all timesteps.  Each step: gates = gin + W_hh h (fp32
+// shared memory (a16x2, k-pair major) for all timesteps.  Each step: gates = gin + W_hh h (fp32
 // FMA), cell update, and the new half of h is written to both CTAs' shared memory (DSMEM) followed
 // by one cluster barrier.
-// whh_packed layout (built on the host): [dir][rank][kp = 0..95][row = 0..383] u32 = bf16x2
+// whh_packed layout (built on the host): [dir][rank][kp = 0..95][row = 0..383] u32 = a16x2
 // {W[grow][2kp], W[grow][2kp+1]}, grow = gate*192 + rank*96 + jj for row = gate*96 + jj.
 // ------------------------------------------------------------------------------------------
 static constexpr int LSTM_ROWS = 384;      // gate rows per CTA
 static constexpr int LSTM_KP = LSTM_H / 2; // 96 k-pairs
 static constexpr int LSTM_LPG = 8;         // lines per group
 
-size_t bilstm_whh_packed_elems() { return (size_t)2 * 2 * LSTM_KP * LSTM_ROWS * 2; }   // bf16 elements
+size_t bilstm_whh_packed_elems() { return (size_t)2 * 2 * LSTM_KP * LSTM_ROWS * 2; }   // a16 elements
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_ROWS, 1)
 bilstm_kernel(const float* __restrict__ gin, const uint32_t* __restrict__ whh, const int* __restrict__ line_tok_off,
               const int* __restrict__ line_T, const LstmGroup* __restrict__ groups, float* __restrict__ mem_f32,
-              __nv_bfloat16* __restrict__ mem_bf16, __nv_bfloat16* __restrict__ mem_lo) {
+              act16_t* __restrict__ mem_a16, act16_t* __restrict__ mem_lo) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint32_t* s_w = reinterpret_cast<uint32_t*>(s_raw);                                 // [96][384]
     float* s_h = reinterpret_cast<float*>(s_raw + LSTM_KP * LSTM_ROWS * 4);              // [2][8][192]
@@ -402,7 +402,7 @@ bilstm_kernel(const float* __restrict__ gin, const uint32_t* __restrict__ whh, c
         for (int kp = 0; kp < LSTM_KP; kp += 2) {
             const uint32_t w01 = s_w[kp * LSTM_ROWS + tid];
             const uint32_t w23 = s_w[(kp + 1) * LSTM_ROWS + tid];
-            const float w0 = bf16_lo(w01), w1 = bf16_hi(w01), w2 = bf16_lo(w23), w3 = bf16_hi(w23);
+            const float w0 = a16_lo(w01), w1 = a16_hi(w01), w2 = a16_lo(w23), w3 = a16_hi(w23);
 #pragma unroll
             for (int l = 0; l < LSTM_LPG; ++l) {
                 const float4 h4 = *reinterpret_cast<const float4*>(hc + l * LSTM_H + 2 * kp);
@@ -433,10 +433,10 @@ bilstm_kernel(const float* __restrict__ gin, const uint32_t* __restrict__ whh, c
                 const int pos = dir == 0 ? s : T[l] - 1 - s;
                 const long o = (long)(tok_off[l] + pos) * D_MODEL + dir * LSTM_H + rank * 96 + j;
                 mem_f32[o] = h;
-                if (mem_bf16) {
-                    const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-                    mem_bf16[o] = hb;
-                    if (mem_lo) mem_lo[o] = __float2bfloat16_rn(h - __bfloat162float(hb));
+                if (mem_a16) {
+                    const act16_t hb = to_a16(h);
+                    mem_a16[o] = hb;
+                    if (mem_lo) mem_lo[o] = to_a16(h - from_a16(hb));
                 }
             }
         }
@@ -445,9 +445,9 @@ bilstm_kernel(const float* __restrict__ gin, const uint32_t* __restrict__ whh, c
     }
 }
 
-int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* line_tok_off, const int* line_T,
-                  const LstmGroup* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
-                  __nv_bfloat16* mem_bf16_lo, cudaStream_t stream) {
+int launch_bilstm(const float* gin, const act16_t* whh_packed, const int* line_tok_off, const int* line_T,
+                  const LstmGroup* groups, int n_groups, float* mem_f32, act16_t* mem_a16,
+                  act16_t* mem_a16_lo, cudaStream_t stream) {
     if (n_groups == 0) return 0;
     const size_t smem = (size_t)LSTM_KP * LSTM_ROWS * 4 + 2 * LSTM_LPG * LSTM_H * 4 + LSTM_LPG * LSTM_ROWS * 4;
     static bool attr_set = false;
@@ -456,8 +456,8 @@ int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* 
         attr_set = true;
     }
     bilstm_kernel<<<dim3(2, n_groups * 2), LSTM_ROWS, smem, stream>>>(
-        gin, reinterpret_cast<const uint32_t*>(whh_packed), line_tok_off, line_T, groups, mem_f32, mem_bf16,
-        mem_bf16_lo);
+        gin, reinterpret_cast<const uint32_t*>(whh_packed), line_tok_off, line_T, groups, mem_f32, mem_a16,
+        mem_a16_lo);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -466,7 +466,7 @@ int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* 
 // BiLSTM recurrence, tensor-core version.  Cluster of 2 CTAs per (group of <= 16 lines, direction), 12 warps
 // per CTA.  Warp w of CTA `rank` owns hidden units [rank*96 + w*8, +8): its 32 gate rows x 192 recurrent weights
 // live in REGISTERS as mma.sync m16n8k16 A-fragments for all timesteps (2 m-tiles {i|f}, {g|o} x 12 k-steps).
-// Per step: D[32 gate rows x 16 lines] = W_hh[32 x 192] . h[192 x 16 lines] with h split into bf16 hi + lo parts
+// Per step: D[32 gate rows x 16 lines] = W_hh[32 x 192] . h[192 x 16 lines] with h split into a16 hi + lo parts
 // (both accumulated, fp32 accumulators), + the input projection; the fragment layout leaves all four gates of a
 // (unit, line) cell in one thread, so the cell update needs no exchange; the new h is written to both CTAs'
 // shared memory (DSMEM) and one cluster barrier closes the step.
@@ -474,13 +474,13 @@ int launch_bilstm(const float* gin, const __nv_bfloat16* whh_packed, const int* 
 // whh_mma layout (host): [dir][rank][warp][mtile][kstep][lane] uint4 = the A fragment registers.
 // ------------------------------------------------------------------------------------------
 static constexpr int LM_LPG = 16;          // lines per group
-static constexpr int LM_HS = 200;          // padded row stride (bf16) of the h buffers: conflict-free B loads
+static constexpr int LM_HS = 200;          // padded row stride (a16) of the h buffers: conflict-free B loads
 static constexpr int LM_THREADS = 384;
 
-size_t bilstm_whh_mma_elems() { return (size_t)2 * 2 * 12 * 2 * 12 * 32 * 8; }   // bf16 elements
+size_t bilstm_whh_mma_elems() { return (size_t)2 * 2 * 12 * 2 * 12 * 32 * 8; }   // a16 elements
 
 // Fast gate non-linearities for the tensor-core recurrence: ex2/rcp and tanh.approx MUFU ops (relative error
-// ~2^-11, far below the bf16 rounding of the memory that feeds the decoder); the accurate expf/tanhf sequences
+// ~2^-11, far below the a16 rounding of the memory that feeds the decoder); the accurate expf/tanhf sequences
 // were the longest part of a recurrence step.
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -489,9 +489,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_a16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32." KOCR_MMA_A16 "." KOCR_MMA_A16 ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
@@ -499,8 +499,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint4& a, ui
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LM_THREADS, 1)
 bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, const int* __restrict__ line_tok_off,
                   const int* __restrict__ line_T, const LstmGroup16* __restrict__ groups, float* __restrict__ mem_f32,
-                  __nv_bfloat16* __restrict__ mem_bf16, __nv_bfloat16* __restrict__ mem_lo) {
-    __shared__ __align__(16) __nv_bfloat16 s_h[2][2][LM_LPG][LM_HS];     // [buffer][hi/lo][line][k]
+                  act16_t* __restrict__ mem_a16, act16_t* __restrict__ mem_lo) {
+    __shared__ __align__(16) act16_t s_h[2][2][LM_LPG][LM_HS];     // [buffer][hi/lo][line][k]
     extern __shared__ __align__(16) float s_gin[];                       // [2][16][384] input-projection prefetch
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -531,8 +531,8 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
         const int li = grp.line[l];
         if (li >= 0) maxT = max(maxT, line_T[li]);
     }
-    for (int i = tid; i < 2 * 2 * LM_LPG * LM_HS; i += LM_THREADS) (&s_h[0][0][0][0])[i] = __float2bfloat16_rn(0.f);
-    __nv_bfloat16* peer = cluster.map_shared_rank(&s_h[0][0][0][0], rank ^ 1);
+    for (int i = tid; i < 2 * 2 * LM_LPG * LM_HS; i += LM_THREADS) (&s_h[0][0][0][0])[i] = to_a16(0.f);
+    act16_t* peer = cluster.map_shared_rank(&s_h[0][0][0][0], rank ^ 1);
     cluster.sync();
 
     const int hid = rank * 96 + warp * 8 + g;                 // hidden unit of this thread's cells
@@ -566,8 +566,8 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-        const __nv_bfloat16* hhi = &s_h[cur][0][0][0];
-        const __nv_bfloat16* hlo = &s_h[cur][1][0][0];
+        const act16_t* hhi = &s_h[cur][0][0][0];
+        const act16_t* hlo = &s_h[cur][1][0][0];
 #pragma unroll
         for (int ks = 0; ks < 12; ++ks) {
 #pragma unroll
@@ -577,10 +577,10 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
                 const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(hhi + o + 8);
                 const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hlo + o);
                 const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(hlo + o + 8);
-                mma_bf16_16816(acc[0][nt], afrag[0][ks], bh0, bh1);
-                mma_bf16_16816(acc[1][nt], afrag[1][ks], bh0, bh1);
-                mma_bf16_16816(acc[0][nt], afrag[0][ks], bl0, bl1);
-                mma_bf16_16816(acc[1][nt], afrag[1][ks], bl0, bl1);
+                mma_a16_16816(acc[0][nt], afrag[0][ks], bh0, bh1);
+                mma_a16_16816(acc[1][nt], afrag[1][ks], bh0, bh1);
+                mma_a16_16816(acc[0][nt], afrag[0][ks], bl0, bl1);
+                mma_a16_16816(acc[1][nt], afrag[1][ks], bl0, bl1);
             }
         }
         // cell update: acc[0][nt] = {i(l0), i(l1), f(l0), f(l1)}, acc[1][nt] = {g(l0), g(l1), o(l0), o(l1)}
@@ -598,8 +598,8 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
                 const float cc = fg * c_state[c] + ig * gg;
                 c_state[c] = cc;
                 const float h = og * tanh_fast(cc);
-                const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-                const __nv_bfloat16 lb = __float2bfloat16_rn(h - __bfloat162float(hb));
+                const act16_t hb = to_a16(h);
+                const act16_t lb = to_a16(h - from_a16(hb));
                 const int line = nt * 8 + 2 * tig + e;
                 const int ohi = ((nxt * 2 + 0) * LM_LPG + line) * LM_HS + hid;
                 const int olo = ((nxt * 2 + 1) * LM_LPG + line) * LM_HS + hid;
@@ -608,7 +608,7 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
                 const int pos = dir == 0 ? s : cell_T[c] - 1 - s;
                 const long o = (long)(cell_off[c] + pos) * D_MODEL + dir * LSTM_H + hid;
                 mem_f32[o] = h;
-                if (mem_bf16) { mem_bf16[o] = hb; if (mem_lo) mem_lo[o] = lb; }
+                if (mem_a16) { mem_a16[o] = hb; if (mem_lo) mem_lo[o] = lb; }
             }
         }
         cluster.sync();
@@ -616,9 +616,9 @@ bilstm_mma_kernel(const float* __restrict__ gin, const uint4* __restrict__ whh, 
     }
 }
 
-int launch_bilstm_mma(const float* gin, const __nv_bfloat16* whh_mma, const int* line_tok_off, const int* line_T,
-                      const LstmGroup16* groups, int n_groups, float* mem_f32, __nv_bfloat16* mem_bf16,
-                      __nv_bfloat16* mem_bf16_lo, cudaStream_t stream) {
+int launch_bilstm_mma(const float* gin, const act16_t* whh_mma, const int* line_tok_off, const int* line_T,
+                      const LstmGroup16* groups, int n_groups, float* mem_f32, act16_t* mem_a16,
+                      act16_t* mem_a16_lo, cudaStream_t stream) {
     if (n_groups == 0) return 0;
     const size_t smem = 2 * 16 * LM_THREADS * sizeof(float);
     static bool attr_set = false;
@@ -627,7 +627,7 @@ int launch_bilstm_mma(const float* gin, const __nv_bfloat16* whh_mma, const int*
         attr_set = true;
     }
     bilstm_mma_kernel<<<dim3(2, n_groups * 2), LM_THREADS, smem, stream>>>(
-        gin, reinterpret_cast<const uint4*>(whh_mma), line_tok_off, line_T, groups, mem_f32, mem_bf16, mem_bf16_lo);
+        gin, reinterpret_cast<const uint4*>(whh_mma), line_tok_off, line_T, groups, mem_f32, mem_a16, mem_a16_lo);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -641,7 +641,7 @@ static constexpr int TOK_LD = DEC_MAX + 1;
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_base, int step_off,
                                  const float* __restrict__ tok_emb,
                                  const float* __restrict__ pos_emb, float* __restrict__ x,
-                                 __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xb_lo, int n_lines) {
+                                 act16_t* __restrict__ xb, act16_t* __restrict__ xb_lo, int n_lines) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // n_lines * 96 float4
     pdl_trigger();
     pdl_wait();
@@ -654,15 +654,15 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __re
     const float4 v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
     reinterpret_cast<float4*>(x)[idx] = v;
     if (xb == nullptr) return;
-    const uint32_t p0 = pack_bf16(v.x, v.y), p1 = pack_bf16(v.z, v.w);
+    const uint32_t p0 = pack_a16(v.x, v.y), p1 = pack_a16(v.z, v.w);
     reinterpret_cast<uint2*>(xb)[idx] = make_uint2(p0, p1);
     if (xb_lo)
-        reinterpret_cast<uint2*>(xb_lo)[idx] = make_uint2(pack_bf16(v.x - bf16_lo(p0), v.y - bf16_hi(p0)),
-                                                          pack_bf16(v.z - bf16_lo(p1), v.w - bf16_hi(p1)));
+        reinterpret_cast<uint2*>(xb_lo)[idx] = make_uint2(pack_a16(v.x - a16_lo(p0), v.y - a16_hi(p0)),
+                                                          pack_a16(v.z - a16_lo(p1), v.w - a16_hi(p1)));
 }
 
 int launch_dec_embed(const int* tokens, const int* step_base, int step_off, const float* tok_emb,
-                     const float* pos_emb, float* x, __nv_bfloat16* xb, __nv_bfloat16* xb_lo, int n_lines,
+                     const float* pos_emb, float* x, act16_t* xb, act16_t* xb_lo, int n_lines,
                      cudaStream_t stream) {
     const int total = n_lines * (D_MODEL / 4);
     KOCR_CUDA(launch_kernel(dec_embed_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, tokens, step_base, step_off,
@@ -674,8 +674,8 @@ __device__ __forceinline__ void store_attn_out(float o, long idx, float* out) { 
 
 // Causal self-attention for the newest position t against the cache (keys 0..t); keys whose token is
 // <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.
-// The cache is fp32: rounding the self-attention K/V to bf16 flips ~2 % of the fixture lines against the fp32
-// reference (near-tie argmaxes late in long sequences), while bf16 cross-attention K/V is harmless.
+// The cache is fp32: rounding the self-attention K/V to a16 flips ~2 % of the fixture lines against the fp32
+// reference (near-tie argmaxes late in long sequences), while a16 cross-attention K/V is harmless.
 __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restrict__ qkv,
                                                             float* __restrict__ kcache,
                                                             float* __restrict__ vcache,
@@ -756,11 +756,11 @@ int launch_dec_self_attn(const float* qkv, float* kcache, float* vcache, const i
 }
 
 // Cross-attention of one query per line over the line's T memory tokens (K/V precomputed once per line,
-// bf16 [Mtok, 1536]: layer*768 + {0: K, 384: V}).  CTA per line.  A K (or V) row of all 8 heads is 768
+// a16 [Mtok, 1536]: layer*768 + {0: K, 384: V}).  CTA per line.  A K (or V) row of all 8 heads is 768
 // contiguous bytes: a warp reads one key per iteration, 24 B (12 dims, a quarter of one head) per lane, so
 // every global read is a fully coalesced 768-byte burst; the 8 warps stride over the keys.
 __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __restrict__ q,
-                                                             const __nv_bfloat16* __restrict__ kv, int layer,
+                                                             const act16_t* __restrict__ kv, int layer,
                                                              const int* __restrict__ line_tok_off,
                                                              const int* __restrict__ line_T, int max_T,
                                                              const int* __restrict__ finished,
@@ -814,8 +814,8 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    acc = fmaf(qv[4 * i], bf16_lo(k[u][i].x), acc); acc = fmaf(qv[4 * i + 1], bf16_hi(k[u][i].x), acc);
-                    acc = fmaf(qv[4 * i + 2], bf16_lo(k[u][i].y), acc); acc = fmaf(qv[4 * i + 3], bf16_hi(k[u][i].y), acc);
+                    acc = fmaf(qv[4 * i], a16_lo(k[u][i].x), acc); acc = fmaf(qv[4 * i + 1], a16_hi(k[u][i].x), acc);
+                    acc = fmaf(qv[4 * i + 2], a16_lo(k[u][i].y), acc); acc = fmaf(qv[4 * i + 3], a16_hi(k[u][i].y), acc);
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -863,8 +863,8 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
             if (j0 + 8 * u < T) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    o[4 * i] = fmaf(pj[u], bf16_lo(v[u][i].x), o[4 * i]); o[4 * i + 1] = fmaf(pj[u], bf16_hi(v[u][i].x), o[4 * i + 1]);
-                    o[4 * i + 2] = fmaf(pj[u], bf16_lo(v[u][i].y), o[4 * i + 2]); o[4 * i + 3] = fmaf(pj[u], bf16_hi(v[u][i].y), o[4 * i + 3]);
+                    o[4 * i] = fmaf(pj[u], a16_lo(v[u][i].x), o[4 * i]); o[4 * i + 1] = fmaf(pj[u], a16_hi(v[u][i].x), o[4 * i + 1]);
+                    o[4 * i + 2] = fmaf(pj[u], a16_lo(v[u][i].y), o[4 * i + 2]); o[4 * i + 3] = fmaf(pj[u], a16_hi(v[u][i].y), o[4 * i + 3]);
                 }
             }
         }
@@ -880,7 +880,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
     }
 }
 
-int launch_dec_cross_attn(const float* q, const __nv_bfloat16* kv, int layer, const int* line_tok_off,
+int launch_dec_cross_attn(const float* q, const act16_t* kv, int layer, const int* line_tok_off,
                           const int* line_T, int max_T, const int* finished, float* out, int n_lines,
                           cudaStream_t stream, int nsplit, const float* bias) {
     const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);

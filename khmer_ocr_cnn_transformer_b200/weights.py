@@ -24,7 +24,9 @@ from .checkpoint import detect_variant, validate_state_dict
 
 BN_EPS = 1e-5
 MAGIC = b"KOCRW001"
-DT_F32, DT_BF16, DT_I32 = 0, 1, 2
+DT_F32, DT_A16, DT_I32 = 0, 1, 2
+DT_BF16 = DT_A16          # historical name of the 16-bit entry type
+A16_FORMAT = 1            # 16-bit storage format of libkocr_b200.so: 1 = IEEE fp16 (default build), 0 = bf16 (-DKOCR_A16_BF16)
 LSTM_H = 192
 
 
@@ -48,6 +50,21 @@ def round_to_tf32(x: np.ndarray) -> np.ndarray:
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def f32_to_a16_bits(x: np.ndarray) -> np.ndarray:
+    """fp32 -> the library's 16-bit operand format (csrc/common.cuh: fp16, round-to-nearest-even, saturating at
+    +-65504 like cvt.rn.satfinite.f16x2.f32; bf16 for the -DKOCR_A16_BF16 build), as uint16 bit patterns."""
+    if A16_FORMAT == 0:
+        return f32_to_bf16_bits(x)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    return np.clip(x, -65504.0, 65504.0).astype(np.float16).view(np.uint16)
+
+
+def a16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    if A16_FORMAT == 0:
+        return bf16_bits_to_f32(b)
+    return np.ascontiguousarray(b, dtype=np.uint16).view(np.float16).astype(np.float32)
 
 
 def fold_bn(w, b, gamma, beta, mean, var):
@@ -107,13 +124,13 @@ def pack_tensors(sd: dict) -> dict:
     def f32(name, a):
         t[name] = (DT_F32, np.ascontiguousarray(a, dtype=np.float32))
 
-    def bf16(name, a):
-        t[name] = (DT_BF16, f32_to_bf16_bits(np.ascontiguousarray(a, dtype=np.float32)))
+    def bf16(name, a):          # 16-bit tensor-core operand (fp16 by default, see f32_to_a16_bits)
+        t[name] = (DT_A16, f32_to_a16_bits(np.ascontiguousarray(a, dtype=np.float32)))
 
     def tf32(name, a):          # decoder GEMM operands stay fp32 (consumed as TF32 by the tensor cores)
         t[name] = (DT_F32, round_to_tf32(np.ascontiguousarray(a, dtype=np.float32)))
 
-    t["meta"] = (DT_I32, np.asarray([0 if se else 1, D, max_len, dec_max, vocab, 0, 0, 0], np.int32))
+    t["meta"] = (DT_I32, np.asarray([0 if se else 1, D, max_len, dec_max, vocab, A16_FORMAT, 0, 0], np.int32))
     for i in range(1, 7):
         p = f"cnn.conv{i}"
         w, b = fold_bn(sd[p + ".0.weight"], sd[p + ".0.bias"], sd[p + ".1.weight"], sd[p + ".1.bias"],

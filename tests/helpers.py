@@ -9,11 +9,13 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
 def bf16_u16_to_f32(a: np.ndarray) -> np.ndarray:
-    return (a.astype(np.uint32) << 16).view(np.float32)
+    """Raw 16-bit activation words of the library (fp16 by default, bf16 for the KOCR_A16_BF16 build) -> fp32."""
+    from khmer_ocr_cnn_transformer_b200.weights import a16_bits_to_f32
+    return a16_bits_to_f32(a)
 
 
 def pl_to_nchw(buf_u16: np.ndarray, n: int, H: int, W: int, C: int) -> np.ndarray:
-    """padded-linear bf16 buffer [(n*(H+1)*(W+1)), C] -> fp32 (n, C, H, W) plus the pad values."""
+    """padded-linear 16-bit buffer [(n*(H+1)*(W+1)), C] -> fp32 (n, C, H, W) plus the pad values."""
     x = bf16_u16_to_f32(buf_u16).reshape(n, H + 1, W + 1, C)
     valid = x[:, :H, :W, :].transpose(0, 3, 1, 2)
     pads = np.concatenate([x[:, H, :, :].reshape(-1), x[:, :, W, :].reshape(-1)])

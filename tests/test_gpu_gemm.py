@@ -5,12 +5,18 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _a16():
+    import torch
+    from khmer_ocr_cnn_transformer_b200 import weights
+    return torch.float16 if weights.A16_FORMAT == 1 else torch.bfloat16
+
+
 def _run(impl, a, w, M, N, taps, cin, tap_off, bias, relu, pl):
     import torch
     from khmer_ocr_cnn_transformer_b200 import _native
     lib = _native.load_library()
     out32 = torch.zeros(M, N, dtype=torch.float32, device="cuda")
-    out16 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    out16 = torch.zeros(M, N, dtype=_a16(), device="cuda")
     to = np.asarray(tap_off, np.int32)
     b = torch.from_numpy(bias).cuda() if bias is not None else None
     _native.check(lib.kocr_test_gemm(impl, a.data_ptr(), a.shape[0], w.data_ptr(), M, N, taps, cin,
@@ -61,8 +67,8 @@ def test_gemm_tcgen05_matches_check_kernel_and_numpy(M, N, taps, cin, relu, pl):
     import torch
     rng = np.random.default_rng(M * 7 + N)
     rows = M
-    a = torch.from_numpy(rng.standard_normal((rows, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
-    w = torch.from_numpy((rng.standard_normal((N, taps * cin)) / np.sqrt(taps * cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    a = torch.from_numpy(rng.standard_normal((rows, cin)).astype(np.float32)).cuda().to(_a16())
+    w = torch.from_numpy((rng.standard_normal((N, taps * cin)) / np.sqrt(taps * cin)).astype(np.float32)).cuda().to(_a16())
     bias = rng.standard_normal(N).astype(np.float32)
     if taps == 9:
         P = pl[1] + 1
@@ -75,8 +81,8 @@ def test_gemm_tcgen05_matches_check_kernel_and_numpy(M, N, taps, cin, relu, pl):
     tc32, tc16 = _run(0, a, w, M, N, taps, cin, tap_off, bias, relu, pl)
     err = np.abs(tc32 - ref).max()
     assert err < 2e-3, f"tcgen05 fp32 output max err {err}"
-    # the bf16 output is the fp32 result rounded to nearest-even
-    want16 = torch.from_numpy(tc32).to(torch.bfloat16).float().numpy()
+    # the 16-bit output is the fp32 result rounded to nearest-even
+    want16 = torch.from_numpy(tc32).to(_a16()).float().numpy()
     assert np.array_equal(tc16, want16)
 
 

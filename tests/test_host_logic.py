@@ -59,6 +59,20 @@ def test_bf16_rounding_matches_torch():
     assert np.array_equal(mine, ref)
 
 
+def test_a16_conversion_is_fp16_rne_saturating():
+    """The library's 16-bit operand format (csrc/common.cuh): fp16, round-to-nearest-even, saturating."""
+    import torch
+    assert weights.A16_FORMAT == 1
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 3
+    x[:6] = [0.0, -0.0, 1.0000001, 65504.0, 1e6, -1e6]
+    mine = weights.f32_to_a16_bits(x)
+    ref = torch.from_numpy(np.clip(x, -65504, 65504)).to(torch.float16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(mine, ref)
+    back = weights.a16_bits_to_f32(mine)
+    assert back[4] == 65504.0 and back[5] == -65504.0 and np.all(np.isfinite(back))
+    assert np.abs(back[6:] - x[6:]).max() <= np.abs(x[6:]).max() * 2.0 ** -11
+
+
 def test_pack_blob_layout_and_folding():
     sd = seeded_state_dict("se", 3)
     assert validate_state_dict(sd)[0] == "se"
@@ -75,21 +89,21 @@ def test_pack_blob_layout_and_folding():
     km = weights.conv_to_kmajor(w)
     assert km.shape == (128, 576) and km[7, (1 * 3 + 2) * 64 + 9] == w[7, 9, 1, 2]
     # patch layout: k = kh*512 + c
-    pw = weights.bf16_bits_to_f32(t["patch.w"][1]).reshape(384, 1024)
-    ref = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(sd["patch.proj.weight"][3, 17, 1, 0].reshape(1)))[0]
+    pw = weights.a16_bits_to_f32(t["patch.w"][1]).reshape(384, 1024)
+    ref = weights.a16_bits_to_f32(weights.f32_to_a16_bits(sd["patch.proj.weight"][3, 17, 1, 0].reshape(1)))[0]
     assert pw[3, 512 + 17] == ref
     # LSTM recurrent packing: [dir][rank][kp][row][pair]
-    whh = weights.bf16_bits_to_f32(t["lstm.w_hh"][1]).reshape(2, 2, 96, 384, 2)
+    whh = weights.a16_bits_to_f32(t["lstm.w_hh"][1]).reshape(2, 2, 96, 384, 2)
     src = sd["context_bilstm.weight_hh_l0_reverse"]
     gate, rank, jj, kp, pair = 2, 1, 40, 33, 1
-    want = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(src[gate * 192 + rank * 96 + jj, 2 * kp + pair].reshape(1)))[0]
+    want = weights.a16_bits_to_f32(weights.f32_to_a16_bits(src[gate * 192 + rank * 96 + jj, 2 * kp + pair].reshape(1)))[0]
     assert whh[1, rank, kp, gate * 96 + jj, pair] == want
     # tensor-core LSTM fragments: [dir][rank][warp][mtile][kstep][lane][reg][2]
-    fr = weights.bf16_bits_to_f32(t["lstm.w_hh_mma"][1]).reshape(2, 2, 12, 2, 12, 32, 4, 2)
+    fr = weights.a16_bits_to_f32(t["lstm.w_hh_mma"][1]).reshape(2, 2, 12, 2, 12, 32, 4, 2)
     rank, warp, mt, ks, lane, e = 1, 7, 1, 5, 22, 1
     gg, tig = lane // 4, lane % 4
     unit = rank * 96 + warp * 8 + gg
-    bf = lambda v: weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(np.asarray([v], np.float32)))[0]
+    bf = lambda v: weights.a16_bits_to_f32(weights.f32_to_a16_bits(np.asarray([v], np.float32)))[0]
     assert fr[1, rank, warp, mt, ks, lane, 0, e] == bf(src[2 * 192 + unit, ks * 16 + 2 * tig + e])        # gate g, row g
     assert fr[1, rank, warp, mt, ks, lane, 1, e] == bf(src[3 * 192 + unit, ks * 16 + 2 * tig + e])        # gate o, row g+8
     assert fr[1, rank, warp, mt, ks, lane, 3, e] == bf(src[3 * 192 + unit, ks * 16 + 2 * tig + 8 + e])
