@@ -5,7 +5,9 @@
 
 A "step" is one pass of the whole hot path (resize + chunk gather -> SE-VGG -> patch projection ->
 encoder -> merge + BiLSTM -> greedy decode) over one batch of 256 synthetic lines of resized width
-400-800 px (BASELINE.json configs[1]) per GPU.  Weak scaling: every rank owns its own batch (lines are
+400-800 px (BASELINE.json configs[1]) per GPU.  `--in-flight` (default 12) such passes run concurrently, each on
+its own handle + stream + host thread, because one decode chain alone leaves most SMs idle; `--coalesce k` puts k
+batches into one C-ABI call instead (K steps = K x 256 lines processed, whatever the grouping).  Weak scaling: every rank owns its own batch (lines are
 independent); no collective on the data path, one gather of the decoded ids at the end
 of each end-to-end step.  Prints ONE JSON line on rank 0.
 
@@ -60,9 +62,12 @@ def load_state_dict():
     return seeded_state_dict("se", 0, max_global_len=1024), "seeded random init"
 
 
-def make_batch(rank: int):
+def make_batch(rank: int, n_batches: int = 1):
+    """`n_batches` c2 batches of 256 lines (seeds rank, rank+1000, ...); seed 0 == the parity-test batch."""
     from khmer_ocr_cnn_transformer_b200 import synth
-    imgs, _ = synth.make_lines(LINES_PER_STEP, WIDTH_LO, WIDTH_HI, seed=rank)   # rank 0 == the parity-test batch
+    imgs = []
+    for b in range(n_batches):
+        imgs += synth.make_lines(LINES_PER_STEP, WIDTH_LO, WIDTH_HI, seed=rank + 1000 * b)[0]
     return imgs
 
 
@@ -155,8 +160,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
-    ap.add_argument("--phased", type=int, default=0,
-                    help="1: all in-flight batches run stages 1-5a, then all decode together (phase-separated schedule)")
     ap.add_argument("--dec-wide", type=int, default=-1,
                     help="decode GEMM shape: 1 = split-K over many CTAs (latency), 0 = few CTAs (throughput), -1 = auto")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch in the decode loop")
@@ -165,7 +168,12 @@ def main():
     ap.add_argument("--big-gemm-sms", type=int, default=132,
                     help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs)")
     ap.add_argument("--in-flight", type=int, default=12,
-                    help="batches in flight per GPU (one handle + stream + host thread each)")
+                    help="device passes in flight per GPU (one handle + stream + host thread each)")
+    ap.add_argument("--coalesce", type=int, default=1,
+                    help="256-line batches (steps) coalesced into one device pass / C-ABI call.  Measured on B200 "
+                         "(profiles/r01/README): 1 x 12 in flight, 4 x 4 and 8 x 3 all give 20-22 k lines/s - the decode "
+                         "loop is bound by per-line attention work, not by launch count - so the default keeps one "
+                         "256-line batch per call")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,75 +199,87 @@ def main():
     blob = weights.pack_blob(sd)
     S = max(1, args.in_flight)
 
+    KB = max(1, args.coalesce)
+    LPC = LINES_PER_STEP * KB                                   # lines per device pass
+
     class Worker:
-        """One in-flight batch: its own handle (weights + workspace + stream), its own pinned buffers."""
+        """One in-flight device pass: its own handle (weights + workspace + stream), its own pinned buffers.
+        A pass covers `KB` steps (256-line batches); `sub[k]` is the same data cut down to k batches for the tail."""
 
         def __init__(self, w):
-            self.imgs = make_batch(rank * 64 + w)           # rank 0 / worker 0 == the parity-test batch (seed 0)
-            self.batch = _native.LineBatch(self.imgs)
-            self.rec = _native.Recognizer(blob, device=local_rank, max_lines=LINES_PER_STEP,
-                                          max_chunks=LINES_PER_STEP * 11)
-            self.pix_host = torch.from_numpy(self.batch.pixels).pin_memory()
-            self.pix_dev = self.pix_host.cuda()
-            self.tok_host = torch.zeros((LINES_PER_STEP, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
-            self.len_host = torch.zeros(LINES_PER_STEP, dtype=torch.int32).pin_memory()
+            self.imgs = make_batch(rank * 64 + w, KB)       # rank 0 / worker 0 starts with the parity-test batch (seed 0)
+            self.rec = _native.Recognizer(blob, device=local_rank, max_lines=LPC, max_chunks=LPC * 11)
+            self.sub = {}
+            for k in sorted({KB, 1} | set(range(1, KB))):
+                b = _native.LineBatch(self.imgs[:k * LINES_PER_STEP])
+                host = torch.from_numpy(b.pixels).pin_memory()
+                bh = _native.LineBatch.__new__(_native.LineBatch)
+                bh.__dict__.update(b.__dict__)
+                bh.pixels = host.numpy()
+                self.sub[k] = (b, bh, host, host.cuda())
+            self.batch = self.sub[KB][0]
+            self.tok_host = torch.zeros((LPC, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
+            self.len_host = torch.zeros(LPC, dtype=torch.int32).pin_memory()
             self.tok_np, self.len_np = self.tok_host.numpy(), self.len_host.numpy()
             self.pool, self.n_stragglers, self.n_flushes = [], 0, 0
-            self.batch_host = _native.LineBatch.__new__(_native.LineBatch)
-            self.batch_host.__dict__.update(self.batch.__dict__)
-            self.batch_host.pixels = self.pix_host.numpy()
-            self.rec.set_option("dec_wide", 1 if (args.dec_wide == 1 or (args.dec_wide < 0 and S <= 4)) else 0)
-            if args.no_pdl:
+            self.rec.set_option("dec_wide", 1 if (args.dec_wide == 1 or (args.dec_wide < 0 and S * KB <= 4)) else 0)
+            # programmatic dependent launch shortens ONE decode chain (latency); with several passes in flight the early-
+            # resident dependents only hold SM slots while they wait, which costs ~7 % of throughput (tools/inflight_probe.py)
+            if args.no_pdl or S > 1:
                 self.rec.set_option("use_pdl", 0)
             if args.big_gemm_sms > 0 and S > 1:
                 self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
-            self.n_chunks = int(self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr()).sum())
+            self.n_chunks = int(self.rec.gather_chunks(self.sub[1][0], pixels_dev_ptr=self.sub[1][3].data_ptr()).sum())
 
-        # Long tail: a step returns once <= 8 of the 256 lines are still decoding; those stragglers are pooled and
-        # decoded to the end in batches of up to 256 (flush), inside the timed region.  Same results, see predictor.py.
-        def _collect(self):
-            todo = np.nonzero(self.rec.unfinished(LINES_PER_STEP))[0]
+        # Long tail: a pass returns once <= 8 lines per 256 are still decoding; those stragglers are pooled and decoded
+        # to the end in passes of up to LPC lines (flush), inside the timed region.  Same results, see predictor.py.
+        def _collect(self, k):
+            todo = np.nonzero(self.rec.unfinished(k * LINES_PER_STEP))[0]
             self.pool.extend(self.imgs[i] for i in todo)
             self.n_stragglers += len(todo)
-            if len(self.pool) >= LINES_PER_STEP:
+            if len(self.pool) >= LPC:
                 self.flush()
 
         def flush(self):
             while self.pool:
-                part, self.pool = self.pool[:LINES_PER_STEP], self.pool[LINES_PER_STEP:]
+                part, self.pool = self.pool[:LPC], self.pool[LPC:]
                 self.rec.set_option("straggler_threshold", 0)
                 self.rec.recognize_lines(_native.LineBatch(part))
                 self.n_flushes += 1
 
-        # The same step as two calls (stages 1-5a, then the decode loop) for the phased schedule below.
-        def step_heavy(self, host):
-            self.rec.set_option("straggler_threshold", args.straggler_threshold)
+        # The same pass as two calls (stages 1-5a, then the decode loop) for the phased schedule below.
+        def step_heavy(self, host, k=None):
+            k = k or KB
+            self.rec.set_option("straggler_threshold", args.straggler_threshold * k)
+            b, bh, _, dev = self.sub[k]
             if host:
-                self.rec.gather_chunks(self.batch_host)
+                self.rec.gather_chunks(bh)
             else:
-                self.rec.gather_chunks(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr())
+                self.rec.gather_chunks(b, pixels_dev_ptr=dev.data_ptr())
             self.rec.sevgg_encoder_forward()
             self.rec.merge_bilstm_forward()
 
-        def step_decode(self):
+        def step_decode(self, k=None):
             check = _native.check
             check(self.rec.lib.kocr_decode_greedy(self.rec._h, 0, self.tok_np.ctypes.data, self.len_np.ctypes.data, None))
-            self._collect()
+            self._collect(k or KB)
 
-        def step_resident(self):
-            self.rec.set_option("straggler_threshold", args.straggler_threshold)
-            self.rec.recognize_lines(self.batch, pixels_dev_ptr=self.pix_dev.data_ptr(), tokens_out=self.tok_np,
-                                     lengths_out=self.len_np)
-            self._collect()
+        def step_resident(self, k=None):
+            k = k or KB
+            self.rec.set_option("straggler_threshold", args.straggler_threshold * k)
+            b, _, _, dev = self.sub[k]
+            self.rec.recognize_lines(b, pixels_dev_ptr=dev.data_ptr(), tokens_out=self.tok_np, lengths_out=self.len_np)
+            self._collect(k)
 
-        def step_e2e(self):       # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
-            self.rec.set_option("straggler_threshold", args.straggler_threshold)
-            self.rec.recognize_lines(self.batch_host, tokens_out=self.tok_np, lengths_out=self.len_np)
-            self._collect()
+        def step_e2e(self, k=None):       # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
+            k = k or KB
+            self.rec.set_option("straggler_threshold", args.straggler_threshold * k)
+            self.rec.recognize_lines(self.sub[k][1], tokens_out=self.tok_np, lengths_out=self.len_np)
+            self._collect(k)
 
     workers = [Worker(w) for w in range(S)]
     n_chunks = workers[0].n_chunks
-    batch = workers[0].batch
+    batch = workers[0].sub[1][0]            # one 256-line step (byte counts are quoted per step)
     rec = workers[0].rec
 
     def barrier():
@@ -268,42 +288,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps_phased(kind, steps):
-        """Phased schedule: all in-flight batches run stages 1-5a (tensor-pipe bound), then all run their decode
-        loops together (latency / HBM bound), so the two kinds of kernels do not fight for SMs."""
-        n_workers = min(S, steps)
-        barrier_t = threading.Barrier(n_workers)
-        errors = []
-        rounds = (steps + n_workers - 1) // n_workers
-
-        def loop(wi, wk):
-            try:
-                torch.cuda.set_device(local_rank)
-                for r in range(rounds):
-                    active = r * n_workers + wi < steps
-                    if active:
-                        wk.step_heavy(kind == "e2e")
-                    barrier_t.wait()
-                    if active:
-                        wk.step_decode()
-                    barrier_t.wait()
-                wk.flush()
-            except Exception as e:
-                errors.append(e)
-                barrier_t.abort()
-
-        threads = [threading.Thread(target=loop, args=(i, wk)) for i, wk in enumerate(workers[:n_workers])]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-
     def run_steps(kind, steps):
-        """`steps` passes over a 256-line batch, at most S in flight (one host thread per in-flight batch)."""
-        if args.phased and S > 1:
-            return run_steps_phased(kind, steps)
+        """`steps` 256-line batches, `KB` of them per device pass, at most S passes in flight (one host thread each)."""
         counter = {"next": 0}
         lock = threading.Lock()
         errors = []
@@ -316,14 +302,15 @@ def main():
                     with lock:
                         i = counter["next"]
                         if i >= steps:
-                            return
-                        counter["next"] = i + 1
-                    fn()
+                            break
+                        k = min(KB, steps - i)
+                        counter["next"] = i + k
+                    fn(k)
                 wk.flush()          # decode this worker's pooled stragglers to the end (inside the timed region)
             except Exception as e:  # surface worker failures instead of hanging
                 errors.append(e)
 
-        threads = [threading.Thread(target=loop, args=(wk,)) for wk in workers[:min(S, steps)]]
+        threads = [threading.Thread(target=loop, args=(wk,)) for wk in workers[:max(1, min(S, (steps + KB - 1) // KB))]]
         for t in threads:
             t.start()
         for t in threads:
@@ -341,7 +328,7 @@ def main():
         a.record()
         run_steps(kind, steps)
         if world > 1 and kind == "e2e":   # the only collective: decoded ids to rank 0 (NCCL gather over NVLink)
-            dist.gather(workers[0].tok_host.cuda(non_blocking=True), gathered, dst=0)
+            dist.gather(workers[0].tok_host[:LINES_PER_STEP].cuda(non_blocking=True), gathered, dst=0)
         b.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -350,10 +337,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), wall_ms
 
-    run_steps("resident", max(args.warmup, S))
-    run_steps("e2e", max(args.warmup, S))
+    run_steps("resident", max(args.warmup, S * KB))
+    run_steps("e2e", max(args.warmup, S * KB))
     if world > 1:       # NCCL creates its communicator lazily on the first collective: do that outside the timed region
-        dist.gather(workers[0].tok_host.cuda(non_blocking=True), gathered, dst=0)
+        dist.gather(workers[0].tok_host[:LINES_PER_STEP].cuda(non_blocking=True), gathered, dst=0)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -366,22 +353,22 @@ def main():
     sampler.join(timeout=2)
     for wk in workers:          # one plain full-length step each for the length statistics
         wk.rec.set_option("straggler_threshold", 0)
-    workers[0].rec.recognize_lines(workers[0].batch, tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
-    mean_len = float(workers[0].len_np.mean())
+    workers[0].rec.recognize_lines(workers[0].sub[1][0], tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
+    mean_len = float(workers[0].len_np[:LINES_PER_STEP].mean())
     decode_steps = int(rec.debug_read("last_steps"))
 
     # ---- single in-flight latency of one step (for context)
     barrier()
     t0 = time.perf_counter()
     for _ in range(3):          # full-length decode of every line (no straggler hand-off)
-        workers[0].rec.recognize_lines(workers[0].batch_host, tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
+        workers[0].rec.recognize_lines(workers[0].sub[1][1], tokens_out=workers[0].tok_np, lengths_out=workers[0].len_np)
     lat_ms = (time.perf_counter() - t0) * 1e3 / 3
 
     # ---- instrumented pass: CUDA events around every launch of stages 2-5a (roofline evidence),
     #      one batch in flight so that the per-launch times are not perturbed by other streams
     rec.set_option("kernel_timing", 1)
     for _ in range(args.steps):
-        workers[0].step_resident()
+        workers[0].step_resident(1)            # one 256-line batch per pass: per-launch times of the c2 batch itself
     kt = rec.kernel_timing()
     rec.set_option("kernel_timing", 0)
     peaks = load_peaks()
@@ -432,7 +419,8 @@ def main():
             "config": {"workload": f"c2: {LINES_PER_STEP} synthetic Khmer text lines per GPU, resized width "
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
-                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_batches": S, "big_gemm_sms": args.big_gemm_sms, "phased_schedule": args.phased,
+                       "mean_decoded_len": mean_len, "decode_steps": decode_steps, "in_flight_device_passes": S, "big_gemm_sms": args.big_gemm_sms,
+                       "batches_coalesced_per_device_pass": KB, "lines_per_device_pass": LPC,
                        "straggler_threshold": args.straggler_threshold,
                        "stragglers_pooled": int(sum(wk.n_stragglers for wk in workers)),
                        "straggler_batches": int(sum(wk.n_flushes for wk in workers)),

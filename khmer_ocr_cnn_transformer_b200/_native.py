@@ -178,7 +178,7 @@ class Recognizer:
     def debug_read(self, name: str) -> np.ndarray:
         n = C.c_size_t()
         check(self.lib.kocr_debug_read(self._h, name.encode(), None, 0, C.byref(n)))
-        if name == "last_steps":
+        if name in ("last_steps", "host_launch_us", "host_wait_us"):       # scalar hooks come back in the size field
             return np.asarray(n.value)
         dtype = self.DEBUG_DTYPES.get(name, np.uint16)       # bf16 buffers come back as raw uint16
         out = np.empty(n.value // np.dtype(dtype).itemsize, dtype)

@@ -283,12 +283,14 @@ template <int C> struct SeSmem {
     static constexpr size_t A_BYTES = 32 * LDA * 2;
     static constexpr size_t Z_BYTES = 32 * LDZ * 2;
     static constexpr size_t G_BYTES = (size_t)SE_W * C * 4;
-    static constexpr size_t BYTES = A_BYTES + Z_BYTES + G_BYTES;
+    // the gate (written by FC2) re-uses the storage of the column means (dead once FC1 is done): 54 KB per CTA for
+    // C = 512 instead of 87 KB -> 4 resident CTAs per SM, which is what hides the HBM latency of the two streaming phases
+    static constexpr size_t BYTES = Z_BYTES + (A_BYTES > G_BYTES ? A_BYTES : G_BYTES);
 };
 
 // FINAL = false: (2,1) max-pool -> padded-linear (H/2, 25, C);  FINAL = true: AdaptiveAvgPool2d((2,32)) -> patch operand.
 template <int C, int H, bool FINAL>
-__global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const act16_t* __restrict__ in,
+__global__ void __launch_bounds__(SE_THREADS, 4) se_fused_kernel(const act16_t* __restrict__ in,
                                                               const act16_t* __restrict__ w0p /*[128][C]*/,
                                                               const float* __restrict__ b0p,
                                                               const act16_t* __restrict__ w2p /*[C][128]*/,
@@ -297,9 +299,9 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_fused_kernel(const act16_t* 
     using S = SeSmem<C>;
     constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8, TPG = SE_THREADS / CG;
     extern __shared__ __align__(16) uint8_t se_smem[];
-    act16_t* sA = reinterpret_cast<act16_t*>(se_smem);
-    act16_t* sZ = reinterpret_cast<act16_t*>(se_smem + S::A_BYTES);
-    float* sG = reinterpret_cast<float*>(se_smem + S::A_BYTES + S::Z_BYTES);
+    act16_t* sZ = reinterpret_cast<act16_t*>(se_smem);
+    act16_t* sA = reinterpret_cast<act16_t*>(se_smem + S::Z_BYTES);
+    float* sG = reinterpret_cast<float*>(se_smem + S::Z_BYTES);          // aliases sA (see SeSmem)
     const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const PLGeom gi = make_pl(H, SE_W);
     const uint4* src = reinterpret_cast<const uint4*>(in + (long)n * gi.S * C);

@@ -15,15 +15,18 @@ namespace kocr {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int EPI_WARPS = 8;              // two epilogue warps per TMEM lane quadrant, each takes half of the tile's columns
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 
 template <int BN> struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);   // 192 KB of operands
+    static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);   // 192 / 160 / 144 KB of operands
+    // per-epilogue-warp staging: one 4 KB tile; a second one where the fp32 addend is prefetched (BN <= 128 only)
+    static constexpr int STG_PER_WARP = (BN == 256) ? 4096 : 8192;
     static constexpr int TMEM_COLS = 2 * BN;                    // 256 / 512
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 8192 /*epilogue staging: 2 x 4 KB per warp*/;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * STG_PER_WARP;
 };
 
 struct GemmKernelParams {
@@ -57,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS * 32); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -135,7 +138,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int row_in_tile = quad * 32 + lane;
         const GemmEpilogue& ep = p.ep;
         // two 4 KB buffers per warp: the addend block of chunk c+1 streams in (cp.async) while chunk c is processed
-        const uint32_t stg_base = smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES + 256 + quad * 8192);
+        const int half = (warp - 2) >> 2;              // which half of the tile's 32-column chunks this warp handles
+        const uint32_t stg_base = smem_u32(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES + 256 + (warp - 2) * Cfg::STG_PER_WARP);
         // staging addressing (16-byte pieces, XOR-swizzled so that both the row-wise and the piece-wise access
         // patterns are bank-conflict free): fp32 rows of 8 pieces, a16 rows of 4 pieces
         const uint32_t own32 = lane * 128, own16 = lane * 64;     // offsets inside a staging buffer
@@ -169,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             auto fetch_addend = [&](int c) {           // async copy of the 32 x 32 fp32 addend block of chunk c (L2 path)
-                const uint32_t dstb = stg_base + (c & 1) * 4096;
+                const uint32_t dstb = stg_base + (c & 1) * (Cfg::STG_PER_WARP - 4096);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + r32;
@@ -177,7 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 cp_async_commit();
             };
-            if (ep.addend) fetch_addend(0);            // overlaps the wait for the accumulator
+            constexpr int CPW = BN / 32 / 2;            // chunks per epilogue warp
+            const int c0 = half * CPW;
+            if (ep.addend) fetch_addend(c0);           // overlaps the wait for the accumulator
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
@@ -194,10 +200,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
                     }
                 }
-                const uint32_t stg_u32 = stg_base + (c & 1) * 4096;
+                const uint32_t stg_u32 = stg_base + (c & 1) * (Cfg::STG_PER_WARP - 4096);
                 if (ep.addend) {
                     // the block of this chunk was requested one chunk ago; request the next one before waiting
-                    if (c + 1 < BN / 32) { fetch_addend(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                    if (c + 1 < c0 + CPW) { fetch_addend(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -262,22 +268,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
             // TMEM reads are double-buffered in registers: the load of chunk c+1 is in flight while chunk c is
             // processed; the accumulator stage is released as soon as its last chunk is in registers.
-            constexpr int NCH = BN / 32;
             uint32_t va[32], vb[32];
-            tmem_ld32(t_row, va);
+            tmem_ld32(t_row + c0 * 32, va);
 #pragma unroll 1
-            for (int c = 0; c < NCH; c += 2) {
+            for (int i = 0; i < CPW; i += 2) {
                 tmem_ld_wait();
-                tmem_ld32(t_row + (c + 1) * 32, vb);
-                if (rows_here > 0) process(va, c);
-                tmem_ld_wait();
-                if (c + 2 < NCH) {
-                    tmem_ld32(t_row + (c + 2) * 32, va);
+                if (i + 1 < CPW) {
+                    tmem_ld32(t_row + (c0 + i + 1) * 32, vb);
                 } else {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[acc]);
                 }
-                if (rows_here > 0) process(vb, c + 1);
+                if (rows_here > 0) process(va, c0 + i);
+                if (i + 1 < CPW) {
+                    tmem_ld_wait();
+                    if (i + 2 < CPW) {
+                        tmem_ld32(t_row + (c0 + i + 2) * 32, va);
+                    } else {
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (rows_here > 0) process(vb, c0 + i + 1);
+                }
             }
         }
     }
@@ -386,6 +398,7 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     KOCR_CHECK(p.N % BN == 0, "gemm: N %d not a multiple of the N tile %d", p.N, BN);
     KOCR_CHECK(p.taps == 1 || p.taps == 9, "gemm: taps must be 1 or 9");
     KOCR_CHECK(p.M > 0, "gemm: empty M");
+    KOCR_CHECK(!(BN == 256 && p.ep.addend), "gemm: the fp32 addend needs the double staging buffer of the N tiles <= 128");
     kp.M = p.M; kp.N = p.N; kp.taps = p.taps; kp.cin_blocks = p.cin / bke;
     for (int i = 0; i < 9; ++i) kp.tap_off[i] = i < p.taps ? p.tap_off[i] : 0;
     kp.num_m_tiles = (p.M + BM - 1) / BM;

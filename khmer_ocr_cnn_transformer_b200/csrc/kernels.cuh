@@ -90,6 +90,7 @@ int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache,
 int launch_dec_cross_attn(const float* q /*[L,384]*/, const act16_t* kv /*[Mtok,1536]*/, int layer,
                           const int* line_tok_off, const int* line_T, int max_T, const int* finished,
                           float* out, int n_lines, cudaStream_t stream, int nsplit, const float* bias);
+void set_dec_cross_attention_impl(int impl);   // 1 = one-pass online-softmax kernel (default), 0 = three-phase kernel
 int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths, int* finished, int* n_active,
                       const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
                       cudaStream_t stream, int nsplit, const float* bias);

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
 #include <map>
 #include <string>
 #include <tuple>
@@ -91,6 +92,7 @@ struct kocr_handle {
     int n_lines = 0, n_chunks = 0, n_tok = 0, max_T = 0, n_groups = 0, max_new_w = 0;
     std::vector<int> line_T, line_first_chunk, line_n_chunks;
     int last_steps = 0;
+    double host_launch_us = 0, host_wait_us = 0;   // decode loop: host time inside graph / kernel launches and inside stream waits
     // options
     int trace_logits = 0, force_tokens = 0;
     bool have_forced = false;
@@ -786,13 +788,17 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
     while (done < max_steps) {
         const int n = std::min(DEC_GROUP, max_steps - done);
         // the first group of a process runs eagerly (it sets the kernels' function attributes)
+        const auto t0 = std::chrono::steady_clock::now();
         if (n == DEC_GROUP && h->use_graphs && h->decode_warmed) KOCR_TRY(decode_group_graph(h, max_T, s));
         else KOCR_TRY(decode_group_eager(h, n, max_T, s));
+        const auto t1 = std::chrono::steady_clock::now();
+        h->host_launch_us += std::chrono::duration<double, std::micro>(t1 - t0).count();
         h->decode_warmed = true;
         done += n;
         if (!forcing && done < max_steps) {
             KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
             KOCR_CUDA(cudaStreamSynchronize(s));
+            h->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
             if (*h->pinned_flag <= h->straggler_threshold) break;     // every line (or all but a few stragglers) has emitted <eos>
         }
     }
@@ -821,6 +827,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
+    if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
@@ -975,6 +982,8 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
     else if (n == "logits") { src = h->named[n].p; bytes = (size_t)h->n_lines * VOCAB_PAD * 4; }
     else if (n == "logits_trace") { src = h->trace.p; bytes = (size_t)h->n_lines * DEC_MAX * VOCAB_PAD * 4; }
     else if (n == "last_steps") { if (bytes_out) *bytes_out = (size_t)h->last_steps; return 0; }
+    else if (n == "host_launch_us") { if (bytes_out) *bytes_out = (size_t)h->host_launch_us; return 0; }
+    else if (n == "host_wait_us") { if (bytes_out) *bytes_out = (size_t)h->host_wait_us; return 0; }
     KOCR_CHECK(src != nullptr, "kocr_debug_read: unknown or empty buffer '%s'", name);
     if (bytes_out) *bytes_out = bytes;
     if (dst == nullptr) return 0;

@@ -736,7 +736,18 @@ __global__ void __launch_bounds__(256) dec_self_attn_kernel(const float* __restr
     if (lane < HEAD_DIM / 2) {           // lanes 0..23 own one pair of the 48 head dims
         float o0 = 0.f, o1 = 0.f;
         const float2* vp = reinterpret_cast<const float2*>(vc + warp * HEAD_DIM) + lane;
-        for (int j = 0; j < nk; ++j) {
+        int j = 0;
+        for (; j + 8 <= nk; j += 8) {    // 8 value rows in flight: the loop is a chain of L2 latencies otherwise
+            float2 v2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v2[u] = __ldcg(vp + (long)(j + u) * (D_MODEL / 2));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                o0 = fmaf(s_p[warp][j + u], v2[u].x, o0);
+                o1 = fmaf(s_p[warp][j + u], v2[u].y, o1);
+            }
+        }
+        for (; j < nk; ++j) {
             const float2 v2 = __ldcg(vp + (long)j * (D_MODEL / 2));
             o0 = fmaf(s_p[warp][j], v2.x, o0);
             o1 = fmaf(s_p[warp][j], v2.y, o1);
@@ -880,9 +891,130 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
     }
 }
 
+// One-pass ("flash-decoding") version of the same cross-attention: every warp walks its keys ONCE, loading the K and
+// the V row of a key together (2 x 768 coalesced bytes, 4 keys = 6 KB in flight per warp), keeps a running
+// (max, sum, weighted V) per head with the online-softmax rescaling, and the 8 warps are merged through shared
+// memory at the end.  No score buffer, no intermediate __syncthreads, twice the bytes in flight: this kernel is the
+// HBM-bound part of a decode position (it streams the K/V of every active line at every position).
+__global__ void __launch_bounds__(256) dec_cross_attn_flash_kernel(const float* __restrict__ q,
+                                                                   const act16_t* __restrict__ kv, int layer,
+                                                                   const int* __restrict__ line_tok_off,
+                                                                   const int* __restrict__ line_T,
+                                                                   const int* __restrict__ finished,
+                                                                   float* __restrict__ out, int nsplit, int n_lines,
+                                                                   const float* __restrict__ bias) {
+    __shared__ float s_m[8][N_HEAD], s_l[8][N_HEAD];
+    __shared__ __align__(16) float s_o[8][D_MODEL];
+    const int l = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_trigger();
+    pdl_wait();
+    if (__ldcg(finished + l)) return;
+    const int T = line_T[l];
+    const int head = lane >> 2;                  // 4 lanes per head, 12 dims each
+    const uint2* kbase = reinterpret_cast<const uint2*>(kv + (long)line_tok_off[l] * (4 * D_MODEL) + layer * 2 * D_MODEL) + lane * 3;
+    const uint2* vbase = kbase + (D_MODEL * 2) / 8;           // +768 bytes
+    const long row_stride = (4 * D_MODEL * 2) / 8;            // uint2 per token row
+    float qv[12];
+    {
+        const float sc = rsqrtf((float)HEAD_DIM) * 1.4426950408889634f;      // scores in the base-2 domain
+        const float4* qp = reinterpret_cast<const float4*>(q + (long)l * D_MODEL + lane * 12);
+        const float4* bp = reinterpret_cast<const float4*>(bias + lane * 12);
+        float4 a = bp[0], b = bp[1], c = bp[2];
+        for (int sp = 0; sp < nsplit; ++sp) {               // sum the split-K partial results of the Q projection
+            const float4* r = qp + (long)sp * n_lines * (D_MODEL / 4);
+            const float4 x = __ldcg(r), y = __ldcg(r + 1), z = __ldcg(r + 2);
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+            c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+        }
+        qv[0] = a.x * sc; qv[1] = a.y * sc; qv[2] = a.z * sc; qv[3] = a.w * sc;
+        qv[4] = b.x * sc; qv[5] = b.y * sc; qv[6] = b.z * sc; qv[7] = b.w * sc;
+        qv[8] = c.x * sc; qv[9] = c.y * sc; qv[10] = c.z * sc; qv[11] = c.w * sc;
+    }
+    float m = -INFINITY, lsum = 0.f, o[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = 0.f;
+    for (int j0 = warp; j0 < T; j0 += 32) {           // keys j0, j0+8, j0+16, j0+24 of this warp in flight together
+        uint2 k[4][3], v[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 8 * u;
+            if (j < T) {
+                const uint2* kp = kbase + (long)j * row_stride;
+                const uint2* vp = vbase + (long)j * row_stride;
+                k[u][0] = __ldg(kp); k[u][1] = __ldg(kp + 1); k[u][2] = __ldg(kp + 2);
+                v[u][0] = __ldg(vp); v[u][1] = __ldg(vp + 1); v[u][2] = __ldg(vp + 2);
+            }
+        }
+        float sc4[4];
+        float mx = m;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float acc = -INFINITY;
+            if (j0 + 8 * u < T) {
+                acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    acc = fmaf(qv[4 * i], a16_lo(k[u][i].x), acc); acc = fmaf(qv[4 * i + 1], a16_hi(k[u][i].x), acc);
+                    acc = fmaf(qv[4 * i + 2], a16_lo(k[u][i].y), acc); acc = fmaf(qv[4 * i + 3], a16_hi(k[u][i].y), acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);        // j0 + 8u < T is warp-uniform
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            }
+            sc4[u] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        const float resc = exp2f(m - mx);           // first iteration: exp2(-inf) = 0 (key j0 always exists, mx is finite)
+        m = mx;
+        lsum *= resc;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) o[i] *= resc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j0 + 8 * u < T) {
+                const float pj = exp2f(sc4[u] - mx);
+                lsum += pj;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    o[4 * i] = fmaf(pj, a16_lo(v[u][i].x), o[4 * i]); o[4 * i + 1] = fmaf(pj, a16_hi(v[u][i].x), o[4 * i + 1]);
+                    o[4 * i + 2] = fmaf(pj, a16_lo(v[u][i].y), o[4 * i + 2]); o[4 * i + 3] = fmaf(pj, a16_hi(v[u][i].y), o[4 * i + 3]);
+                }
+            }
+        }
+    }
+    // ---- merge the 8 warps (a warp with no key at all has m = -inf, l = 0, o = 0 and drops out)
+    if ((lane & 3) == 0) { s_m[warp][head] = m; s_l[warp][head] = lsum; }
+#pragma unroll
+    for (int i = 0; i < 12; i += 4)
+        *reinterpret_cast<float4*>(&s_o[warp][lane * 12 + i]) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    __syncthreads();
+    for (int d = tid; d < D_MODEL; d += 256) {
+        const int h = d / HEAD_DIM;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w][h]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float f = exp2f(s_m[w][h] - M);
+            num = fmaf(s_o[w][d], f, num);
+            den = fmaf(s_l[w][h], f, den);
+        }
+        store_attn_out(num / den, (long)l * D_MODEL + d, out);
+    }
+}
+
+static int g_dec_cross_impl = 1;       // 1: one-pass kernel, 0: three-phase kernel (kept for A/B tests)
+void set_dec_cross_attention_impl(int impl) { g_dec_cross_impl = impl; }
+
 int launch_dec_cross_attn(const float* q, const act16_t* kv, int layer, const int* line_tok_off,
                           const int* line_T, int max_T, const int* finished, float* out, int n_lines,
                           cudaStream_t stream, int nsplit, const float* bias) {
+    if (g_dec_cross_impl == 1) {
+        KOCR_CUDA(launch_kernel(dec_cross_attn_flash_kernel, dim3(n_lines), dim3(256), 0, stream, q, kv, layer, line_tok_off,
+                                line_T, finished, out, nsplit, n_lines, bias));
+        return 0;
+    }
     const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);
     KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
     static bool attr_set = false;
