@@ -89,6 +89,114 @@ int launch_conv1_pool(const float* d_chunks, const float* w, const float* b, act
     return 0;
 }
 
+__device__ __forceinline__ void mma_a16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." KOCR_MMA_A16 "." KOCR_MMA_A16 ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------
+// conv1 + pool1 on the tensor cores.  The CUDA-core kernel above issues 9 FMAs per output value (10.4 GFLOP over the
+// c2 batch = 0.32 ms of FP32 pipe); here one CTA per chunk keeps the chunk as a zero-bordered 16-bit tile in shared
+// memory and runs the 3x3 conv as an implicit GEMM with K = 9 taps padded to 16 on mma.sync.m16n8k16
+// (M = 16 pixels, N = 8 channels, fp32 accumulation; K = 9 is far too thin for a tcgen05 tile, and the kernel
+// is bound by its 163 KB of output per chunk anyway).
+// Row mapping of the two M-tiles of a "pool tile" (8 pooled pixels of one pooled row): tile A rows g / g+8 are the
+// pixels (2py, 2px) / (2py, 2px+1), tile B the same on row 2py+1, px = 8i + g - so the four partners of a 2x2 pool
+// window are the accumulators c0/c2 (c1/c3) of the two tiles of ONE thread: pooling needs no data exchange.
+// bias and ReLU commute with the max.  Output: padded-linear (24, 50, 64), staged per warp in shared memory and
+// written as one contiguous 1 KB run (8 pixels x 128 B) per pool tile.
+// ------------------------------------------------------------------------------------------
+static constexpr int C1M_LD = 104;                // halves per tile row: 102 used (x = -1 .. 100), 16-byte multiple
+
+__global__ void __launch_bounds__(256) conv1_pool_mma_kernel(const float* __restrict__ chunks,
+                                                             const act16_t* __restrict__ w16 /*[64][16], k = tap, 9..15 zero*/,
+                                                             const float* __restrict__ b, act16_t* __restrict__ out) {
+    __shared__ __align__(16) act16_t s_tile[(IMG_H + 2) * C1M_LD];
+    __shared__ __align__(16) uint32_t s_stage[8][8][32];          // [warp][pooled pixel][64 channels as 32 words]
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const PLGeom go = make_pl(IMG_H / 2, CHUNK_W / 2);            // 24 x 50 output
+    {   // zero-bordered 16-bit copy of the chunk: s_tile[(y + 1) * LD + (x + 1)]
+        uint32_t* z = reinterpret_cast<uint32_t*>(s_tile);
+        for (int i = tid; i < (IMG_H + 2) * C1M_LD / 2; i += 256) z[i] = 0u;
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(chunks + (long)n * IMG_H * CHUNK_W);
+#pragma unroll 5
+        for (int i = tid; i < IMG_H * (CHUNK_W / 4); i += 256) {
+            const int y = i / (CHUNK_W / 4), x4 = i - y * (CHUNK_W / 4);
+            const float4 v = __ldg(src + i);
+            act16_t* d = s_tile + (y + 1) * C1M_LD + x4 * 4 + 1;
+            d[0] = to_a16(v.x); d[1] = to_a16(v.y); d[2] = to_a16(v.z); d[3] = to_a16(v.w);
+        }
+    }
+    // weights as B fragments (B[k = tap][n = channel] = w16[channel][tap]) and the bias of this thread's channels
+    uint32_t bw[8][2];
+    float bs[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const act16_t* wr = w16 + (nt * 8 + g) * 16 + 2 * t;
+        bw[nt][0] = *reinterpret_cast<const uint32_t*>(wr);
+        bw[nt][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+        bs[nt][0] = __ldg(b + nt * 8 + 2 * t);
+        bs[nt][1] = __ldg(b + nt * 8 + 2 * t + 1);
+    }
+    __syncthreads();
+    // taps of this thread's A registers: k = 2t, 2t + 1 (a0/a1) and k = 8 (a2/a3, t == 0 only); tap k = (k / 3, k % 3)
+    const int k0 = 2 * t, k1 = 2 * t + 1;
+    const int off0 = (k0 / 3) * C1M_LD + (k0 % 3), off1 = (k1 / 3) * C1M_LD + (k1 % 3), off8 = 2 * C1M_LD + 2;
+    const unsigned short* tile16 = reinterpret_cast<const unsigned short*>(s_tile);
+    constexpr int GROUPS = (CHUNK_W / 2 + 7) / 8;                 // 7 groups of 8 pooled columns per pooled row
+    for (int pt = warp; pt < (IMG_H / 2) * GROUPS; pt += 8) {
+        const int py = pt / GROUPS, gi = pt - py * GROUPS;
+        const int px = min(gi * 8 + g, CHUNK_W / 2 - 1);          // clamped: results of columns >= 50 are never stored
+        uint32_t a[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                             // tile A: input row 2py, tile B: 2py + 1
+            const unsigned short* p0 = tile16 + (2 * py + r) * C1M_LD + 2 * px;       // pixel (2py + r, 2px), tap (0, 0)
+            a[r][0] = (uint32_t)p0[off0] | ((uint32_t)p0[off1] << 16);
+            a[r][1] = (uint32_t)p0[off0 + 1] | ((uint32_t)p0[off1 + 1] << 16);        // pixel (2py + r, 2px + 1)
+            a[r][2] = t == 0 ? (uint32_t)p0[off8] : 0u;
+            a[r][3] = t == 0 ? (uint32_t)p0[off8 + 1] : 0u;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_a16_16816(ca, a[0], bw[nt][0], bw[nt][1]);
+            mma_a16_16816(cb, a[1], bw[nt][0], bw[nt][1]);
+            const float v0 = fmaxf(fmaxf(fmaxf(ca[0], ca[2]), fmaxf(cb[0], cb[2])) + bs[nt][0], 0.f);
+            const float v1 = fmaxf(fmaxf(fmaxf(ca[1], ca[3]), fmaxf(cb[1], cb[3])) + bs[nt][1], 0.f);
+            s_stage[warp][g][((nt ^ g) & 7) * 4 + t] = pack_a16(v0, v1);         // XOR swizzle: conflict-free both ways
+        }
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(out + ((long)n * go.S + (long)py * go.P + gi * 8) * 64);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int idx = lane + 32 * r, x = idx >> 3, p = idx & 7;             // pooled pixel x of the tile, 16-byte piece p
+            const int col = gi * 8 + x;
+            const uint4 v = *reinterpret_cast<const uint4*>(&s_stage[warp][x][((p ^ x) & 7) * 4]);
+            if (col < go.W) dst[idx] = v;
+            else if (col == go.W) dst[idx] = make_uint4(0, 0, 0, 0);             // the shared zero pad column
+        }
+        __syncwarp();
+    }
+    if (warp == 0) {                                                             // the zero pad row below the chunk
+        uint4* dst = reinterpret_cast<uint4*>(out + ((long)n * go.S + (long)go.H * go.P) * 64);
+        for (int i = lane; i < go.P * 8; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+static int g_conv1_impl = 1;           // 1: tensor-core kernel, 0: CUDA-core kernel (A/B tests)
+void set_conv1_impl(int impl) { g_conv1_impl = impl; }
+
+int launch_conv1_pool_mma(const float* d_chunks, const act16_t* w16, const float* b, act16_t* out, int n_chunks,
+                          cudaStream_t stream) {
+    if (n_chunks == 0) return 0;
+    conv1_pool_mma_kernel<<<n_chunks, 256, 0, stream>>>(d_chunks, w16, b, out);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+int conv1_impl() { return g_conv1_impl; }
+
 // ------------------------------------------------------------------------------------------
 // 2x2 max-pool between padded-linear layouts.  One thread per (output position, 8 channels).
 // ------------------------------------------------------------------------------------------
@@ -267,11 +375,6 @@ int launch_se_apply_finalpool(const act16_t* in, const float* gate, act16_t* out
 // run on mma.sync.m16n8k16 (a16, fp32 accumulate) with the column means / hidden vector as A operands in shared
 // memory and the weights read straight from L2 as B fragments.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_a16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." KOCR_MMA_A16 "." KOCR_MMA_A16 ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 static constexpr int SE_W = 25;            // columns of every SE stage (100 / 4)
 static constexpr int SE_THREADS = 256;

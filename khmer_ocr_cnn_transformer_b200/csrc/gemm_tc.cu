@@ -15,17 +15,22 @@ namespace kocr {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int EPI_WARPS = 8;              // two epilogue warps per TMEM lane quadrant, each takes half of the tile's columns
-static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-
-template <int BN> struct GemmCfg {
+// Two instantiation families:
+//  * 16-bit operands (stages 2-5a, throughput): 8 epilogue warps (two per TMEM lane quadrant, each takes half of the
+//    tile's columns), operand ring as deep as shared memory allows, one CTA per SM;
+//  * TF32 operands (decode loop, latency chains of tiny GEMMs from many streams): 4 epilogue warps, 3-stage ring,
+//    ~113 KB and 192 threads per CTA so that two of them - or one plus the attention CTAs of other streams - fit on an SM.
+template <int BN, bool TF32> struct GemmCfg {
+    static constexpr int EPI_WARPS = TF32 ? 4 : 8;
+    static constexpr int THREADS = 64 + EPI_WARPS * 32;
+    static constexpr int MIN_CTAS = (TF32 && BN <= 128) ? 2 : 1;
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
-    static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
+    static constexpr int B_BYTES = BN * BK * 2;                 // 8 / 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);   // 192 / 160 / 144 KB of operands
-    // per-epilogue-warp staging: one 4 KB tile; a second one where the fp32 addend is prefetched (BN <= 128 only)
-    static constexpr int STG_PER_WARP = (BN == 256) ? 4096 : 8192;
-    static constexpr int TMEM_COLS = 2 * BN;                    // 256 / 512
+    static constexpr int NSTAGE = TF32 ? 3 : ((BN == 256) ? 4 : 5);
+    // per-epilogue-warp staging: one 4 KB tile; a second one where the fp32 addend is prefetched (16-bit, BN <= 128 only)
+    static constexpr int STG_PER_WARP = (TF32 || BN == 256) ? 4096 : 8192;
+    static constexpr int TMEM_COLS = 2 * BN;                    // 128 / 256 / 512
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * STG_PER_WARP;
 };
 
@@ -39,10 +44,10 @@ struct GemmKernelParams {
 
 // BK is 128 bytes of K per row in both precisions: 64 a16 or 32 fp32 (TF32) elements.
 template <int BN, bool TF32>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, TF32>::THREADS), (GemmCfg<BN, TF32>::MIN_CTAS))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmKernelParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, TF32>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
@@ -60,7 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS * 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], Cfg::EPI_WARPS * 32); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -181,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 cp_async_commit();
             };
-            constexpr int CPW = BN / 32 / 2;            // chunks per epilogue warp
+            constexpr int CPW = BN / 32 / (Cfg::EPI_WARPS / 4);      // chunks per epilogue warp
             const int c0 = half * CPW;
             if (ep.addend) fetch_addend(c0);           // overlaps the wait for the accumulator
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -398,7 +403,7 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     KOCR_CHECK(p.N % BN == 0, "gemm: N %d not a multiple of the N tile %d", p.N, BN);
     KOCR_CHECK(p.taps == 1 || p.taps == 9, "gemm: taps must be 1 or 9");
     KOCR_CHECK(p.M > 0, "gemm: empty M");
-    KOCR_CHECK(!(BN == 256 && p.ep.addend), "gemm: the fp32 addend needs the double staging buffer of the N tiles <= 128");
+    KOCR_CHECK(!((BN == 256 || p.tf32) && p.ep.addend), "gemm: the fp32 addend needs the double staging buffer of the 16-bit N tiles <= 128");
     kp.M = p.M; kp.N = p.N; kp.taps = p.taps; kp.cin_blocks = p.cin / bke;
     for (int i = 0; i < 9; ++i) kp.tap_off[i] = i < p.taps ? p.tap_off[i] : 0;
     kp.num_m_tiles = (p.M + BM - 1) / BM;
@@ -418,7 +423,7 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
 template <int BN, bool TF32>
 static int launch_impl(const void* a, long rowsA, const void* w, const GemmProblem& p, int num_sms,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, TF32>;
     GemmKernelParams kp;
     KOCR_TRY(fill_params(kp, p, BN));
     CUtensorMap ta, tb;
@@ -432,7 +437,7 @@ static int launch_impl(const void* a, long rowsA, const void* w, const GemmProbl
     }
     const int tiles = kp.num_m_tiles * kp.num_n_tiles * kp.split_k;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    KOCR_CUDA(launch_kernel(gemm_tc_kernel<BN, TF32>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, kp));
+    KOCR_CUDA(launch_kernel(gemm_tc_kernel<BN, TF32>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, kp));
     ++g_gemm_launches;
     return 0;
 }

@@ -34,6 +34,11 @@ int preprocess_kmax();
 // conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool: f32 chunks -> a16 padded-linear (24x50, 64).
 int launch_conv1_pool(const float* d_chunks, const float* w /*[64][9]*/, const float* b /*[64]*/,
                       act16_t* out, int n_chunks, cudaStream_t stream);
+// Tensor-core version (mma.sync, K = 9 taps padded to 16): w16 = a16 [64][16].  set_conv1_impl(0) selects the CUDA-core kernel.
+int launch_conv1_pool_mma(const float* d_chunks, const act16_t* w16, const float* b, act16_t* out, int n_chunks,
+                          cudaStream_t stream);
+void set_conv1_impl(int impl);
+int conv1_impl();
 // 2x2 max-pool between padded-linear layouts (C multiple of 8).
 int launch_pool2x2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
 // 1D-SE: squeeze -> column means a16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;

@@ -63,6 +63,7 @@ struct kocr_handle {
     size_t blob_bytes = 0;
     std::map<std::string, std::pair<const void*, size_t>> w;
     const float *conv1_w, *conv1_b;
+    const act16_t* conv1_w16;      // [64][16]: 9 taps + 7 zeros, tensor-core conv1
     const act16_t* conv_w[8];
     const float* conv_b[8];
     SEWeights se[3];
@@ -144,6 +145,7 @@ int resolve_weights(kocr_handle* h) {
     static const int cout[8] = {0, 64, 128, 256, 256, 512, 512, 512};
     W_F32(h->conv1_w, "conv1.w", 64 * 9);
     W_F32(h->conv1_b, "conv1.b", 64);
+    W_A16(h->conv1_w16, "conv1.w16", 64 * 16);
     char nm[64];
     for (int i = 2; i <= 7; ++i) {
         snprintf(nm, sizeof nm, "conv%d.w", i); W_A16(h->conv_w[i], nm, (size_t)cout[i] * 9 * cin[i]);
@@ -258,6 +260,10 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaMallocHost(&h->fin_host, (size_t)h->max_lines * 4));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming));
     KOCR_CUDA(cudaStreamCreate(&h->own_stream));
+    // input staging sized for the handle's capacity up front (4x the bytes of the height-48 chunks: source lines are
+    // rarely more than 2x oversampled): a cudaMalloc in the middle of a run would synchronise every in-flight batch
+    KOCR_TRY(ensure(h->pixels_dev, (size_t)h->max_chunks * CHUNK_STRIDE * IMG_H * 4));
+    KOCR_TRY(ensure(h->mid_dev, (size_t)h->max_chunks * CHUNK_STRIDE * IMG_H * 2));
     return 0;
 }
 
@@ -352,7 +358,9 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     auto B = [&](const char* n) { return buf<act16_t>(h, n); };
     const double nc = NC;
     auto cf = [&](int H, int W, int ci, int co) { return 2.0 * nc * H * W * 9.0 * ci * co; };   // algorithmic conv FLOPs
-    TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s)); ++g_launches;
+    if (conv1_impl() == 1) TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
+    else TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s));
+    ++g_launches;
     TIMED("conv2", cf(24, 50, 64, 128), gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
     TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
     TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
@@ -828,6 +836,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
+    if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }

@@ -137,6 +137,8 @@ def pack_tensors(sd: dict) -> dict:
                        sd[p + ".1.running_mean"], sd[p + ".1.running_var"])
         if i == 1:
             f32("conv1.w", w.reshape(64, 9))
+            w16 = np.zeros((64, 16), np.float32); w16[:, :9] = w.reshape(64, 9)
+            bf16("conv1.w16", w16)                      # tensor-core conv1: K = 9 taps zero-padded to 16
             f32("conv1.b", b)
         else:
             bf16(f"conv{i}.w", conv_to_kmajor(w))

@@ -274,3 +274,24 @@ def test_chunk_attention_mma_agrees_with_cuda_core_kernel(rec_seeded_se):
     err = rel_err(got[1], got[0])
     _report("chunk_attention_mma_vs_fp32_rel_err", err)
     assert err < 5e-3, err
+
+
+def test_conv1_tensor_core_kernel_agrees_with_cuda_core_kernel(rec_seeded_se):
+    """conv1 + pool1 as an implicit GEMM on mma.sync (K = 9 taps padded to 16, 16-bit pixels and weights, fp32
+    accumulation) against the fp32 CUDA-core kernel: pool1 agrees to the 16-bit operand rounding, pads stay zero."""
+    from khmer_ocr_cnn_transformer_b200 import _native
+    rec, _ = rec_seeded_se
+    imgs = _lines(5, 100, 1200, seed=23)
+    got = {}
+    try:
+        for mode in (0, 1):
+            rec.set_option("conv1_impl", mode)
+            counts = rec.gather_chunks(_native.LineBatch(imgs))
+            rec.sevgg_encoder_forward()
+            got[mode] = pl_to_nchw(rec.debug_read("pool1"), int(counts.sum()), 24, 50, 64)
+    finally:
+        rec.set_option("conv1_impl", 1)
+    assert np.all(got[1][1] == 0) and np.all(got[0][1] == 0)
+    err = rel_err(got[1][0], got[0][0])
+    _report("conv1_mma_vs_fp32_rel_err", err)
+    assert err < 2e-3, err
