@@ -219,6 +219,8 @@ const PLGeom G1 = make_pl(24, 50), G2 = make_pl(12, 25), G3 = make_pl(6, 25), G4
 
 struct WsItem { const char* name; size_t bytes; };
 
+int ensure(Buf& b, size_t bytes);
+
 int carve_workspace(kocr_handle* h) {
     const size_t NC = h->max_chunks, L = h->max_lines, M = NC * TOK_PER_CHUNK;
     const size_t D = D_MODEL;
