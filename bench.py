@@ -165,8 +165,9 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch in the decode loop")
     ap.add_argument("--straggler-threshold", type=int, default=8,
                     help="a step returns once <= this many of its 256 lines are still decoding; they are pooled")
-    ap.add_argument("--big-gemm-sms", type=int, default=132,
-                    help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs)")
+    ap.add_argument("--big-gemm-sms", type=int, default=0,
+                    help="persistent grid size of the large GEMMs when several batches are in flight (0 = all SMs; "
+                         "reserving SMs for the small decode kernels measured no gain: tools/inflight_probe.py)")
     ap.add_argument("--in-flight", type=int, default=12,
                     help="device passes in flight per GPU (one handle + stream + host thread each)")
     ap.add_argument("--coalesce", type=int, default=1,

@@ -376,6 +376,10 @@ int launch_se_apply_finalpool(const act16_t* in, const float* gate, act16_t* out
 // memory and the weights read straight from L2 as B fragments.
 // ------------------------------------------------------------------------------------------
 
+// sigmoid with the approximate reciprocal (MUFU.RCP, 1 ulp): the IEEE division of `1.f / (1.f + __expf(-x))` expands to a
+// branchy ~20-instruction sequence and was a third of this kernel's stall samples; the gate only scales 16-bit activations
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 static constexpr int SE_W = 25;            // columns of every SE stage (100 / 4)
 static constexpr int SE_THREADS = 256;
 
@@ -496,10 +500,10 @@ __global__ void __launch_bounds__(SE_THREADS, 4) se_fused_kernel(const act16_t* 
                 const int r0 = mt * 16 + g, r1 = r0 + 8;
                 if (r0 < SE_W)
                     *reinterpret_cast<float2*>(sG + r0 * C + col) =
-                        make_float2(1.f / (1.f + __expf(-(d[0] + bb0))), 1.f / (1.f + __expf(-(d[1] + bb1))));
+                        make_float2(fast_sigmoid(d[0] + bb0), fast_sigmoid(d[1] + bb1));
                 if (r1 < SE_W)
                     *reinterpret_cast<float2*>(sG + r1 * C + col) =
-                        make_float2(1.f / (1.f + __expf(-(d[2] + bb0))), 1.f / (1.f + __expf(-(d[3] + bb1))));
+                        make_float2(fast_sigmoid(d[2] + bb0), fast_sigmoid(d[3] + bb1));
             }
         }
     }
