@@ -377,7 +377,7 @@ def main():
     dom = kt.get("conv6", {"ms": 0.0, "launches": 0, "flops": 0.0})
     traffic, traffic_note = None, None
     try:        # DRAM bytes of this launch from the committed `ncu --set full` capture of the same workload
-        cap = json.loads((REPO / "profiles" / "r01" / "conv6_ncu_v2.json").read_text())
+        cap = json.loads((REPO / "profiles" / "r01" / "conv6_ncu_v4.json").read_text())
         if cap.get("chunks") == n_chunks:
             traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * 1e6
             traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, " + cap["source"] +
@@ -416,7 +416,7 @@ def main():
         line = {
             "metric": "text_lines_per_s", "value": value, "unit": "lines/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": f"c2: {LINES_PER_STEP} synthetic Khmer text lines per GPU, resized width "
                                    f"{WIDTH_LO}-{WIDTH_HI} px ({n_chunks} chunks of 48x100), SE-VGG-Transformer, greedy decode",
                        "weights": wname, "lines_per_gpu": LINES_PER_STEP, "chunks_per_gpu": n_chunks,
