@@ -96,6 +96,18 @@ int kocr_set_option(kocr_handle* h, const char* name, int value);
 int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
                    float* logits_out, void* stream);
 
+/* Input side - extract_textline_crops (netra_ocr/textline_detection.py:7-53) and the custom-detector crop of
+ * OCREngine (netra_ocr/ocr_engine.py:72-76), followed by the `convert('L')` of ImagePreprocessor.process
+ * (recognition/preprocessor.py:39-41).  page = uint8 [page_h][page_w][channels] (3 = RGB, 1 = L), host or device.
+ * boxes = host int32 [n_lines][4] = (x0, y0, x1, y1), already expanded and clipped to the page by the caller (the
+ * reference does that arithmetic in Python ints).  Line i is written to out_pixels_dev + out_offsets[i] (DEVICE
+ * memory owned by the caller) as a grey image of (y1 - y0 + 2 pad_px) rows x (x1 - x0 + 2 pad_px) columns: the crop
+ * in the middle of a white (255) canvas - ready for kocr_gather_chunks / kocr_recognize_lines with
+ * pixels_on_device = 1.  Bit-exact with Pillow (crop, paste, rgb2l = (19595 R + 38470 G + 7471 B + 0x8000) >> 16). */
+int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w, int channels, int page_on_device,
+                    const int32_t* boxes, int n_lines, int pad_px, uint8_t* out_pixels_dev, const int64_t* out_offsets,
+                    void* stream);
+
 /* Long-tail handling.  With option "straggler_threshold" = n > 0, kocr_decode_greedy / kocr_recognize_lines return as
  * soon as at most n lines are still decoding (checked every 8 positions).  flags_out[i] = 1 marks the lines whose
  * row is incomplete; the caller re-submits those lines in a later batch (greedy decoding is deterministic, so the

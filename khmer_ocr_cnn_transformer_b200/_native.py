@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_crop_lines",
 ]
 
 _lib = None
@@ -56,6 +56,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
     lib.kocr_beam_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp]
     lib.kocr_beam_step.restype = i32
+    lib.kocr_crop_lines.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]
+    lib.kocr_crop_lines.restype = i32
     lib.kocr_read_unfinished.argtypes = [vp, vp]
     lib.kocr_read_unfinished.restype = i32
     lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
@@ -103,6 +105,21 @@ class LineBatch:
         self.offsets = np.asarray(offs, np.int64)
         self.heights = np.asarray(hs, np.int32)
         self.widths = np.asarray(ws, np.int32)
+
+
+def line_batch_from_shapes(shapes):
+    """A LineBatch that only describes lines living in DEVICE memory (kocr_crop_lines output): shapes = [(h, w), ...]."""
+    b = LineBatch.__new__(LineBatch)
+    hs = [int(h) for h, _ in shapes]
+    ws = [int(w) for _, w in shapes]
+    sizes = [h * w for h, w in zip(hs, ws)]
+    b.n = len(shapes)
+    b.pixel_bytes = int(sum(sizes))
+    b.pixels = np.empty(1, np.uint8)
+    b.offsets = np.asarray(np.cumsum([0] + sizes[:-1]) if sizes else [], np.int64)
+    b.heights = np.asarray(hs, np.int32)
+    b.widths = np.asarray(ws, np.int32)
+    return b
 
 
 class Recognizer:
@@ -194,6 +211,18 @@ class Recognizer:
         logits = np.zeros((n_rows, 128), np.float32)
         check(self.lib.kocr_beam_step(self._h, line, n_rows, _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
         return logits[:, :124]
+
+    def crop_lines(self, page, boxes, pad_px: int, out_dev_ptr: int, out_offsets, page_dev_ptr=None, stream=None):
+        """Cut `boxes` (int32 [n, 4] = x0, y0, x1, y1, clipped) out of `page` (uint8 (H, W) or (H, W, 3); pass
+        `page_dev_ptr` if it already lives on the device), add `pad_px` of white and convert to grey, into the device
+        buffer at `out_dev_ptr` (line i at out_offsets[i])."""
+        boxes = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
+        offs = np.ascontiguousarray(out_offsets, np.int64)
+        ch = 1 if page.ndim == 2 else int(page.shape[2])
+        src = _ptr(page_dev_ptr) if page_dev_ptr is not None else _ptr(np.ascontiguousarray(page))
+        check(self.lib.kocr_crop_lines(self._h, src, int(page.shape[0]), int(page.shape[1]), ch,
+                                       1 if page_dev_ptr is not None else 0, _ptr(boxes), boxes.shape[0], int(pad_px),
+                                       _ptr(out_dev_ptr), _ptr(offs), _ptr(stream)))
 
     def unfinished(self, n_lines: int) -> np.ndarray:
         """Flags of the lines left incomplete by an early return (option "straggler_threshold")."""

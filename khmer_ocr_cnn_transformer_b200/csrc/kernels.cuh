@@ -27,6 +27,9 @@ struct LineDesc {
 // ---- stage 1 ---------------------------------------------------------------------------
 int launch_preprocess(const uint8_t* d_pixels, uint8_t* d_mid, const LineDesc* d_lines, const int* d_chunk_line,
                       int* d_vtab, float* d_chunks, int n_lines, int n_chunks, int max_new_w, cudaStream_t stream);
+// text-line crops of a page (box + white padding + RGB->L), see preprocess.cu
+int launch_crop_lines(const uint8_t* d_page, int page_w, int channels, const int* d_boxes, const long long* d_offsets,
+                      int n_lines, int pad, uint8_t* d_out, cudaStream_t stream);
 int preprocess_vtab_ints_per_line();
 int preprocess_kmax();
 

@@ -106,6 +106,7 @@ struct kocr_handle {
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
+    Buf crop_page, crop_tab;      // kocr_crop_lines: device copy of a host page, boxes + offsets
     Buf beam_cache;              // [2 ping-pong][K,V][2 layers][BEAM_MAX][DEC_MAX][384] fp32, allocated on first use
     int beam_cur = 0;
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
@@ -634,6 +635,8 @@ int kocr_destroy(kocr_handle* h) {
     if (h->mid_dev.p) cudaFree(h->mid_dev.p);
     if (h->trace.p) cudaFree(h->trace.p);
     if (h->beam_cache.p) cudaFree(h->beam_cache.p);
+    if (h->crop_page.p) cudaFree(h->crop_page.p);
+    if (h->crop_tab.p) cudaFree(h->crop_tab.p);
     if (h->staging_host) cudaFreeHost(h->staging_host);
     if (h->staging_dev) cudaFree(h->staging_dev);
     if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
@@ -933,6 +936,41 @@ int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents,
     KOCR_CUDA(cudaMemcpy2DAsync(logits_out, VOCAB_PAD * 4, reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
                                 (size_t)DEC_MAX * VOCAB_PAD * 4, VOCAB_PAD * 4, n_rows, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w, int channels, int page_on_device,
+                    const int32_t* boxes, int n_lines, int pad_px, uint8_t* out_pixels_dev, const int64_t* out_offsets,
+                    void* stream) {
+    KOCR_CHECK(h != nullptr && page != nullptr, "kocr_crop_lines: null argument");
+    KOCR_CHECK(n_lines >= 0 && pad_px >= 0 && page_h > 0 && page_w > 0, "kocr_crop_lines: bad sizes");
+    KOCR_CHECK(channels == 1 || channels == 3, "kocr_crop_lines: page must be L (1 channel) or RGB (3 channels)");
+    if (n_lines == 0) return 0;
+    KOCR_CHECK(boxes != nullptr && out_pixels_dev != nullptr && out_offsets != nullptr, "kocr_crop_lines: null argument");
+    for (int i = 0; i < n_lines; ++i) {
+        const int32_t* b = boxes + 4 * i;
+        KOCR_CHECK(b[0] >= 0 && b[1] >= 0 && b[2] <= page_w && b[3] <= page_h && b[2] > b[0] && b[3] > b[1],
+                   "kocr_crop_lines: box %d = (%d, %d, %d, %d) is empty or outside the %d x %d page", i, b[0], b[1], b[2], b[3],
+                   page_w, page_h);
+    }
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    const uint8_t* d_page = page;
+    if (!page_on_device) {
+        const size_t bytes = (size_t)page_h * page_w * channels;
+        KOCR_TRY(ensure(h->crop_page, bytes));
+        KOCR_CUDA(cudaMemcpyAsync(h->crop_page.p, page, bytes, cudaMemcpyHostToDevice, s));
+        d_page = reinterpret_cast<const uint8_t*>(h->crop_page.p);
+    }
+    const size_t box_bytes = (size_t)n_lines * 16, off_bytes = (size_t)n_lines * 8;
+    KOCR_TRY(ensure(h->crop_tab, box_bytes + off_bytes));
+    uint8_t* tab = reinterpret_cast<uint8_t*>(h->crop_tab.p);
+    KOCR_CUDA(cudaMemcpyAsync(tab, out_offsets, off_bytes, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaMemcpyAsync(tab + off_bytes, boxes, box_bytes, cudaMemcpyHostToDevice, s));
+    KOCR_TRY(launch_crop_lines(d_page, page_w, channels, reinterpret_cast<const int*>(tab + off_bytes),
+                               reinterpret_cast<const long long*>(tab), n_lines, pad_px, out_pixels_dev, s));
+    ++g_launches;
+    KOCR_CUDA(cudaStreamSynchronize(s));        // boxes / offsets (and a pageable page) are host memory of the caller
     return 0;
 }
 

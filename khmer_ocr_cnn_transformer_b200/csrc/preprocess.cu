@@ -148,4 +148,49 @@ int launch_preprocess(const uint8_t* d_pixels, uint8_t* d_mid, const LineDesc* d
 int preprocess_vtab_ints_per_line() { return IMG_H * (2 + KMAX); }
 int preprocess_kmax() { return KMAX; }
 
+// ------------------------------------------------------------------------------------------
+// Input side: text-line crops of a page image, the way the reference cuts them before recognition -
+// extract_textline_crops (netra_ocr/textline_detection.py:7-53: crop the expanded, clipped box, paste it on a white
+// canvas with `padding_px` on every side) and the custom-detector branch of OCREngine (ocr_engine.py:72-76: clipped
+// box, no canvas) - followed by `convert('L')` (preprocessor.py:39-41; Pillow rgb2l: (19595 R + 38470 G + 7471 B +
+// 0x8000) >> 16).  Pure byte indexing: one CTA row-strides over a line, a warp reads 96 contiguous bytes of a page
+// row.  grid = (n_lines, CROP_ROW_CTAS).
+// ------------------------------------------------------------------------------------------
+static constexpr int CROP_ROW_CTAS = 8;
+
+__global__ void __launch_bounds__(256) crop_lines_kernel(const uint8_t* __restrict__ page, int page_w, int channels,
+                                                         const int* __restrict__ boxes, const long long* __restrict__ offsets,
+                                                         int pad, uint8_t* __restrict__ out) {
+    const int line = blockIdx.x;
+    const int x0 = boxes[4 * line], y0 = boxes[4 * line + 1], x1 = boxes[4 * line + 2], y1 = boxes[4 * line + 3];
+    const int cw = x1 - x0, chh = y1 - y0, ow = cw + 2 * pad, oh = chh + 2 * pad;
+    uint8_t* dst = out + offsets[line];
+    for (int r = blockIdx.y; r < oh; r += gridDim.y) {
+        const int sy = r - pad;
+        const bool row_in = sy >= 0 && sy < chh;
+        const uint8_t* src = page + ((long)(y0 + sy) * page_w + x0) * channels;
+        for (int c = threadIdx.x; c < ow; c += blockDim.x) {
+            const int sx = c - pad;
+            uint8_t v = 255;                                    // white canvas (textline_detection.py:44)
+            if (row_in && sx >= 0 && sx < cw) {
+                if (channels == 1) {
+                    v = src[sx];
+                } else {
+                    const uint8_t* px = src + (long)sx * channels;
+                    v = (uint8_t)((19595u * px[0] + 38470u * px[1] + 7471u * px[2] + 0x8000u) >> 16);
+                }
+            }
+            dst[(long)r * ow + c] = v;
+        }
+    }
+}
+
+int launch_crop_lines(const uint8_t* d_page, int page_w, int channels, const int* d_boxes, const long long* d_offsets,
+                      int n_lines, int pad, uint8_t* d_out, cudaStream_t stream) {
+    if (n_lines == 0) return 0;
+    crop_lines_kernel<<<dim3(n_lines, CROP_ROW_CTAS), 256, 0, stream>>>(d_page, page_w, channels, d_boxes, d_offsets, pad, d_out);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace kocr

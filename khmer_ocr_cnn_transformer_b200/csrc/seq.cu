@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(256) dec_cross_attn_kernel(const float* __rest
 // (max, sum, weighted V) per head with the online-softmax rescaling, and the 8 warps are merged through shared
 // memory at the end.  No score buffer, no intermediate __syncthreads, twice the bytes in flight: this kernel is the
 // HBM-bound part of a decode position (it streams the K/V of every active line at every position).
-__global__ void __launch_bounds__(256) dec_cross_attn_flash_kernel(const float* __restrict__ q,
+__global__ void __launch_bounds__(256, 3) dec_cross_attn_flash_kernel(const float* __restrict__ q,
                                                                    const act16_t* __restrict__ kv, int layer,
                                                                    const int* __restrict__ line_tok_off,
                                                                    const int* __restrict__ line_T,

@@ -130,6 +130,34 @@ class OCRPredictor:
                 results[i] = self._beam_search_line(j, beam_width)
         return results
 
+    def predict_page(self, image, textline_pred, expansion_px: int = 5, padding_px: int = 10) -> list:
+        """Page image + detected text-line polygons -> one greedy-decoded string per line, in detection order: the
+        `extract_textline_crops` -> `recognize_batch(crops, beam_width=1)` sequence of OCREngine.process_image
+        (ocr_engine.py:54-86, textline_detection.py:7-53) with the crops cut, padded and grey-converted on the GPU."""
+        from ..textline_crops import textline_boxes, crop_lines_device
+        from PIL import Image
+        if isinstance(image, (str, Path)):
+            image = Image.open(image).convert("RGB")
+        size = image.size if hasattr(image, "size") and not isinstance(image, np.ndarray) else (image.shape[1], image.shape[0])
+        boxes = textline_boxes(size, textline_pred, expansion_px)
+        if not boxes:
+            return []
+        crops = crop_lines_device(self.model, image, boxes, padding_px)
+        shapes = list(zip(crops.batch.heights.tolist(), crops.batch.widths.tolist()))
+        from ..scheduling import plan_batches
+        from .._native import line_batch_from_shapes
+        results = [None] * len(boxes)
+        self.model.set_option("straggler_threshold", 0)
+        for idxs in plan_batches(shapes, self._max_lines, self._max_chunks, self.cfg.max_seq_len):
+            if list(idxs) != list(range(idxs[0], idxs[0] + len(idxs))):
+                raise RuntimeError("plan_batches must keep device-resident crops contiguous")
+            sub = line_batch_from_shapes([shapes[i] for i in idxs])
+            tokens, lengths = self.model.recognize_lines(sub, max_steps=self.cfg.decode_max_len,
+                                                         pixels_dev_ptr=crops.dev_ptr + int(crops.batch.offsets[idxs[0]]))
+            for j, text in zip(idxs, self._decode_ids(tokens, lengths)):
+                results[j] = text
+        return results
+
     def predict(self, image_input, beam_width: int = 3) -> str:
         gray = ImagePreprocessor.to_gray(image_input)
         if beam_width <= 1:

@@ -50,6 +50,34 @@ def rgb_to_l(rgb: np.ndarray) -> np.ndarray:
     return ((19595 * r + 38470 * g + 7471 * b + 0x8000) >> 16).astype(np.uint8)
 
 
+def textline_boxes(image_size, polygons, expansion_px=5):
+    """extract_textline_crops steps 1-2 (netra_ocr/textline_detection.py:17-34): int() of the polygon extremes,
+    expansion, clipping, empty boxes skipped."""
+    img_w, img_h = image_size
+    boxes = []
+    for poly in polygons:
+        xs = [p[0] for p in poly]
+        ys = [p[1] for p in poly]
+        x0, y0, x1, y1 = int(min(xs)), int(min(ys)), int(max(xs)), int(max(ys))
+        x0, y0 = max(0, x0 - expansion_px), max(0, y0 - expansion_px)
+        x1, y1 = min(img_w, x1 + expansion_px), min(img_h, y1 + expansion_px)
+        if x1 - x0 <= 0 or y1 - y0 <= 0:
+            continue
+        boxes.append((x0, y0, x1, y1))
+    return boxes
+
+
+def crop_line_gray(page: np.ndarray, box, padding_px=10) -> np.ndarray:
+    """extract_textline_crops steps 3-4 (textline_detection.py:36-47: crop, paste on a white RGB canvas) followed by the
+    `convert('L')` of ImagePreprocessor.process (preprocessor.py:41).  page: uint8 (H, W, 3) or (H, W)."""
+    x0, y0, x1, y1 = box
+    crop = page[y0:y1, x0:x1]
+    gray = rgb_to_l(crop) if crop.ndim == 3 else crop
+    out = np.full((gray.shape[0] + 2 * padding_px, gray.shape[1] + 2 * padding_px), 255, np.uint8)
+    out[padding_px:padding_px + gray.shape[0], padding_px:padding_px + gray.shape[1]] = gray
+    return out
+
+
 def resized_width(w: int, h: int) -> int:
     """preprocessor.py:45-47: Python float division, truncation, floor of chunk_width//2."""
     aspect = w / h

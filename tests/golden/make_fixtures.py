@@ -7,6 +7,7 @@ tests, `smoke()` or `bench.py` runs this; they read the files it wrote.
   python tests/golden/make_fixtures.py bank      # wordbank.npz      (Pillow + reference fonts)
   python tests/golden/make_fixtures.py train     # fixture_se_ckpt.npz  (reference model, CPU training)
   python tests/golden/make_fixtures.py golden    # golden_*.npz      (reference outputs = pinned oracle)
+  python tests/golden/make_fixtures.py crops     # golden_crops.npz  (Pillow crop / paste / convert('L') of a page)
 
 Why a trained checkpoint: with default random init the reference's decoder output is
 input-independent and top-1/top-2 logit gaps are ~1e-3, so token-level parity under bf16 would be
@@ -303,9 +304,64 @@ def stage_golden(args):
         print(f, f"{(HERE / f).stat().st_size/1e6:.2f} MB")
 
 
+def stage_crops(args):
+    """Input-side goldens.  netra_ocr/textline_detection.py imports surya (absent here), so the ten lines of
+    `extract_textline_crops` (:17-47) are restated with the SAME Pillow calls - Image.crop, Image.new("RGB", ..., white),
+    paste - followed by the `convert('L')` of preprocessor.py:41; the custom-detector branch (ocr_engine.py:72-76) is
+    the same crop without the canvas.  The pixels are Pillow's, the box arithmetic is the reference's."""
+    from PIL import Image
+    rng = np.random.Generator(np.random.PCG64(77))
+    bank = synth.WordBank()
+    page = np.full((420, 900, 3), 255, np.uint8)
+    polys, y = [], 12
+    for k in range(7):                                    # a synthetic page: coloured text lines on a tinted background
+        im, _ = synth.compose_line(bank, rng, int(rng.integers(200, 800)))
+        h, w = im.shape
+        x = int(rng.integers(0, 40))
+        w = min(w, 900 - x)
+        tint = rng.integers(0, 80, 3)
+        for c in range(3):
+            page[y:y + h, x:x + w, c] = np.clip(im[:, :w].astype(np.int32) + tint[c] * (im[:, :w] < 128), 0, 255)
+        polys.append([[x + 0.6, y + 0.4], [x + w - 0.3, y + 0.9], [x + w - 0.7, y + h - 0.2], [x + 0.2, y + h - 0.8]])
+        y += h + int(rng.integers(0, 9))
+    polys.append([[880.5, 400.2], [905.0, 400.0], [905.0, 430.0], [880.0, 430.0]])     # hangs over the page edge
+    polys.append([[-4.0, -3.0], [30.0, -3.0], [30.0, 8.0], [-4.0, 8.0]])               # negative coordinates
+    polys.append([[950.0, 10.0], [960.0, 10.0], [960.0, 20.0], [950.0, 20.0]])         # outside: skipped
+    page += (rng.integers(0, 3, page.shape)).astype(np.uint8) * (page < 250)           # a little noise
+    pil = Image.fromarray(page)
+    out = {"page": page, "polys": np.asarray(polys, np.float64)}
+    for tag, (expansion, padding) in {"a": (5, 10), "b": (2, 0), "c": (0, 3)}.items():
+        img_w, img_h = pil.size
+        n = 0
+        for poly in polys:
+            xs = [p[0] for p in poly]; ys = [p[1] for p in poly]
+            x0, y0 = int(min(xs)), int(min(ys)); x1, y1 = int(max(xs)), int(max(ys))
+            x0 = max(0, x0 - expansion); y0 = max(0, y0 - expansion)
+            x1 = min(img_w, x1 + expansion); y1 = min(img_h, y1 + expansion)
+            if x1 - x0 <= 0 or y1 - y0 <= 0:
+                continue
+            crop = pil.crop((x0, y0, x1, y1))
+            if padding > 0:
+                padded = Image.new("RGB", (crop.width + 2 * padding, crop.height + 2 * padding), (255, 255, 255))
+                padded.paste(crop, (padding, padding))
+                crop = padded
+            out[f"{tag}_crop{n}"] = np.asarray(crop.convert("L"))
+            out[f"{tag}_box{n}"] = np.asarray([x0, y0, x1, y1], np.int32)
+            n += 1
+        out[f"{tag}_n"] = np.asarray(n)
+        out[f"{tag}_params"] = np.asarray([expansion, padding])
+    # grey page variant (mode L in, L out)
+    gl = pil.convert("L")
+    out["page_l"] = np.asarray(gl)
+    crop = gl.crop((10, 5, 300, 60))
+    out["l_crop"] = np.asarray(crop)
+    np.savez_compressed(HERE / "golden_crops.npz", **out)
+    print("golden_crops.npz", f"{(HERE / 'golden_crops.npz').stat().st_size/1e6:.2f} MB", {k: int(out[k]) for k in out if k.endswith("_n")})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("stage", choices=["bank", "train", "golden"])
+    ap.add_argument("stage", choices=["bank", "train", "golden", "crops"])
     ap.add_argument("--words-per-group", type=int, default=36)
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--batch", type=int, default=8)
@@ -313,4 +369,4 @@ if __name__ == "__main__":
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--threads", type=int, default=6)
     a = ap.parse_args()
-    {"bank": stage_bank, "train": stage_train, "golden": stage_golden}[a.stage](a)
+    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops}[a.stage](a)

@@ -133,3 +133,19 @@ def test_oracle_against_live_reference_random_weights():
     mem2 = O.memory_for_line(sd, enc, "se")
     assert rel_err(mem2, mem[0].numpy()) < 1e-5
     assert max_err(O.decoder_forward(sd, toks, mem2), lg[0].numpy()) < 1e-4
+
+
+def test_textline_crops_against_pillow_outputs():
+    """oracle.textline_boxes / crop_line_gray == the Pillow calls of extract_textline_crops (textline_detection.py:17-47)
+    + convert('L') (preprocessor.py:41), bit for bit, incl. clipping at the page edges and skipped boxes."""
+    z = _need("golden_crops.npz")
+    page, polys = z["page"], z["polys"].tolist()
+    for tag in "abc":
+        expansion, padding = [int(v) for v in z[f"{tag}_params"]]
+        boxes = O.textline_boxes((page.shape[1], page.shape[0]), polys, expansion)
+        assert len(boxes) == int(z[f"{tag}_n"]) == 9                   # 10 polygons, one entirely outside the page
+        for i, b in enumerate(boxes):
+            assert list(b) == [int(v) for v in z[f"{tag}_box{i}"]]
+            assert np.array_equal(O.crop_line_gray(page, b, padding), z[f"{tag}_crop{i}"]), (tag, i)
+    assert np.array_equal(O.rgb_to_l(page), z["page_l"])
+    assert np.array_equal(O.crop_line_gray(z["page_l"], (10, 5, 300, 60), 0), z["l_crop"])
