@@ -95,6 +95,10 @@ int kocr_set_option(kocr_handle* h, const char* name, int value);
  * top-k, stable sort, pruning, length normalisation) stays on the host, identical to the reference's Python. */
 int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
                    float* logits_out, void* stream);
+/* The same for the hypotheses of MANY lines in one pass (what predict_batch(beam_width > 1) uses): row r belongs to line
+ * row_line[r] of the current batch; n_rows <= max_lines of the handle; parents index the rows of the previous call. */
+int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, const int32_t* parents,
+                         const int32_t* prefixes, int t, float* logits_out, void* stream);
 
 /* Input side - extract_textline_crops (netra_ocr/textline_detection.py:7-53) and the custom-detector crop of
  * OCREngine (netra_ocr/ocr_engine.py:72-76), followed by the `convert('L')` of ImagePreprocessor.process

@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_crop_lines",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines",
 ]
 
 _lib = None
@@ -56,6 +56,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_debug_read.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
     lib.kocr_beam_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp]
     lib.kocr_beam_step.restype = i32
+    lib.kocr_beam_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
+    lib.kocr_beam_step_batch.restype = i32
     lib.kocr_crop_lines.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.kocr_crop_lines.restype = i32
     lib.kocr_read_unfinished.argtypes = [vp, vp]
@@ -210,6 +212,18 @@ class Recognizer:
         par = np.ascontiguousarray(parents if parents is not None else np.zeros(n_rows), np.int32)
         logits = np.zeros((n_rows, 128), np.float32)
         check(self.lib.kocr_beam_step(self._h, line, n_rows, _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
+        return logits[:, :124]
+
+    def beam_step_batch(self, row_line, prefixes: np.ndarray, parents, t: int) -> np.ndarray:
+        """One decoder position for hypotheses of many lines: row r continues hypothesis `parents[r]` (row of the previous
+        call) of line `row_line[r]`; prefixes [n_rows, t+1]; returns logits [n_rows, 124]."""
+        prefixes = np.ascontiguousarray(prefixes, np.int32)
+        n_rows = prefixes.shape[0]
+        assert prefixes.shape[1] == t + 1
+        rl = np.ascontiguousarray(row_line, np.int32)
+        par = np.ascontiguousarray(parents if parents is not None else np.zeros(n_rows), np.int32)
+        logits = np.zeros((n_rows, 128), np.float32)
+        check(self.lib.kocr_beam_step_batch(self._h, n_rows, _ptr(rl), _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
         return logits[:, :124]
 
     def crop_lines(self, page, boxes, pad_px: int, out_dev_ptr: int, out_offsets, page_dev_ptr=None, stream=None):

@@ -107,7 +107,7 @@ struct kocr_handle {
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
     Buf crop_page, crop_tab;      // kocr_crop_lines: device copy of a host page, boxes + offsets
-    Buf beam_cache;              // [2 ping-pong][K,V][2 layers][BEAM_MAX][DEC_MAX][384] fp32, allocated on first use
+    Buf beam_cache;              // [2 ping-pong][K,V][2 layers][max_lines][DEC_MAX][384] fp32, allocated on first use
     int beam_cur = 0;
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
@@ -466,7 +466,7 @@ int gemm_dec(kocr_handle* h, const float* a, int L, const float* w, int N, int K
 // small self-attention cache.
 struct DecRows {
     int n_rows;
-    float *kcache, *vcache;          // [2 layers][BEAM_MAX][DEC_MAX][384]
+    float *kcache, *vcache;          // [2 layers][max_lines][DEC_MAX][384]
     size_t layer_stride;
     const int *tok_off, *T;          // device arrays [n_rows]
 };
@@ -880,41 +880,45 @@ __global__ void beam_reorder_kernel(const float* __restrict__ src, float* __rest
 }
 }  // namespace
 
-int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
-                   float* logits_out, void* stream) {
-    KOCR_CHECK(h != nullptr && prefixes != nullptr && logits_out != nullptr, "kocr_beam_step: null argument");
-    KOCR_CHECK(line >= 0 && line < h->n_lines, "kocr_beam_step: line %d outside the current batch of %d", line, h->n_lines);
-    KOCR_CHECK(n_rows >= 1 && n_rows <= kocr_handle::BEAM_MAX, "kocr_beam_step: %d hypotheses (max %d)", n_rows, kocr_handle::BEAM_MAX);
-    KOCR_CHECK(t >= 0 && t < h->dec_max_len, "kocr_beam_step: position %d out of range", t);
-    KOCR_CHECK(t == 0 || parents != nullptr, "kocr_beam_step: parents required for t > 0");
+int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, const int32_t* parents,
+                         const int32_t* prefixes, int t, float* logits_out, void* stream) {
+    KOCR_CHECK(h != nullptr && prefixes != nullptr && logits_out != nullptr && row_line != nullptr, "kocr_beam_step_batch: null argument");
+    const int R = h->max_lines;                          // every decode buffer of the handle has max_lines rows
+    KOCR_CHECK(n_rows >= 1 && n_rows <= R, "kocr_beam_step_batch: %d hypotheses (handle capacity %d rows)", n_rows, R);
+    KOCR_CHECK(t >= 0 && t < h->dec_max_len, "kocr_beam_step_batch: position %d out of range", t);
+    KOCR_CHECK(t == 0 || parents != nullptr, "kocr_beam_step_batch: parents required for t > 0");
     KOCR_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
-    const size_t row = (size_t)DEC_MAX * D_MODEL, layer_stride = kocr_handle::BEAM_MAX * row, kv_stride = 2 * layer_stride,
+    const size_t row = (size_t)DEC_MAX * D_MODEL, layer_stride = (size_t)R * row, kv_stride = 2 * layer_stride,
                  buf_stride = 2 * kv_stride;
     KOCR_TRY(ensure(h->beam_cache, 2 * buf_stride * sizeof(float)));
     KOCR_TRY(ensure(h->trace, (size_t)h->max_lines * DEC_MAX * VOCAB_PAD * 4));
     float* base = reinterpret_cast<float*>(h->beam_cache.p);
     int* tokens = buf<int>(h, "tokens");
-    int* scratch = buf<int>(h, "forced");             // [0, 8): parents, [8, 16): tok_off, [16, 24): T
-    int32_t host_tab[24];
-    for (int r = 0; r < kocr_handle::BEAM_MAX; ++r) {
-        host_tab[r] = (t > 0 && r < n_rows) ? parents[r] : 0;
-        KOCR_CHECK(host_tab[r] >= 0 && host_tab[r] < kocr_handle::BEAM_MAX, "kocr_beam_step: bad parent index");
-        host_tab[8 + r] = h->line_first_chunk[line] * TOK_PER_CHUNK;
-        host_tab[16 + r] = h->line_T[line];
+    int* scratch = buf<int>(h, "forced");             // [0, R): parents, [R, 2R): tok_off, [2R, 3R): T  (buffer: R x 257 ints)
+    std::vector<int32_t> tab((size_t)3 * R, 0);
+    int max_T = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const int line = row_line[r];
+        KOCR_CHECK(line >= 0 && line < h->n_lines, "kocr_beam_step_batch: row %d refers to line %d outside the current batch of %d", r, line, h->n_lines);
+        tab[r] = t > 0 ? parents[r] : 0;
+        KOCR_CHECK(tab[r] >= 0 && tab[r] < R, "kocr_beam_step_batch: bad parent index %d", tab[r]);
+        tab[(size_t)R + r] = h->line_first_chunk[line] * TOK_PER_CHUNK;
+        tab[(size_t)2 * R + r] = h->line_T[line];
+        max_T = std::max(max_T, h->line_T[line]);
     }
-    KOCR_CUDA(cudaMemcpyAsync(scratch, host_tab, sizeof host_tab, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaMemcpyAsync(scratch, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
     // token prefixes of all hypotheses (positions 0..t): row r of `prefixes` is [t + 1] ints
     KOCR_CUDA(cudaMemcpy2DAsync(tokens, KOCR_TOKENS_LD * 4, prefixes, (size_t)(t + 1) * 4, (size_t)(t + 1) * 4, n_rows,
                                 cudaMemcpyHostToDevice, s));
-    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "finished"), 0, (size_t)kocr_handle::BEAM_MAX * 4, s));
+    KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "finished"), 0, (size_t)R * 4, s));
     const int32_t step = t;
     KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "step_base"), &step, 4, cudaMemcpyHostToDevice, s));
     if (t == 0) h->beam_cur = 0;
     if (t > 0) {
         const int nxt = h->beam_cur ^ 1;
         beam_reorder_kernel<<<dim3(n_rows, 2, 2), 256, 0, s>>>(base + h->beam_cur * buf_stride, base + nxt * buf_stride, scratch,
-                                                              n_rows, t, row * kocr_handle::BEAM_MAX, kv_stride);
+                                                              n_rows, t, layer_stride, kv_stride);
         KOCR_CUDA(cudaGetLastError());
         ++g_launches;
         h->beam_cur = nxt;
@@ -924,19 +928,27 @@ int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents,
     rows.kcache = base + h->beam_cur * buf_stride;
     rows.vcache = rows.kcache + kv_stride;
     rows.layer_stride = layer_stride;
-    rows.tok_off = scratch + 8;
-    rows.T = scratch + 16;
-    const int max_T = (h->line_T[line] + 127) / 128 * 128;
+    rows.tok_off = scratch + R;
+    rows.T = scratch + 2 * R;
     const int saved_force = h->force_tokens;
     h->force_tokens = 0;
-    int rc = decode_step(h, 0, max_T, s, &rows);
+    int rc = decode_step(h, 0, (max_T + 127) / 128 * 128, s, &rows);
     h->force_tokens = saved_force;
     if (rc) return rc;
     // the argmax kernel wrote the (bias-added, slice-summed) logits of position t into the trace rows
     KOCR_CUDA(cudaMemcpy2DAsync(logits_out, VOCAB_PAD * 4, reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
                                 (size_t)DEC_MAX * VOCAB_PAD * 4, VOCAB_PAD * 4, n_rows, cudaMemcpyDeviceToHost, s));
-    KOCR_CUDA(cudaStreamSynchronize(s));
+    KOCR_CUDA(cudaStreamSynchronize(s));     // tab / prefixes are host memory of this call
     return 0;
+}
+
+int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents, const int32_t* prefixes, int t,
+                   float* logits_out, void* stream) {
+    KOCR_CHECK(h != nullptr, "kocr_beam_step: null handle");
+    KOCR_CHECK(n_rows >= 1 && n_rows <= kocr_handle::BEAM_MAX, "kocr_beam_step: %d hypotheses (max %d)", n_rows, kocr_handle::BEAM_MAX);
+    int32_t lines[kocr_handle::BEAM_MAX];
+    for (int r = 0; r < n_rows; ++r) lines[r] = line;
+    return kocr_beam_step_batch(h, n_rows, lines, parents, prefixes, t, logits_out, stream);
 }
 
 int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w, int channels, int page_on_device,

@@ -82,52 +82,77 @@ class OCRPredictor:
         return results
 
     # ------------------------------------------------------------------------------------
-    def _beam_search_line(self, line: int, beam_width: int) -> str:
-        """`OCRPredictor._beam_search` (reference predictor.py:101-136) for line `line` of the batch whose stages 1-5a
-        have just run: same candidate generation, stable sort, pruning and length normalisation; the decoder
-        positions run on the GPU (kocr_beam_step), one call per position."""
+    def _beam_search_batch(self, n_lines: int, beam_width: int) -> list:
+        """`OCRPredictor._beam_search` (reference predictor.py:101-136) for every line of the batch whose stages 1-5a
+        have just run.  Per line exactly the reference's bookkeeping - log-softmax of the last position, top
+        `beam_width` tokens of every live hypothesis, stable sort by score, candidates ending in <eos> moved to
+        `completed` with score / len(seq), the first `beam_width` others survive, best completed (else first live)
+        hypothesis wins - while each decoder position of ALL lines' hypotheses is one GPU pass (kocr_beam_step_batch,
+        KV-cached: the reference re-runs the whole prefix)."""
         import torch
         import torch.nn.functional as F
         sos, eos = self.tokenizer.sos_idx, self.tokenizer.eos_idx
-        beams = [(0.0, [sos])]
-        completed = []
-        parents = None
+        beams = [[(0.0, [sos])] for _ in range(n_lines)]
+        completed = [[] for _ in range(n_lines)]
+        prev_rows = [[0] for _ in range(n_lines)]        # row (of the previous pass) holding each live hypothesis' cache
+        first = True
         for t in range(self.cfg.decode_max_len):
-            k_curr = len(beams)
-            prefixes = np.asarray([b[1] for b in beams], np.int32)
-            logits = self.model.beam_step(line, prefixes, parents, t)
-            log_probs = F.log_softmax(torch.from_numpy(logits.copy()), dim=-1)
-            candidates = []
-            for i in range(k_curr):
-                score, seq = beams[i]
-                top_probs, top_idxs = log_probs[i].topk(beam_width)
-                for k in range(beam_width):
-                    candidates.append((score + top_probs[k].item(), seq + [top_idxs[k].item()], i))
-            candidates.sort(key=lambda x: x[0], reverse=True)
-            next_beams, next_parents = [], []
-            for s, seq, parent in candidates:
-                if seq[-1] == eos:
-                    completed.append((s / len(seq), seq))
-                elif len(next_beams) < beam_width:
-                    next_beams.append((s, seq))
-                    next_parents.append(parent)
-            beams, parents = next_beams, next_parents
-            if not beams:
+            live = [l for l in range(n_lines) if beams[l]]
+            if not live:
                 break
-        best_seq = sorted(completed, key=lambda x: x[0], reverse=True)[0][1] if completed else beams[0][1]
-        return self.tokenizer.decode(best_seq)
+            row_line, prefixes, parents, start = [], [], [], {}
+            for l in live:
+                start[l] = len(row_line)
+                for (_, seq), pr in zip(beams[l], prev_rows[l]):
+                    row_line.append(l)
+                    prefixes.append(seq)
+                    parents.append(pr)
+            logits = self.model.beam_step_batch(row_line, np.asarray(prefixes, np.int32), None if first else parents, t)
+            first = False
+            log_probs = F.log_softmax(torch.from_numpy(logits.copy()), dim=-1)
+            # `log_probs[i].topk(beam_width)` + `.item()` of the reference (:119-122), for all rows at once: the same fp32
+            # values widened to Python floats, without ~10^5 scalar tensor reads per batch
+            top_probs, top_idxs = log_probs.topk(beam_width, dim=-1)
+            top_probs, top_idxs = top_probs.tolist(), top_idxs.tolist()
+            for l in live:
+                candidates = []
+                for i, (score, seq) in enumerate(beams[l]):
+                    row = start[l] + i
+                    for k in range(beam_width):
+                        candidates.append((score + top_probs[row][k], seq + [top_idxs[row][k]], row))
+                candidates.sort(key=lambda x: x[0], reverse=True)
+                nxt, rows = [], []
+                for sc, seq, row in candidates:
+                    if seq[-1] == eos:
+                        completed[l].append((sc / len(seq), seq))
+                    elif len(nxt) < beam_width:
+                        nxt.append((sc, seq))
+                        rows.append(row)
+                # `beams = next_beams; if not beams: break` (predictor.py:131-132): an empty list ends this line; it can only
+                # be empty if every candidate ended in <eos>, so `completed` is non-empty then
+                beams[l], prev_rows[l] = nxt, rows
+        out = []
+        for l in range(n_lines):
+            if completed[l]:
+                best = sorted(completed[l], key=lambda x: x[0], reverse=True)[0][1]
+            else:
+                best = beams[l][0][1]
+            out.append(self.tokenizer.decode(best))
+        return out
 
     def _beam_gray(self, grays, beam_width: int):
         if beam_width > 8:
             raise ValueError("beam_width > 8 is not supported by the CUDA path")
         results = [None] * len(grays)
         from ..scheduling import plan_batches
-        for idxs in plan_batches([g.shape for g in grays], self._max_lines, self._max_chunks, self.cfg.max_seq_len):
+        # every hypothesis is a row of the decode workspace: at most max_lines // beam_width lines per pass
+        lines_per_pass = max(1, self._max_lines // max(beam_width, 1))
+        for idxs in plan_batches([g.shape for g in grays], lines_per_pass, self._max_chunks, self.cfg.max_seq_len):
             self.model.gather_chunks(LineBatch([grays[i] for i in idxs]))
             self.model.sevgg_encoder_forward()
             self.model.merge_bilstm_forward()
-            for j, i in enumerate(idxs):
-                results[i] = self._beam_search_line(j, beam_width)
+            for i, text in zip(idxs, self._beam_search_batch(len(idxs), beam_width)):
+                results[i] = text
         return results
 
     def predict_page(self, image, textline_pred, expansion_px: int = 5, padding_px: int = 10) -> list:
