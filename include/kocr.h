@@ -100,6 +100,17 @@ int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents,
 int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, const int32_t* parents,
                          const int32_t* prefixes, int t, float* logits_out, void* stream);
 
+/* Teacher-forced batched forward - KhmerOCR.forward (recognition/model/se_model.py:240-289; vgg_model.py:214-246), the
+ * training-time / evaluation-loop semantics: after kocr_gather_chunks + kocr_sevgg_encoder_forward on a batch of B
+ * lines, every merged sequence is padded to Tmax = max T_i, global_pos is added to the pad rows too, the BiLSTM runs
+ * over all Tmax rows of every line WITHOUT packing (the backward direction reads the pad rows first), the cross-
+ * attention is masked to the real length (memory_key_padding_mask) and the self-attention is causal with <pad> keys
+ * masked.  tgt_tokens = host int32 [B][L] (row = <sos> + target, right-padded with <pad> = 0), 1 <= L <= 256;
+ * logits_out = host fp32 [B][L][128] (first 124 valid): row t = distribution of token t + 1 given tokens 0..t.
+ * Needs B * Tmax <= 32 * max_chunks.  Leaves the handle's memory in the padded layout (kocr_decode_greedy then decodes
+ * with the training-time memory); the next kocr_gather_chunks resets it. */
+int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L, float* logits_out, void* stream);
+
 /* Input side - extract_textline_crops (netra_ocr/textline_detection.py:7-53) and the custom-detector crop of
  * OCREngine (netra_ocr/ocr_engine.py:72-76), followed by the `convert('L')` of ImagePreprocessor.process
  * (recognition/preprocessor.py:39-41).  page = uint8 [page_h][page_w][channels] (3 = RGB, 1 = L), host or device.

@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines", "kocr_forward_teacher_forced",
 ]
 
 _lib = None
@@ -60,6 +60,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_beam_step_batch.restype = i32
     lib.kocr_crop_lines.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.kocr_crop_lines.restype = i32
+    lib.kocr_forward_teacher_forced.argtypes = [vp, vp, i32, vp, vp]
+    lib.kocr_forward_teacher_forced.restype = i32
     lib.kocr_read_unfinished.argtypes = [vp, vp]
     lib.kocr_read_unfinished.restype = i32
     lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
@@ -213,6 +215,15 @@ class Recognizer:
         logits = np.zeros((n_rows, 128), np.float32)
         check(self.lib.kocr_beam_step(self._h, line, n_rows, _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
         return logits[:, :124]
+
+    def forward_teacher_forced(self, tgt_tokens: np.ndarray) -> np.ndarray:
+        """KhmerOCR.forward semantics on the batch whose stages 1-4 have just run: tgt_tokens int [B, L] -> logits
+        fp32 [B, L, 124] (padded memory, un-packed BiLSTM, memory_key_padding_mask)."""
+        tgt = np.ascontiguousarray(tgt_tokens, np.int32)
+        B, L = tgt.shape
+        out = np.zeros((B, L, 128), np.float32)
+        check(self.lib.kocr_forward_teacher_forced(self._h, _ptr(tgt), L, _ptr(out), None))
+        return out[:, :, :124]
 
     def beam_step_batch(self, row_line, prefixes: np.ndarray, parents, t: int) -> np.ndarray:
         """One decoder position for hypotheses of many lines: row r continues hypothesis `parents[r]` (row of the previous

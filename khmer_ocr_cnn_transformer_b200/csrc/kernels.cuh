@@ -72,6 +72,9 @@ int launch_layernorm(const float* x, const float* g, const float* b, const float
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
                    act16_t* out_a16_lo, int rows, cudaStream_t stream);
 
+// padded memory of the teacher-forced batched forward: out[b*Tmax + t] = t < T_b ? xb[src_off_b + t] : a16(global_pos[t])
+int launch_pad_memory(const act16_t* xb, const float* global_pos, const int* src_off, const int* line_T, int n_lines,
+                      int Tmax, act16_t* out, cudaStream_t stream);
 // BiLSTM recurrence (input projection already in gin): persistent 2-CTA cluster kernel.
 struct LstmGroup { int line[8]; };   // lines handled together by one cluster (-1 = unused)
 int launch_bilstm(const float* gin /*[Mtok,1536]*/, const act16_t* whh_packed, const int* line_tok_off,

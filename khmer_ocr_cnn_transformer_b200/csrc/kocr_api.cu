@@ -106,6 +106,7 @@ struct kocr_handle {
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
+    Buf tf_x, tf_tab;             // kocr_forward_teacher_forced: padded memory operand, per-line tables
     Buf crop_page, crop_tab;      // kocr_crop_lines: device copy of a host page, boxes + offsets
     Buf beam_cache;              // [2 ping-pong][K,V][2 layers][max_lines][DEC_MAX][384] fp32, allocated on first use
     int beam_cur = 0;
@@ -636,6 +637,8 @@ int kocr_destroy(kocr_handle* h) {
     if (h->trace.p) cudaFree(h->trace.p);
     if (h->beam_cache.p) cudaFree(h->beam_cache.p);
     if (h->crop_page.p) cudaFree(h->crop_page.p);
+    if (h->tf_x.p) cudaFree(h->tf_x.p);
+    if (h->tf_tab.p) cudaFree(h->tf_tab.p);
     if (h->crop_tab.p) cudaFree(h->crop_tab.p);
     if (h->staging_host) cudaFreeHost(h->staging_host);
     if (h->staging_dev) cudaFree(h->staging_dev);
@@ -949,6 +952,66 @@ int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents,
     int32_t lines[kocr_handle::BEAM_MAX];
     for (int r = 0; r < n_rows; ++r) lines[r] = line;
     return kocr_beam_step_batch(h, n_rows, lines, parents, prefixes, t, logits_out, stream);
+}
+
+// ---- teacher-forced batched forward (KhmerOCR.forward, se_model.py:240-289) -----------------------------------
+int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L, float* logits_out, void* stream) {
+    KOCR_CHECK(h != nullptr && tgt_tokens != nullptr && logits_out != nullptr, "kocr_forward_teacher_forced: null argument");
+    const int B = h->n_lines, Tmax = h->max_T;
+    KOCR_CHECK(B > 0 && h->n_tok > 0, "kocr_forward_teacher_forced: run kocr_gather_chunks + kocr_sevgg_encoder_forward on a batch first");
+    KOCR_CHECK(L >= 1 && L <= h->dec_max_len, "kocr_forward_teacher_forced: target length %d outside [1, %d]", L, h->dec_max_len);
+    const long rows = (long)B * Tmax;
+    KOCR_CHECK(rows <= (long)h->max_chunks * TOK_PER_CHUNK, "kocr_forward_teacher_forced: %d lines padded to %d tokens exceed the "
+               "handle's %ld memory rows (create it with a larger max_chunks)", B, Tmax, (long)h->max_chunks * TOK_PER_CHUNK);
+    for (int b = 0; b < B; ++b)
+        KOCR_CHECK(tgt_tokens[(size_t)b * L] == 2, "kocr_forward_teacher_forced: target %d does not start with <sos>", b);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    // tables: padded token offsets (b * Tmax) and the full length Tmax of every line for the BiLSTM
+    std::vector<int32_t> tab((size_t)2 * B);
+    for (int b = 0; b < B; ++b) { tab[b] = b * Tmax; tab[(size_t)B + b] = Tmax; }
+    KOCR_TRY(ensure(h->tf_tab, tab.size() * 4));
+    KOCR_TRY(ensure(h->tf_x, (size_t)rows * D_MODEL * 2));
+    int* d_off_pad = reinterpret_cast<int*>(h->tf_tab.p);
+    int* d_T_full = d_off_pad + B;
+    KOCR_CUDA(cudaMemcpyAsync(d_off_pad, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
+    act16_t* xpad = reinterpret_cast<act16_t*>(h->tf_x.p);
+    KOCR_TRY(launch_pad_memory(buf<act16_t>(h, "xb"), h->global_pos, h->d_line_tok_off, h->d_line_T, B, Tmax, xpad, s)); ++g_launches;
+    const act16_t* memb = xpad;                       // VGG baseline: the padded merged sequence is the memory
+    if (h->variant == 0) {
+        GemmEpilogue e = ep_none();
+        e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
+        KOCR_TRY(gemm_linear(h, xpad, rows, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
+        // no packing (se_model.py:278-279): both directions run over all Tmax rows, the backward one reads the pads first
+        KOCR_TRY(launch_bilstm_mma(buf<float>(h, "gin"), h->lstm_w_hh_mma, d_off_pad, d_T_full, h->d_groups16, h->n_groups16,
+                                   buf<float>(h, "mem"), buf<act16_t>(h, "memb"), nullptr, s));
+        ++g_launches;
+        memb = buf<act16_t>(h, "memb");
+    }
+    {
+        GemmEpilogue e = ep_none();
+        e.bias = h->dec_kv_b; e.out_a16 = buf<act16_t>(h, "kv"); e.ld_a16 = 4 * D_MODEL;
+        KOCR_TRY(gemm_linear(h, memb, rows, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
+    }
+    // from here on the handle's memory lives in the padded layout: point the decoder at it (the real lengths in d_line_T
+    // are the memory_key_padding_mask, se_model.py:282-285); the next kocr_gather_chunks rewrites these tables
+    KOCR_CUDA(cudaMemcpyAsync(h->d_line_tok_off, d_off_pad, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    for (int b = 0; b < B; ++b) h->line_first_chunk[b] = b * Tmax / TOK_PER_CHUNK;
+    std::vector<int32_t> forced((size_t)B * KOCR_TOKENS_LD, 0);
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < L; ++t) forced[(size_t)b * KOCR_TOKENS_LD + t] = tgt_tokens[(size_t)b * L + t];
+    KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "forced"), forced.data(), forced.size() * 4, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaStreamSynchronize(s));              // `tab` / `forced` are host vectors of this call
+    const int sv_force = h->force_tokens, sv_trace = h->trace_logits, sv_thr = h->straggler_threshold;
+    const bool sv_have = h->have_forced;
+    h->force_tokens = 1; h->trace_logits = 1; h->have_forced = true; h->straggler_threshold = 0;
+    const int rc = kocr_decode_greedy(h, L, nullptr, nullptr, stream);
+    h->force_tokens = sv_force; h->trace_logits = sv_trace; h->have_forced = sv_have; h->straggler_threshold = sv_thr;
+    if (rc) return rc;
+    KOCR_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)L * VOCAB_PAD * 4, h->trace.p, (size_t)DEC_MAX * VOCAB_PAD * 4,
+                                (size_t)L * VOCAB_PAD * 4, B, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 
 int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w, int channels, int page_on_device,

@@ -330,6 +330,37 @@ int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* 
     return 0;
 }
 
+// Training-time memory layout of KhmerOCR.forward (se_model.py:262-273): every line padded to Tmax rows; real rows are
+// the merged encoder output + global_pos (already in `xb`), pad rows are 0 + global_pos[t].  One thread per 8 channels.
+__global__ void __launch_bounds__(256) pad_memory_kernel(const act16_t* __restrict__ xb, const float* __restrict__ global_pos,
+                                                         const int* __restrict__ src_off, const int* __restrict__ line_T,
+                                                         int Tmax, long total, act16_t* __restrict__ out) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    constexpr int CG = D_MODEL / 8;
+    const int cg = (int)(idx % CG);
+    const long row = idx / CG;
+    const int b = (int)(row / Tmax), t = (int)(row - (long)b * Tmax);
+    uint4 v;
+    if (t < line_T[b]) {
+        v = reinterpret_cast<const uint4*>(xb + ((long)src_off[b] + t) * D_MODEL)[cg];
+    } else {
+        const float4 p0 = reinterpret_cast<const float4*>(global_pos + (long)t * D_MODEL)[2 * cg];
+        const float4 p1 = reinterpret_cast<const float4*>(global_pos + (long)t * D_MODEL)[2 * cg + 1];
+        v = make_uint4(pack_a16(p0.x, p0.y), pack_a16(p0.z, p0.w), pack_a16(p1.x, p1.y), pack_a16(p1.z, p1.w));
+    }
+    reinterpret_cast<uint4*>(out)[idx] = v;
+}
+
+int launch_pad_memory(const act16_t* xb, const float* global_pos, const int* src_off, const int* line_T, int n_lines,
+                      int Tmax, act16_t* out, cudaStream_t stream) {
+    const long total = (long)n_lines * Tmax * (D_MODEL / 8);
+    if (total == 0) return 0;
+    pad_memory_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(xb, global_pos, src_off, line_T, Tmax, total, out);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // BiLSTM recurrence.  Cluster of 2 CTAs per (group of <= 8 lines, direction); CTA `rank` owns hidden
 // units [rank*96, rank*96+96) i.e. 384 gate rows (i,f,g,o x 96), whose recurrent weights stay in

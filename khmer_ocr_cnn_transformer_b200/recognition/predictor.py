@@ -155,6 +155,21 @@ class OCRPredictor:
                 results[i] = text
         return results
 
+    def forward_logits(self, image_list: list, tgt_tokens) -> np.ndarray:
+        """Teacher-forced batched forward with the reference's TRAINING-time semantics - `KhmerOCR.forward(chunk_lists,
+        tgt_tokens)` (model/se_model.py:240-289), as used by its CER evaluation loop (notebook cell 19): memory padded to
+        the longest line of the batch, BiLSTM over the pads (no packing), memory_key_padding_mask, <pad> target keys
+        masked.  image_list: paths / PIL images / grey arrays (the reference builds `chunk_lists` from the same
+        ImagePreprocessor); tgt_tokens: int (B, L), rows = <sos> + target right-padded with <pad>.  Returns fp32
+        logits (B, L, vocab).  The whole list is one device batch (B <= max_lines, B * Tmax <= 32 * max_chunks)."""
+        grays = [ImagePreprocessor.to_gray(im) for im in image_list]
+        tgt = np.asarray(tgt_tokens)
+        if tgt.ndim != 2 or tgt.shape[0] != len(grays):
+            raise ValueError("tgt_tokens must have shape (len(image_list), L)")
+        self.model.gather_chunks(LineBatch(grays))
+        self.model.sevgg_encoder_forward()
+        return self.model.forward_teacher_forced(tgt)
+
     def predict_page(self, image, textline_pred, expansion_px: int = 5, padding_px: int = 10) -> list:
         """Page image + detected text-line polygons -> one greedy-decoded string per line, in detection order: the
         `extract_textline_crops` -> `recognize_batch(crops, beam_width=1)` sequence of OCREngine.process_image

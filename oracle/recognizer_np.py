@@ -428,6 +428,47 @@ def decoder_forward(sd, tokens, memory):
     return linear(x, sd["dec.out_proj.weight"], sd["dec.out_proj.bias"])
 
 
+def forward_teacher_forced(sd, enc_lines, tgt_tokens, variant="se"):
+    """KhmerOCR.forward (se_model.py:240-289; vgg_model.py:214-246 without the BiLSTM) AFTER the per-chunk encoder:
+    enc_lines = list of (n_i, 32, D) encoder outputs, tgt_tokens = int array (B, L).  Training-time semantics:
+    merged sequences zero-padded to Tmax (pad_sequence :262), global_pos added to EVERY row incl. the pads (:265-273),
+    BiLSTM over all Tmax positions of every line (:278-279: no packing, so the backward direction reads the pad rows
+    first), memory_key_padding_mask = positions >= T_i (:282-285), decoder with causal + <pad>-key masks.
+    Returns logits (B, L, V)."""
+    B = len(enc_lines)
+    D = enc_lines[0].shape[-1]
+    merged = [e.reshape(-1, D) for e in enc_lines]
+    T = [m.shape[0] for m in merged]
+    limit = min(max(T), sd["global_pos"].shape[0])
+    out = []
+    for b in range(B):
+        mem = np.zeros((limit, D), F32)
+        tb = min(T[b], limit)
+        mem[:tb] = merged[b][:tb]
+        mem = (mem + sd["global_pos"][:limit]).astype(F32)
+        if variant == "se":
+            mem = bilstm(sd, mem)
+        tok = np.asarray(tgt_tokens[b], np.int64)
+        L = tok.shape[0]
+        x = (sd["dec.tok_emb.weight"][tok] + sd["dec.pos_emb"][:L]).astype(F32)
+        causal = np.where(np.arange(L)[None, :] > np.arange(L)[:, None], -np.inf, 0.0).astype(F32)
+        self_mask = causal + np.where(tok == PAD, -np.inf, 0.0).astype(F32)[None, :]
+        cross_mask = np.broadcast_to(np.where(np.arange(limit) >= tb, -np.inf, 0.0).astype(F32)[None, :], (L, limit))
+        for l in range(2):
+            pre = f"dec.decoder.layers.{l}."
+            a = mha(x, x, x, sd[pre + "self_attn.in_proj_weight"], sd[pre + "self_attn.in_proj_bias"],
+                    sd[pre + "self_attn.out_proj.weight"], sd[pre + "self_attn.out_proj.bias"], self_mask)
+            x = layer_norm(x + a, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
+            a = mha(x, mem, mem, sd[pre + "multihead_attn.in_proj_weight"], sd[pre + "multihead_attn.in_proj_bias"],
+                    sd[pre + "multihead_attn.out_proj.weight"], sd[pre + "multihead_attn.out_proj.bias"], cross_mask)
+            x = layer_norm(x + a, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
+            ff = linear(relu(linear(x, sd[pre + "linear1.weight"], sd[pre + "linear1.bias"])),
+                        sd[pre + "linear2.weight"], sd[pre + "linear2.bias"])
+            x = layer_norm(x + ff, sd[pre + "norm3.weight"], sd[pre + "norm3.bias"])
+        out.append(linear(x, sd["dec.out_proj.weight"], sd["dec.out_proj.bias"]))
+    return np.stack(out)
+
+
 def greedy_decode(sd, memory, max_len=256, return_logits=False):
     """OCRPredictor._greedy_decode (predictor.py:85-99): start [sos]; up to `max_len` iterations;
     argmax of the last position (ties -> lowest index); stop BEFORE appending eos.

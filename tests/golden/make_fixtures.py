@@ -8,6 +8,7 @@ tests, `smoke()` or `bench.py` runs this; they read the files it wrote.
   python tests/golden/make_fixtures.py train     # fixture_se_ckpt.npz  (reference model, CPU training)
   python tests/golden/make_fixtures.py golden    # golden_*.npz      (reference outputs = pinned oracle)
   python tests/golden/make_fixtures.py crops     # golden_crops.npz  (Pillow crop / paste / convert('L') of a page)
+  python tests/golden/make_fixtures.py forward   # golden_forward.npz (reference KhmerOCR.forward, teacher forcing)
 
 Why a trained checkpoint: with default random init the reference's decoder output is
 input-independent and top-1/top-2 logit gaps are ~1e-3, so token-level parity under bf16 would be
@@ -304,6 +305,39 @@ def stage_golden(args):
         print(f, f"{(HERE / f).stat().st_size/1e6:.2f} MB")
 
 
+def stage_forward(args):
+    """Teacher-forced batched forward: logits of the reference's `KhmerOCR.forward` (se_model.py:240-289) in
+    eval mode on 5 lines of different lengths, targets = the labels right-padded with <pad> (one target deliberately
+    wrong and one containing <pad> in the middle)."""
+    import torch
+    from PIL import Image
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    sys.path.insert(0, str(REF))
+    from netra_ocr.recognition.preprocessor import ImagePreprocessor
+    from netra_ocr.recognition.config import OCRConfig
+    torch.set_num_threads(args.threads)
+    sd = load_checkpoint(CKPT)
+    m = _ref_model(sd, "se").eval()
+    pre = ImagePreprocessor(OCRConfig(device="cpu", max_seq_len=MAX_GLOBAL_LEN))
+    bank = synth.WordBank()
+    imgs, lbls = synth.make_lines(5, 90, 900, seed=12, bank=bank)
+    L = max(len(l) for l in lbls) + 2
+    tgt = np.zeros((5, L), np.int64)
+    for r, l in enumerate(lbls):
+        tgt[r, 0] = 2
+        tgt[r, 1:len(l) + 1] = l
+    tgt[1, 3] = 0                          # a <pad> in the middle of a target: masked as a key (se_model.py:190)
+    tgt[2, 1:6] = [44, 45, 46, 47, 48]     # a wrong prefix
+    chunk_lists = [list(pre.process(Image.fromarray(im))) for im in imgs]
+    with torch.no_grad():
+        logits = m(chunk_lists, torch.from_numpy(tgt)).numpy()
+    out = {"n": np.asarray(5), "tgt": tgt.astype(np.int32), "logits": logits.astype(np.float32)}
+    for i, im in enumerate(imgs):
+        out[f"img{i}"] = im
+    np.savez_compressed(HERE / "golden_forward.npz", **out)
+    print("golden_forward.npz", logits.shape, [len(c) for c in chunk_lists], f"{(HERE / 'golden_forward.npz').stat().st_size/1e6:.2f} MB")
+
+
 def stage_crops(args):
     """Input-side goldens.  netra_ocr/textline_detection.py imports surya (absent here), so the ten lines of
     `extract_textline_crops` (:17-47) are restated with the SAME Pillow calls - Image.crop, Image.new("RGB", ..., white),
@@ -361,7 +395,7 @@ def stage_crops(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("stage", choices=["bank", "train", "golden", "crops"])
+    ap.add_argument("stage", choices=["bank", "train", "golden", "crops", "forward"])
     ap.add_argument("--words-per-group", type=int, default=36)
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--batch", type=int, default=8)
@@ -369,4 +403,4 @@ if __name__ == "__main__":
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--threads", type=int, default=6)
     a = ap.parse_args()
-    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops}[a.stage](a)
+    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops, "forward": stage_forward}[a.stage](a)

@@ -149,3 +149,18 @@ def test_textline_crops_against_pillow_outputs():
             assert np.array_equal(O.crop_line_gray(page, b, padding), z[f"{tag}_crop{i}"]), (tag, i)
     assert np.array_equal(O.rgb_to_l(page), z["page_l"])
     assert np.array_equal(O.crop_line_gray(z["page_l"], (10, 5, 300, 60), 0), z["l_crop"])
+
+
+def test_teacher_forced_forward_against_reference_outputs():
+    """oracle.forward_teacher_forced == the reference's KhmerOCR.forward (se_model.py:240-289): padded memory, BiLSTM
+    over the pads, memory_key_padding_mask, <pad> target keys masked."""
+    z = _need("golden_forward.npz")
+    sd = load_fixture_ckpt()
+    n = int(z["n"])
+    enc = []
+    for i in range(n):
+        chunks = O.preprocess_gray(z[f"img{i}"])[1]
+        enc.append(O.encoder_forward(sd, O.patch_forward(sd, O.cnn_forward(sd, chunks, "se"))))
+    got = O.forward_teacher_forced(sd, enc, z["tgt"], "se")
+    assert got.shape == z["logits"].shape
+    assert rel_err(got, z["logits"]) < 1e-4 and max_err(got, z["logits"]) < 2e-3
