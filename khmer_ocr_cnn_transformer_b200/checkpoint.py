@@ -17,17 +17,37 @@ import numpy as np
 VOCAB_SIZE = 124
 NHEAD = 8
 ENC_FF = 1024
+# BasicBlocks of the ResNet baseline in execution order: (state_dict prefix under cnn., in channels, out channels)
+RESNET_BLOCKS = [("layer1.0", 64, 128), ("layer2.0", 128, 256), ("layer2.1", 256, 256), ("layer3.0", 256, 512),
+                 ("layer3.1", 512, 512), ("layer4.0", 512, 512)]
 
 
 def state_dict_spec(variant: str = "se", emb_dim: int = 384, max_global_len: int = 4096,
                     vocab_size: int = VOCAB_SIZE, dec_max_len: int = 256) -> dict:
     """Ordered {name: shape} of every floating-point entry of the reference state_dict
     (`num_batches_tracked` int64 scalars are accepted on load and ignored)."""
-    assert variant in ("se", "vgg")
+    assert variant in ("se", "vgg", "resnet")
     D = emb_dim
     spec: dict[str, tuple] = {"global_pos": (max_global_len, D)}
+    if variant == "resnet":
+        # ResNetFeatureExtractor (model/resnet_model.py:37-91): conv1/bn1, then BasicBlocks layer1.0, layer2.{0,1},
+        # layer3.{0,1}, layer4.0 (conv bias=False; a 1x1 conv + BN shortcut where the channel count changes)
+        def bn(p, c):
+            for n in ("weight", "bias", "running_mean", "running_var"):
+                spec[f"{p}.{n}"] = (c,)
+        spec["cnn.conv1.weight"] = (64, 1, 3, 3)
+        bn("cnn.bn1", 64)
+        for name, cin, cout in RESNET_BLOCKS:
+            p = f"cnn.{name}"
+            spec[p + ".conv1.weight"] = (cout, cin, 3, 3)
+            bn(p + ".bn1", cout)
+            spec[p + ".conv2.weight"] = (cout, cout, 3, 3)
+            bn(p + ".bn2", cout)
+            if cin != cout:
+                spec[p + ".shortcut.0.weight"] = (cout, cin, 1, 1)
+                bn(p + ".shortcut.1", cout)
     chans = [1, 64, 128, 256, 256, 512, 512]
-    for i in range(1, 7):
+    for i in (range(1, 7) if variant != "resnet" else ()):
         ci, co = chans[i - 1], chans[i]
         p = f"cnn.conv{i}"
         spec[p + ".0.weight"] = (co, ci, 3, 3)
@@ -40,8 +60,9 @@ def state_dict_spec(variant: str = "se", emb_dim: int = 384, max_global_len: int
             spec[s + ".fc.0.bias"] = (co // 16,)
             spec[s + ".fc.2.weight"] = (co, co // 16, 1)
             spec[s + ".fc.2.bias"] = (co,)
-    spec["cnn.conv7.weight"] = (512, 512, 3, 3)
-    spec["cnn.conv7.bias"] = (512,)
+    if variant != "resnet":
+        spec["cnn.conv7.weight"] = (512, 512, 3, 3)
+        spec["cnn.conv7.bias"] = (512,)
     if variant == "se":
         for n in ("weight", "bias", "running_mean", "running_var"):
             spec[f"cnn.bn7.{n}"] = (512,)
@@ -106,9 +127,11 @@ def seeded_state_dict(variant: str = "se", seed: int = 0, emb_dim: int = 384,
             v = rng.uniform(0.5, 1.5, shape)
         elif name.endswith("running_mean"):
             v = rng.uniform(-0.2, 0.2, shape)
-        elif (".1.weight" in name and name.startswith("cnn.conv")) or name == "cnn.bn7.weight":
+        elif ((".1.weight" in name and name.startswith("cnn.conv")) or name == "cnn.bn7.weight"
+              or (variant == "resnet" and name.startswith("cnn.") and len(shape) == 1 and name.endswith(".weight"))):
             v = rng.uniform(0.8, 1.2, shape)
-        elif (".1.bias" in name and name.startswith("cnn.conv")) or name == "cnn.bn7.bias":
+        elif ((".1.bias" in name and name.startswith("cnn.conv")) or name == "cnn.bn7.bias"
+              or (variant == "resnet" and name.startswith("cnn.") and len(shape) == 1 and name.endswith(".bias"))):
             v = rng.uniform(-0.1, 0.1, shape)
         elif "norm" in name and name.endswith("weight"):
             v = rng.uniform(0.9, 1.1, shape)
@@ -125,13 +148,15 @@ def seeded_state_dict(variant: str = "se", seed: int = 0, emb_dim: int = 384,
             v = rng.uniform(-0.05, 0.05, shape)
         else:
             fan_in = int(np.prod(shape[1:]))
-            a = gain * np.sqrt(3.0 / fan_in) * (np.sqrt(2.0) if name.startswith("cnn.conv") else 1.0)
+            a = gain * np.sqrt(3.0 / fan_in) * (np.sqrt(2.0) if name.startswith("cnn.") and len(shape) == 4 else 1.0)
             v = rng.uniform(-a, a, shape)
         sd[name] = np.ascontiguousarray(v, dtype=np.float32)
     return sd
 
 
 def detect_variant(sd: dict) -> str:
+    if "cnn.layer1.0.conv1.weight" in sd:
+        return "resnet"
     return "se" if "context_bilstm.weight_ih_l0" in sd else "vgg"
 
 

@@ -580,4 +580,22 @@ int launch_se_fused(const act16_t* in, const SEWeights& w, act16_t* out, int n_c
     return 2;
 }
 
+// 16-bit -> fp32 copy (identity shortcut of a ResNet BasicBlock as the fp32 addend of the block's second conv GEMM).
+__global__ void __launch_bounds__(256) a16_to_f32_kernel(const act16_t* __restrict__ in, float* __restrict__ out, long n8) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(a16_lo(v.x), a16_hi(v.x), a16_lo(v.y), a16_hi(v.y));
+    o[1] = make_float4(a16_lo(v.z), a16_hi(v.z), a16_lo(v.w), a16_hi(v.w));
+}
+
+int launch_a16_to_f32(const act16_t* in, float* out, long n_elems, cudaStream_t stream) {
+    if (n_elems == 0) return 0;
+    const long n8 = n_elems / 8;
+    a16_to_f32_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(in, out, n8);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace kocr

@@ -42,6 +42,8 @@ int launch_conv1_pool_mma(const float* d_chunks, const act16_t* w16, const float
                           cudaStream_t stream);
 void set_conv1_impl(int impl);
 int conv1_impl();
+// 16-bit -> fp32 copy (n_elems multiple of 8)
+int launch_a16_to_f32(const act16_t* in, float* out, long n_elems, cudaStream_t stream);
 // 2x2 max-pool between padded-linear layouts (C multiple of 8).
 int launch_pool2x2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
 // 1D-SE: squeeze -> column means a16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;

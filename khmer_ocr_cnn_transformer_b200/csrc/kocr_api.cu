@@ -35,6 +35,10 @@ static std::atomic<int64_t> g_launches{0};     // non-GEMM kernel launches (GEMM
 struct BlobHeader { char magic[8]; uint32_t n_entries; uint32_t reserved; };
 struct BlobEntry { char name[48]; uint32_t dtype; uint32_t pad; uint64_t offset; uint64_t nbytes; };
 
+struct ResBlockW {                 // BasicBlock of the ResNet baseline (model/resnet_model.py:5-37), BN folded
+    const act16_t *c1w, *c2w, *scw;     // 3x3 convs [Cout][9][Cin]; 1x1 shortcut conv [Cout][Cin] or null (identity)
+    const float *c1b, *c2b, *scb;
+};
 struct EncLayerW {
     const act16_t *in_w, *out_w, *l1_w, *l2_w;
     const float *in_b, *out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b;
@@ -63,6 +67,7 @@ struct kocr_handle {
     size_t blob_bytes = 0;
     std::map<std::string, std::pair<const void*, size_t>> w;
     const float *conv1_w, *conv1_b;
+    ResBlockW res[6];
     const act16_t* conv1_w16;      // [64][16]: 9 taps + 7 zeros, tensor-core conv1
     const act16_t* conv_w[8];
     const float* conv_b[8];
@@ -141,6 +146,9 @@ int lookup(kocr_handle* h, const char* name, const void** out, size_t min_bytes)
 #define W_F32(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 4))
 #define W_A16(field, name, n) KOCR_TRY(lookup(h, name, reinterpret_cast<const void**>(&(field)), (size_t)(n) * 2))
 
+// channels of the six BasicBlocks in execution order: layer1.0, layer2.0, layer2.1, layer3.0, layer3.1, layer4.0
+static const int RES_CIN[6] = {64, 128, 256, 256, 512, 512}, RES_COUT[6] = {128, 256, 256, 512, 512, 512};
+
 int resolve_weights(kocr_handle* h) {
     const int D = D_MODEL;
     static const int cin[8] = {0, 1, 64, 128, 256, 256, 512, 512};
@@ -149,9 +157,24 @@ int resolve_weights(kocr_handle* h) {
     W_F32(h->conv1_b, "conv1.b", 64);
     W_A16(h->conv1_w16, "conv1.w16", 64 * 16);
     char nm[64];
-    for (int i = 2; i <= 7; ++i) {
+    for (int i = 2; i <= 7 && h->variant != 2; ++i) {
         snprintf(nm, sizeof nm, "conv%d.w", i); W_A16(h->conv_w[i], nm, (size_t)cout[i] * 9 * cin[i]);
         snprintf(nm, sizeof nm, "conv%d.b", i); W_F32(h->conv_b[i], nm, cout[i]);
+    }
+    if (h->variant == 2) {
+        for (int b = 0; b < 6; ++b) {
+            const int ci = RES_CIN[b], co = RES_COUT[b];
+            ResBlockW& r = h->res[b];
+            snprintf(nm, sizeof nm, "res%d.c1.w", b); W_A16(r.c1w, nm, (size_t)co * 9 * ci);
+            snprintf(nm, sizeof nm, "res%d.c1.b", b); W_F32(r.c1b, nm, co);
+            snprintf(nm, sizeof nm, "res%d.c2.w", b); W_A16(r.c2w, nm, (size_t)co * 9 * co);
+            snprintf(nm, sizeof nm, "res%d.c2.b", b); W_F32(r.c2b, nm, co);
+            r.scw = nullptr; r.scb = nullptr;
+            if (ci != co) {
+                snprintf(nm, sizeof nm, "res%d.sc.w", b); W_A16(r.scw, nm, (size_t)co * ci);
+                snprintf(nm, sizeof nm, "res%d.sc.b", b); W_F32(r.scb, nm, co);
+            }
+        }
     }
     if (h->variant == 0) {
         static const int sc[3] = {256, 512, 512};
@@ -244,6 +267,10 @@ int carve_workspace(kocr_handle* h) {
         {"dparts", 8 * L * 3 * D * 4},
         {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
     };
+    if (h->variant == 2) {      // ResNet baseline: second 24x50x128 activation + the fp32 shortcut (largest: layer1)
+        items.push_back({"res_t1", NC * G1.S * 128 * 2});
+        items.push_back({"res_add", NC * G1.S * 128 * 4});
+    }
     size_t total = 0;
     for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
     KOCR_CUDA(cudaMalloc(&h->ws, total));
@@ -319,7 +346,7 @@ int gemm_linear(kocr_handle* h, const void* a, long rows, const void* w, int N, 
 }
 
 int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, const PLGeom& g, int Cin,
-              int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s) {
+              int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s, const float* addend = nullptr) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = n_chunks * g.S; p.N = Cout; p.taps = 9; p.cin = Cin;
@@ -329,6 +356,10 @@ int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, con
     p.ep.bias = b; p.ep.relu = relu;
     p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W;
     p.ep.out_a16 = out; p.ep.ld_a16 = Cout;
+    if (addend) {               // residual connection: out = act(conv + bias + addend); the addend path needs the 128-wide N tile
+        p.ep.addend = addend; p.ep.ld_add = Cout; p.ep.add_period = 0;
+        p.bn = 128;
+    }
     const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
     return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, sms, s);
 }
@@ -355,6 +386,49 @@ int se_gate(kocr_handle* h, const act16_t* act, int NC, int H, int W, int C, con
     return 0;
 }
 
+// One BasicBlock (model/resnet_model.py:28-37) on the implicit-GEMM kernel: c1 = relu(bn1(conv1 x)); shortcut as an
+// fp32 tensor (1x1 conv + BN as a per-position linear layer, or a widening copy of x); out = relu(bn2(conv2 c1) + shortcut)
+// through the GEMM's fp32 addend.  `out` may alias `in` for an identity block (the addend was copied out before).
+int resnet_block(kocr_handle* h, int bi, const act16_t* in, act16_t* tmp, act16_t* out, int NC, const PLGeom& g, cudaStream_t s) {
+    const int ci = RES_CIN[bi], co = RES_COUT[bi];
+    const ResBlockW& r = h->res[bi];
+    const long rows = (long)NC * g.S;
+    float* add = buf<float>(h, "res_add");
+    char nm[32];
+    snprintf(nm, sizeof nm, "res%d_conv1", bi);
+    TIMED(nm, 2.0 * NC * g.H * g.W * 9.0 * ci * co, gemm_conv(h, in, tmp, NC, g, ci, co, r.c1w, r.c1b, 1, s));
+    snprintf(nm, sizeof nm, "res%d_shortcut", bi);
+    if (r.scw) {
+        GemmEpilogue e = ep_none();
+        e.bias = r.scb; e.out_f32 = add; e.ld_f32 = co;
+        TIMED(nm, 2.0 * NC * g.H * g.W * ci * co, gemm_linear(h, in, rows, r.scw, co, ci, e, s));
+    } else {
+        TIMED(nm, 0, launch_a16_to_f32(in, add, rows * ci, s)); ++g_launches;
+    }
+    snprintf(nm, sizeof nm, "res%d_conv2", bi);
+    TIMED(nm, 2.0 * NC * g.H * g.W * 9.0 * co * co, gemm_conv(h, tmp, out, NC, g, co, co, r.c2w, r.c2b, 1, s, add));
+    return 0;
+}
+
+int stage_resnet_backbone(kocr_handle* h, cudaStream_t s) {
+    const int NC = h->n_chunks;
+    auto B = [&](const char* n) { return buf<act16_t>(h, n); };
+    if (conv1_impl() == 1) TIMED("conv1_pool1", 2.0 * NC * 48 * 100 * 9.0 * 64, launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
+    else TIMED("conv1_pool1", 2.0 * NC * 48 * 100 * 9.0 * 64, launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s));
+    ++g_launches;
+    KOCR_TRY(resnet_block(h, 0, B("pool1"), B("res_t1"), B("conv2"), NC, G1, s));                    // layer1
+    TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
+    KOCR_TRY(resnet_block(h, 1, B("pool2"), B("conv3"), B("conv4"), NC, G2, s));                     // layer2.0
+    KOCR_TRY(resnet_block(h, 2, B("conv4"), B("conv3"), B("conv4"), NC, G2, s));                     // layer2.1 (identity)
+    TIMED("pool3", 0, launch_se_apply_pool(B("conv4"), nullptr, B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
+    KOCR_TRY(resnet_block(h, 3, B("pool3"), B("conv5"), B("conv6"), NC, G3, s));                     // layer3.0
+    KOCR_TRY(resnet_block(h, 4, B("conv6"), B("conv5"), B("conv6"), NC, G3, s));                     // layer3.1 (identity)
+    TIMED("pool4", 0, launch_se_apply_pool(B("conv6"), nullptr, B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
+    KOCR_TRY(resnet_block(h, 5, B("pool4"), B("conv7"), B("pool4"), NC, G4, s));                     // layer4 (identity)
+    TIMED("final_pool", 0, launch_se_apply_finalpool(B("pool4"), nullptr, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
+    return 0;
+}
+
 int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     const int NC = h->n_chunks;
     if (NC == 0) return 0;
@@ -362,6 +436,9 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     auto B = [&](const char* n) { return buf<act16_t>(h, n); };
     const double nc = NC;
     auto cf = [&](int H, int W, int ci, int co) { return 2.0 * nc * H * W * 9.0 * ci * co; };   // algorithmic conv FLOPs
+    if (h->variant == 2) {
+        KOCR_TRY(stage_resnet_backbone(h, s));
+    } else {
     if (conv1_impl() == 1) TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
     else TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s));
     ++g_launches;
@@ -390,6 +467,7 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     if (se) KOCR_TRY(se_gate(h, B("conv7"), NC, 3, 25, 512, h->se[2], "se5", &gate, s));
     TIMED("se5_apply_finalpool", 0, launch_se_apply_finalpool(B("conv7"), gate, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
     }
+    }   // SE / VGG backbone
 
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");

@@ -10,6 +10,7 @@ from .tokenizer import Tokenizer
 from .predictor import OCRPredictor
 from .model.se_model import KhmerOCR as SE_KhmerOCR
 from .model.vgg_model import KhmerOCR as VGG_KhmerOCR
+from .model.resnet_model import KhmerOCR as ResNet_KhmerOCR
 
 CURRENT_DIR = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_MODEL_PATH = os.path.join(CURRENT_DIR, "weight", "khmerocr_se_transformer.pth")
@@ -27,14 +28,12 @@ def _get_predictor(model_path=None, vocab_path=None):
     if "vgg" in str(model_path).lower():
         model = VGG_KhmerOCR
     elif "resnet" in str(model_path).lower():
-        model = None
+        model = ResNet_KhmerOCR
     else:
         model = SE_KhmerOCR
     if _PREDICTOR_INSTANCE is not None:
         return _PREDICTOR_INSTANCE
     try:
-        if model is None:
-            raise NotImplementedError("the ResNet-Transformer baseline is outside this path (SURVEY.md §8f-4)")
         detected_cfg = autodetect_config(model_path)
         config = OCRConfig(**detected_cfg)
         tokenizer = Tokenizer(vocab_path)

@@ -20,7 +20,7 @@ from __future__ import annotations
 import struct
 import numpy as np
 
-from .checkpoint import detect_variant, validate_state_dict
+from .checkpoint import detect_variant, validate_state_dict, RESNET_BLOCKS
 
 BN_EPS = 1e-5
 MAGIC = b"KOCRW001"
@@ -130,8 +130,29 @@ def pack_tensors(sd: dict) -> dict:
     def tf32(name, a):          # decoder GEMM operands stay fp32 (consumed as TF32 by the tensor cores)
         t[name] = (DT_F32, round_to_tf32(np.ascontiguousarray(a, dtype=np.float32)))
 
-    t["meta"] = (DT_I32, np.asarray([0 if se else 1, D, max_len, dec_max, vocab, A16_FORMAT, 0, 0], np.int32))
-    for i in range(1, 7):
+    resnet = variant == "resnet"
+    t["meta"] = (DT_I32, np.asarray([0 if se else (2 if resnet else 1), D, max_len, dec_max, vocab, A16_FORMAT, 0, 0], np.int32))
+    if resnet:
+        # BasicBlock convs have no bias: the folded BN supplies it.  1x1 shortcut convs are [Cout][Cin] linear layers.
+        def fold(conv, bnp):
+            w = sd[conv + ".weight"]
+            return fold_bn(w, np.zeros(w.shape[0], np.float32), sd[bnp + ".weight"], sd[bnp + ".bias"],
+                           sd[bnp + ".running_mean"], sd[bnp + ".running_var"])
+        w, b = fold("cnn.conv1", "cnn.bn1")
+        f32("conv1.w", w.reshape(64, 9))
+        w16 = np.zeros((64, 16), np.float32); w16[:, :9] = w.reshape(64, 9)
+        bf16("conv1.w16", w16)
+        f32("conv1.b", b)
+        for bi, (name, cin, cout) in enumerate(RESNET_BLOCKS):
+            p = f"cnn.{name}"
+            w, b = fold(p + ".conv1", p + ".bn1")
+            bf16(f"res{bi}.c1.w", conv_to_kmajor(w)); f32(f"res{bi}.c1.b", b)
+            w, b = fold(p + ".conv2", p + ".bn2")
+            bf16(f"res{bi}.c2.w", conv_to_kmajor(w)); f32(f"res{bi}.c2.b", b)
+            if cin != cout:
+                w, b = fold(p + ".shortcut.0", p + ".shortcut.1")
+                bf16(f"res{bi}.sc.w", w.reshape(cout, cin)); f32(f"res{bi}.sc.b", b)
+    for i in (range(1, 7) if not resnet else ()):
         p = f"cnn.conv{i}"
         w, b = fold_bn(sd[p + ".0.weight"], sd[p + ".0.bias"], sd[p + ".1.weight"], sd[p + ".1.bias"],
                        sd[p + ".1.running_mean"], sd[p + ".1.running_var"])
@@ -143,7 +164,7 @@ def pack_tensors(sd: dict) -> dict:
         else:
             bf16(f"conv{i}.w", conv_to_kmajor(w))
             f32(f"conv{i}.b", b)
-    w7, b7 = sd["cnn.conv7.weight"], sd["cnn.conv7.bias"]
+    w7, b7 = (sd["cnn.conv7.weight"], sd["cnn.conv7.bias"]) if not resnet else (None, None)
     if se:
         w7, b7 = fold_bn(w7, b7, sd["cnn.bn7.weight"], sd["cnn.bn7.bias"], sd["cnn.bn7.running_mean"],
                          sd["cnn.bn7.running_var"])
@@ -159,8 +180,9 @@ def pack_tensors(sd: dict) -> dict:
             f32(f"se{k}.b0p", b0p)
             bf16(f"se{k}.w2p", w2p)
             f32(f"se{k}.b2", sd[f"cnn.se{k}.fc.2.bias"])
-    bf16("conv7.w", conv_to_kmajor(w7))
-    f32("conv7.b", b7)
+    if not resnet:
+        bf16("conv7.w", conv_to_kmajor(w7))
+        f32("conv7.b", b7)
     pw = sd["patch.proj.weight"][:, :, :, 0]                       # (D, 512, 2)
     bf16("patch.w", pw.transpose(0, 2, 1).reshape(D, 1024))       # k = kh*512 + c
     f32("patch.b", sd["patch.proj.bias"])

@@ -292,10 +292,50 @@ def _conv_bn_relu(x, sd, name):
     return relu(y)
 
 
+def _bn(x, sd, p):
+    return batchnorm_eval(x, sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"])
+
+
+def basic_block(x, sd, p):
+    """BasicBlock.forward (model/resnet_model.py:28-37): relu(bn1(conv1 x)) -> bn2(conv2 .) + shortcut(x) -> relu; the
+    shortcut is a 1x1 conv + BN where the channel count changes (:20-26), identity otherwise.  Convs have no bias."""
+    zero = lambda w: np.zeros(w.shape[0], F32)
+    w1, w2 = sd[p + ".conv1.weight"], sd[p + ".conv2.weight"]
+    out = relu(_bn(conv3x3(x, w1, zero(w1)), sd, p + ".bn1"))
+    out = _bn(conv3x3(out, w2, zero(w2)), sd, p + ".bn2")
+    if p + ".shortcut.0.weight" in sd:
+        ws = sd[p + ".shortcut.0.weight"][:, :, 0, 0]
+        sc = _bn(np.einsum("oc,nchw->nohw", ws, x).astype(F32), sd, p + ".shortcut.1")
+    else:
+        sc = x
+    return relu(out + sc).astype(F32)
+
+
+def resnet_forward(sd, chunks, taps=None):
+    """ResNetFeatureExtractor.forward (model/resnet_model.py:75-91)."""
+    def tap(k, v):
+        if taps is not None:
+            taps[k] = v
+        return v
+    w = sd["cnn.conv1.weight"]
+    x = tap("pool1", maxpool(relu(_bn(conv3x3(chunks, w, np.zeros(64, F32)), sd, "cnn.bn1")), 2, 2))
+    x = tap("layer1", basic_block(x, sd, "cnn.layer1.0"))
+    x = tap("pool2", maxpool(x, 2, 2))
+    x = tap("layer2", basic_block(basic_block(x, sd, "cnn.layer2.0"), sd, "cnn.layer2.1"))
+    x = tap("pool3", maxpool(x, 2, 1))
+    x = tap("layer3", basic_block(basic_block(x, sd, "cnn.layer3.0"), sd, "cnn.layer3.1"))
+    x = tap("pool4", maxpool(x, 2, 1))
+    x = tap("layer4", basic_block(x, sd, "cnn.layer4.0"))
+    return tap("final_pool", adaptive_avg_pool(x, 2, 32))
+
+
 def cnn_forward(sd, chunks, variant="se", taps=None):
     """ImprovedFeatureExtractor.forward (se_model.py:63-79) or the VGG baseline
     (vgg_model.py:50-59; no SE, conv7 without BN/ReLU).  chunks: (N,1,48,100) -> (N,512,2,32).
     `taps`, if a dict, receives the intermediate activations by name."""
+    if variant == "resnet":
+        return resnet_forward(sd, chunks, taps)
+
     def tap(k, v):
         if taps is not None:
             taps[k] = v

@@ -9,6 +9,7 @@ tests, `smoke()` or `bench.py` runs this; they read the files it wrote.
   python tests/golden/make_fixtures.py golden    # golden_*.npz      (reference outputs = pinned oracle)
   python tests/golden/make_fixtures.py crops     # golden_crops.npz  (Pillow crop / paste / convert('L') of a page)
   python tests/golden/make_fixtures.py forward   # golden_forward.npz (reference KhmerOCR.forward, teacher forcing)
+  python tests/golden/make_fixtures.py resnet    # golden_resnet.npz  (reference ResNet-Transformer baseline, seeded init)
 
 Why a trained checkpoint: with default random init the reference's decoder output is
 input-independent and top-1/top-2 logit gaps are ~1e-3, so token-level parity under bf16 would be
@@ -116,6 +117,8 @@ def _ref_model(sd=None, variant="se", max_global_len=MAX_GLOBAL_LEN):
     sys.path.insert(0, str(REF))
     if variant == "se":
         from netra_ocr.recognition.model.se_model import KhmerOCR
+    elif variant == "resnet":
+        from netra_ocr.recognition.model.resnet_model import KhmerOCR
     else:
         from netra_ocr.recognition.model.vgg_model import KhmerOCR
     m = KhmerOCR(vocab_size=124, pad_idx=0, emb_dim=384, max_global_len=max_global_len)
@@ -338,6 +341,49 @@ def stage_forward(args):
     print("golden_forward.npz", logits.shape, [len(c) for c in chunk_lists], f"{(HERE / 'golden_forward.npz').stat().st_size/1e6:.2f} MB")
 
 
+def stage_resnet(args):
+    """ResNet-Transformer baseline (model/resnet_model.py, selected by "resnet" in the checkpoint name,
+    recognize_text.py:41-42) with the seeded init: backbone output, encoder output, memory and a short greedy decode of
+    the reference itself."""
+    import torch
+    from PIL import Image
+    sys.path.insert(0, str(REF))
+    from netra_ocr.recognition.preprocessor import ImagePreprocessor
+    from netra_ocr.recognition.config import OCRConfig
+    torch.set_num_threads(args.threads)
+    rsd = seeded_state_dict("resnet", seed=13, max_global_len=MAX_GLOBAL_LEN)
+    rm = _ref_model(rsd, "resnet").eval()
+    pre = ImagePreprocessor(OCRConfig(device="cpu", max_seq_len=MAX_GLOBAL_LEN))
+    bank = synth.WordBank()
+    imgs, _ = synth.make_lines(3, 150, 900, seed=21, bank=bank)
+    g = {}
+    for li, im in enumerate(imgs):
+        chunks = pre.process(Image.fromarray(im))
+        with torch.no_grad():
+            f = rm.cnn(chunks)
+            p = rm.patch(f)[0]
+            e = rm.enc(p.transpose(0, 1).contiguous()).transpose(0, 1)
+            mem = e.reshape(1, -1, 384) + rm.global_pos[: e.shape[0] * 32].unsqueeze(0)
+            gen, step_logits = [2], []
+            mask = torch.zeros((1, mem.shape[1]), dtype=torch.bool)
+            for _ in range(24):
+                lg = rm.dec(torch.LongTensor([gen]), mem, mask)
+                step_logits.append(lg[0, -1].numpy().copy())
+                nx = int(torch.argmax(lg[0, -1]).item())
+                if nx == 3:
+                    break
+                gen.append(nx)
+        g[f"img{li}"] = im
+        g[f"cnn{li}"] = f.numpy().astype(np.float32)
+        g[f"enc{li}"] = e.numpy().astype(np.float32)
+        g[f"mem{li}"] = mem[0].numpy().astype(np.float32)
+        g[f"tokens{li}"] = np.asarray(gen, np.int32)
+        g[f"step_logits{li}"] = np.stack(step_logits).astype(np.float32)
+    g["n_lines"] = np.asarray(3)
+    np.savez_compressed(HERE / "golden_resnet.npz", **g)
+    print("golden_resnet.npz", f"{(HERE / 'golden_resnet.npz').stat().st_size/1e6:.2f} MB")
+
+
 def stage_crops(args):
     """Input-side goldens.  netra_ocr/textline_detection.py imports surya (absent here), so the ten lines of
     `extract_textline_crops` (:17-47) are restated with the SAME Pillow calls - Image.crop, Image.new("RGB", ..., white),
@@ -395,7 +441,7 @@ def stage_crops(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("stage", choices=["bank", "train", "golden", "crops", "forward"])
+    ap.add_argument("stage", choices=["bank", "train", "golden", "crops", "forward", "resnet"])
     ap.add_argument("--words-per-group", type=int, default=36)
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--batch", type=int, default=8)
@@ -403,4 +449,4 @@ if __name__ == "__main__":
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--threads", type=int, default=6)
     a = ap.parse_args()
-    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops, "forward": stage_forward}[a.stage](a)
+    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops, "forward": stage_forward, "resnet": stage_resnet}[a.stage](a)

@@ -164,3 +164,21 @@ def test_teacher_forced_forward_against_reference_outputs():
     got = O.forward_teacher_forced(sd, enc, z["tgt"], "se")
     assert got.shape == z["logits"].shape
     assert rel_err(got, z["logits"]) < 1e-4 and max_err(got, z["logits"]) < 2e-3
+
+
+def test_resnet_baseline_against_reference_outputs():
+    """oracle 'resnet' variant == the reference's ResNet-Transformer (model/resnet_model.py) with the seeded init."""
+    from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict
+    z = _need("golden_resnet.npz")
+    sd = seeded_state_dict("resnet", seed=13, max_global_len=1024)
+    for i in range(int(z["n_lines"])):
+        chunks = O.preprocess_gray(z[f"img{i}"])[1]
+        f = O.cnn_forward(sd, chunks, "resnet")
+        assert rel_err(f, z[f"cnn{i}"]) < 1e-4
+        enc = O.encoder_forward(sd, O.patch_forward(sd, f))
+        assert rel_err(enc, z[f"enc{i}"]) < 1e-4
+        mem = O.memory_for_line(sd, enc, "resnet")
+        assert rel_err(mem, z[f"mem{i}"]) < 1e-4
+        toks = O.greedy_decode(sd, mem, max_len=24)
+        want = [int(t) for t in z[f"tokens{i}"]]
+        assert toks[:len(want)] == want[:len(toks)]
