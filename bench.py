@@ -156,7 +156,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-lines", type=int, default=8, help="lines of the bounded cpu_baseline sample")
@@ -205,6 +205,8 @@ def main():
     KB = max(1, args.coalesce)
     LPC = LINES_PER_STEP * KB                                   # lines per device pass
 
+    pool, pool_lock = [], threading.Lock()      # stragglers handed back by the in-flight passes
+
     class Worker:
         """One in-flight device pass: its own handle (weights + workspace + stream), its own pinned buffers.
         A pass covers `KB` steps (256-line batches); `sub[k]` is the same data cut down to k batches for the tail."""
@@ -224,7 +226,7 @@ def main():
             self.tok_host = torch.zeros((LPC, _native.TOKENS_LD), dtype=torch.int32).pin_memory()
             self.len_host = torch.zeros(LPC, dtype=torch.int32).pin_memory()
             self.tok_np, self.len_np = self.tok_host.numpy(), self.len_host.numpy()
-            self.pool, self.n_stragglers, self.n_flushes = [], 0, 0
+            self.n_stragglers, self.n_flushes = 0, 0
             self.rec.set_option("dec_wide", 1 if (args.dec_wide == 1 or (args.dec_wide < 0 and S * KB <= 4)) else 0)
             # programmatic dependent launch shortens ONE decode chain (latency); with several passes in flight the early-
             # resident dependents only hold SM slots while they wait, which costs ~7 % of throughput (tools/inflight_probe.py)
@@ -234,21 +236,35 @@ def main():
                 self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
             self.n_chunks = int(self.rec.gather_chunks(self.sub[1][0], pixels_dev_ptr=self.sub[1][3].data_ptr()).sum())
 
-        # Long tail: a pass returns once <= 8 lines per 256 are still decoding; those stragglers are pooled and decoded
-        # to the end in passes of up to LPC lines (flush), inside the timed region.  Same results, see predictor.py.
+        # Long tail: a pass returns once <= 8 lines per 256 are still decoding; those stragglers go to a pool SHARED by the
+        # in-flight passes and are decoded to the end in passes of up to LPC lines, inside the timed region.  Same
+        # results, see predictor.py.  The last passes of a run (`final`) decode every line in place instead, so that the
+        # run does not end with a lone, latency-bound straggler pass.
         def _collect(self, k):
             todo = np.nonzero(self.rec.unfinished(k * LINES_PER_STEP))[0]
-            self.pool.extend(self.imgs[i] for i in todo)
             self.n_stragglers += len(todo)
-            if len(self.pool) >= LPC:
-                self.flush()
+            part = None
+            with pool_lock:
+                pool.extend(self.imgs[i] for i in todo)
+                if len(pool) >= LPC:
+                    part = pool[:LPC]
+                    del pool[:LPC]
+            if part:
+                self._decode_pool(part)
+
+        def _decode_pool(self, part):
+            self.rec.set_option("straggler_threshold", 0)
+            self.rec.recognize_lines(_native.LineBatch(part))
+            self.n_flushes += 1
 
         def flush(self):
-            while self.pool:
-                part, self.pool = self.pool[:LPC], self.pool[LPC:]
-                self.rec.set_option("straggler_threshold", 0)
-                self.rec.recognize_lines(_native.LineBatch(part))
-                self.n_flushes += 1
+            while True:
+                with pool_lock:
+                    part = pool[:LPC]
+                    del pool[:LPC]
+                if not part:
+                    return
+                self._decode_pool(part)
 
         # The same pass as two calls (stages 1-5a, then the decode loop) for the phased schedule below.
         def step_heavy(self, host, k=None):
@@ -267,16 +283,16 @@ def main():
             check(self.rec.lib.kocr_decode_greedy(self.rec._h, 0, self.tok_np.ctypes.data, self.len_np.ctypes.data, None))
             self._collect(k or KB)
 
-        def step_resident(self, k=None):
+        def step_resident(self, k=None, final=False):
             k = k or KB
-            self.rec.set_option("straggler_threshold", args.straggler_threshold * k)
+            self.rec.set_option("straggler_threshold", 0 if final else args.straggler_threshold * k)
             b, _, _, dev = self.sub[k]
             self.rec.recognize_lines(b, pixels_dev_ptr=dev.data_ptr(), tokens_out=self.tok_np, lengths_out=self.len_np)
             self._collect(k)
 
-        def step_e2e(self, k=None):       # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
+        def step_e2e(self, k=None, final=False):   # H2D of the pixels (pinned) ... D2H of the ids, all inside the C-ABI call
             k = k or KB
-            self.rec.set_option("straggler_threshold", args.straggler_threshold * k)
+            self.rec.set_option("straggler_threshold", 0 if final else args.straggler_threshold * k)
             self.rec.recognize_lines(self.sub[k][1], tokens_out=self.tok_np, lengths_out=self.len_np)
             self._collect(k)
 
@@ -308,12 +324,13 @@ def main():
                             break
                         k = min(KB, steps - i)
                         counter["next"] = i + k
-                    fn(k)
+                    fn(k, final=(steps - i) <= n_threads * KB)      # the last pass of every worker: no hand-off
                 wk.flush()          # decode this worker's pooled stragglers to the end (inside the timed region)
             except Exception as e:  # surface worker failures instead of hanging
                 errors.append(e)
 
-        threads = [threading.Thread(target=loop, args=(wk,)) for wk in workers[:max(1, min(S, (steps + KB - 1) // KB))]]
+        n_threads = max(1, min(S, (steps + KB - 1) // KB))
+        threads = [threading.Thread(target=loop, args=(wk,)) for wk in workers[:n_threads]]
         for t in threads:
             t.start()
         for t in threads:
