@@ -232,6 +232,8 @@ def main():
             # resident dependents only hold SM slots while they wait, which costs ~7 % of throughput (tools/inflight_probe.py)
             if args.no_pdl or S > 1:
                 self.rec.set_option("use_pdl", 0)
+            if S > 1:       # a dozen host threads per GPU (x 8 ranks per host) must not spin inside cudaStreamSynchronize
+                self.rec.set_option("blocking_wait", 1)
             if args.big_gemm_sms > 0 and S > 1:
                 self.rec.set_option("big_gemm_sms", args.big_gemm_sms)
             self.n_chunks = int(self.rec.gather_chunks(self.sub[1][0], pixels_dev_ptr=self.sub[1][3].data_ptr()).sum())
@@ -378,6 +380,7 @@ def main():
     decode_steps = int(rec.debug_read("last_steps"))
 
     # ---- single in-flight latency of one step (for context)
+    workers[0].rec.set_option("blocking_wait", 0)
     barrier()
     t0 = time.perf_counter()
     for _ in range(3):          # full-length decode of every line (no straggler hand-off)

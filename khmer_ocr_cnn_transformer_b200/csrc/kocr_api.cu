@@ -92,6 +92,7 @@ struct kocr_handle {
     uint8_t* staging_dev = nullptr;
     size_t staging_bytes = 0;
     cudaEvent_t staging_done = nullptr;
+    cudaEvent_t sync_event = nullptr;     // cudaEventBlockingSync: host waits sleep instead of spinning
     int32_t* pinned_flag = nullptr;    // pinned int for early-exit polling
     int32_t* fin_host = nullptr;       // pinned copy of the per-line finished flags of the last decode
     // batch state
@@ -109,6 +110,7 @@ struct kocr_handle {
     bool decode_warmed = false;
     int use_graphs = 1;
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
+    int blocking_wait = 0;       // 1: host waits sleep on a blocking-sync event (many handles / host threads per process)
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
     Buf tf_x, tf_tab;             // kocr_forward_teacher_forced: padded memory operand, per-line tables
@@ -246,6 +248,15 @@ struct WsItem { const char* name; size_t bytes; };
 
 int ensure(Buf& b, size_t bytes);
 
+// Wait for stream `s` WITHOUT spinning: cudaStreamSynchronize busy-waits by default, and bench.py / a serving process
+// keeps a dozen host threads per GPU blocked in here (x 8 GPUs on one host).  A blocking-sync event lets them sleep.
+cudaError_t wait_stream(kocr_handle* h, cudaStream_t s) {
+    if (!h->blocking_wait) return cudaStreamSynchronize(s);      // one handle, latency matters: spin (a sleep costs ~0.4 ms)
+    cudaError_t e = cudaEventRecord(h->sync_event, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->sync_event);
+}
+
 int carve_workspace(kocr_handle* h) {
     const size_t NC = h->max_chunks, L = h->max_lines, M = NC * TOK_PER_CHUNK;
     const size_t D = D_MODEL;
@@ -289,7 +300,8 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaMalloc(&h->staging_dev, h->staging_bytes));
     KOCR_CUDA(cudaMallocHost(&h->pinned_flag, 64));
     KOCR_CUDA(cudaMallocHost(&h->fin_host, (size_t)h->max_lines * 4));
-    KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming));
+    KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    KOCR_CUDA(cudaEventCreateWithFlags(&h->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
     KOCR_CUDA(cudaStreamCreate(&h->own_stream));
     // input staging sized for the handle's capacity up front (4x the bytes of the height-48 chunks: source lines are
     // rarely more than 2x oversampled): a cudaMalloc in the middle of a run would synchronise every in-flight batch
@@ -723,6 +735,7 @@ int kocr_destroy(kocr_handle* h) {
     if (h->pinned_flag) cudaFreeHost(h->pinned_flag);
     if (h->fin_host) cudaFreeHost(h->fin_host);
     if (h->staging_done) cudaEventDestroy(h->staging_done);
+    if (h->sync_event) cudaEventDestroy(h->sync_event);
     for (auto& g : h->dec_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -870,7 +883,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         std::vector<int32_t> init((size_t)L, 2), ones((size_t)L, 1);
         KOCR_CUDA(cudaMemcpy2DAsync(tokens, KOCR_TOKENS_LD * 4, init.data(), 4, 4, L, cudaMemcpyHostToDevice, s));
         KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "lengths"), ones.data(), (size_t)L * 4, cudaMemcpyHostToDevice, s));
-        KOCR_CUDA(cudaStreamSynchronize(s));   // the two host vectors die at scope end
+        KOCR_CUDA(wait_stream(h, s));   // the two host vectors die at scope end
     }
     if (h->trace_logits) {
         KOCR_TRY(ensure(h->trace, (size_t)h->max_lines * DEC_MAX * VOCAB_PAD * 4));
@@ -891,7 +904,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         done += n;
         if (!forcing && done < max_steps) {
             KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
-            KOCR_CUDA(cudaStreamSynchronize(s));
+            KOCR_CUDA(wait_stream(h, s));
             h->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
             if (*h->pinned_flag <= h->straggler_threshold) break;     // every line (or all but a few stragglers) has emitted <eos>
         }
@@ -900,7 +913,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
     if (tokens_out) KOCR_CUDA(cudaMemcpyAsync(tokens_out, tokens, (size_t)L * KOCR_TOKENS_LD * 4, cudaMemcpyDeviceToHost, s));
     if (lengths_out) KOCR_CUDA(cudaMemcpyAsync(lengths_out, buf<int>(h, "lengths"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(cudaMemcpyAsync(h->fin_host, buf<int>(h, "finished"), (size_t)L * 4, cudaMemcpyDeviceToHost, s));
-    KOCR_CUDA(cudaStreamSynchronize(s));
+    KOCR_CUDA(wait_stream(h, s));
     return 0;
 }
 
@@ -921,6 +934,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
+    if (strcmp(name, "blocking_wait") == 0) { h->blocking_wait = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
     if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
@@ -1019,7 +1033,7 @@ int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, co
     // the argmax kernel wrote the (bias-added, slice-summed) logits of position t into the trace rows
     KOCR_CUDA(cudaMemcpy2DAsync(logits_out, VOCAB_PAD * 4, reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
                                 (size_t)DEC_MAX * VOCAB_PAD * 4, VOCAB_PAD * 4, n_rows, cudaMemcpyDeviceToHost, s));
-    KOCR_CUDA(cudaStreamSynchronize(s));     // tab / prefixes are host memory of this call
+    KOCR_CUDA(wait_stream(h, s));     // tab / prefixes are host memory of this call
     return 0;
 }
 
@@ -1079,7 +1093,7 @@ int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L
     for (int b = 0; b < B; ++b)
         for (int t = 0; t < L; ++t) forced[(size_t)b * KOCR_TOKENS_LD + t] = tgt_tokens[(size_t)b * L + t];
     KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "forced"), forced.data(), forced.size() * 4, cudaMemcpyHostToDevice, s));
-    KOCR_CUDA(cudaStreamSynchronize(s));              // `tab` / `forced` are host vectors of this call
+    KOCR_CUDA(wait_stream(h, s));              // `tab` / `forced` are host vectors of this call
     const int sv_force = h->force_tokens, sv_trace = h->trace_logits, sv_thr = h->straggler_threshold;
     const bool sv_have = h->have_forced;
     h->force_tokens = 1; h->trace_logits = 1; h->have_forced = true; h->straggler_threshold = 0;
@@ -1088,7 +1102,7 @@ int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L
     if (rc) return rc;
     KOCR_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)L * VOCAB_PAD * 4, h->trace.p, (size_t)DEC_MAX * VOCAB_PAD * 4,
                                 (size_t)L * VOCAB_PAD * 4, B, cudaMemcpyDeviceToHost, s));
-    KOCR_CUDA(cudaStreamSynchronize(s));
+    KOCR_CUDA(wait_stream(h, s));
     return 0;
 }
 
@@ -1123,7 +1137,7 @@ int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w,
     KOCR_TRY(launch_crop_lines(d_page, page_w, channels, reinterpret_cast<const int*>(tab + off_bytes),
                                reinterpret_cast<const long long*>(tab), n_lines, pad_px, out_pixels_dev, s));
     ++g_launches;
-    KOCR_CUDA(cudaStreamSynchronize(s));        // boxes / offsets (and a pageable page) are host memory of the caller
+    KOCR_CUDA(wait_stream(h, s));        // boxes / offsets (and a pageable page) are host memory of the caller
     return 0;
 }
 
