@@ -165,3 +165,38 @@ def test_no_cpu_fallback_fails_loudly():
     from khmer_ocr_cnn_transformer_b200.recognition.model.se_model import KhmerOCR
     with pytest.raises(RuntimeError, match="no CPU path"):
         OCRPredictor("x.pth", Tokenizer(REC / "char2idx.json"), OCRConfig(device="cpu"), KhmerOCR)
+
+
+def test_resnet_variant_spec_and_packing():
+    """Third checkpoint family (model/resnet_model.py): key layout, variant detection, blob entries, BN folding of the
+    bias-free convs."""
+    from khmer_ocr_cnn_transformer_b200.checkpoint import detect_variant, RESNET_BLOCKS
+    sd = seeded_state_dict("resnet", 13)
+    assert detect_variant(sd) == "resnet" and validate_state_dict(sd)[0] == "resnet"
+    assert "cnn.layer2.1.shortcut.0.weight" not in sd and sd["cnn.layer2.0.shortcut.0.weight"].shape == (256, 128, 1, 1)
+    assert "context_bilstm.weight_ih_l0" not in sd and "cnn.conv7.weight" not in sd
+    t = weights.pack_tensors(sd)
+    assert t["meta"][1][0] == 2 and "lstm.w_ih" not in t and "conv2.w" not in t
+    for bi, (name, cin, cout) in enumerate(RESNET_BLOCKS):
+        assert t[f"res{bi}.c1.w"][1].shape == (cout, 9 * cin) and t[f"res{bi}.c2.w"][1].shape == (cout, 9 * cout)
+        assert (f"res{bi}.sc.w" in t) == (cin != cout)
+    # folded bias of a bias-free conv = beta - mean * gamma / sqrt(var + eps)
+    p = "cnn.layer3.0.bn2"
+    want = sd[p + ".bias"] - sd[p + ".running_mean"] * sd[p + ".weight"] / np.sqrt(sd[p + ".running_var"] + 1e-5)
+    assert np.allclose(t["res3.c2.b"][1], want, atol=1e-6)
+
+
+def test_textline_box_arithmetic_matches_reference_rules():
+    """textline_detection.py:17-34 / ocr_engine.py:72-76 in Python ints (host side of kocr_crop_lines)."""
+    from khmer_ocr_cnn_transformer_b200 import textline_crops as T
+
+    class Box:
+        def __init__(self, poly):
+            self.polygon = poly
+
+    class Pred:
+        bboxes = [Box([[10.9, 20.2], [99.9, 20.2], [99.9, 40.7], [10.9, 40.7]]), Box([[-3.0, 5.0], [4.0, 5.0], [4.0, 9.0], [-3.0, 9.0]]),
+                  Box([[300.0, 10.0], [310.0, 10.0], [310.0, 20.0], [300.0, 20.0]])]
+    assert T.textline_boxes((200, 100), Pred(), 5) == [(5, 15, 104, 45), (0, 0, 9, 14)]       # third box is outside: skipped
+    assert T.textline_boxes((200, 100), [p.polygon for p in Pred.bboxes], 0) == [(10, 20, 99, 40), (0, 5, 4, 9)]
+    assert T.element_boxes((200, 100), [((50, 60, 150, 90), 3), ((0, 0, 20, 10), 3)], 8) == [(0, 0, 28, 18), (42, 52, 158, 98)]
