@@ -624,7 +624,6 @@ int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
     auto key = std::make_tuple(h->n_lines, max_T, h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
-        const int64_t before = g_launches.load() + gemm_tc_launch_count();
         cudaGraph_t graph = nullptr;
         KOCR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         int rc = decode_group_eager(h, DEC_GROUP, max_T, s);
@@ -632,11 +631,17 @@ int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
         if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
         KOCR_CHECK(ce == cudaSuccess && graph != nullptr, "decode graph capture failed: %s", cudaGetErrorString(ce));
         kocr_handle::DecGraph g;
+        // kernel nodes of the graph = launches this thread "made" while capturing (the global counters are shared with the
+        // other in-flight handles' threads, so a before/after difference would over-count): captured, not launched -
+        // take them back out and count them per replay below
+        size_t n_nodes = 0;
+        cudaError_t ne = cudaGraphGetNodes(graph, nullptr, &n_nodes);
         ce = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
+        KOCR_CHECK(ne == cudaSuccess, "cudaGraphGetNodes failed: %s", cudaGetErrorString(ne));
         KOCR_CHECK(ce == cudaSuccess, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-        g.nodes = (size_t)(g_launches.load() + gemm_tc_launch_count() - before);
-        g_launches -= (int64_t)g.nodes;      // captured, not launched: counted per replay below
+        g.nodes = n_nodes;
+        g_launches -= (int64_t)g.nodes;
         if (h->dec_graphs.size() > 64) {
             for (auto& d : h->dec_graphs) cudaGraphExecDestroy(d.second.exec);
             h->dec_graphs.clear();
