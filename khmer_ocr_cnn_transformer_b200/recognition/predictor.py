@@ -84,61 +84,22 @@ class OCRPredictor:
     # ------------------------------------------------------------------------------------
     def _beam_search_batch(self, n_lines: int, beam_width: int) -> list:
         """`OCRPredictor._beam_search` (reference predictor.py:101-136) for every line of the batch whose stages 1-5a
-        have just run.  Per line exactly the reference's bookkeeping - log-softmax of the last position, top
-        `beam_width` tokens of every live hypothesis, stable sort by score, candidates ending in <eos> moved to
-        `completed` with score / len(seq), the first `beam_width` others survive, best completed (else first live)
-        hypothesis wins - while each decoder position of ALL lines' hypotheses is one GPU pass (kocr_beam_step_batch,
-        KV-cached: the reference re-runs the whole prefix)."""
+        have just run.  Each decoder position of ALL lines' hypotheses is one GPU pass (kocr_beam_step_batch, KV-cached:
+        the reference re-runs the whole prefix); log-softmax and top-k are torch's, like the reference's; the
+        candidate / pruning / completion bookkeeping is `beam.BatchedBeam` (same arithmetic and tie order, vectorised)."""
         import torch
         import torch.nn.functional as F
-        sos, eos = self.tokenizer.sos_idx, self.tokenizer.eos_idx
-        beams = [[(0.0, [sos])] for _ in range(n_lines)]
-        completed = [[] for _ in range(n_lines)]
-        prev_rows = [[0] for _ in range(n_lines)]        # row (of the previous pass) holding each live hypothesis' cache
-        first = True
+        from .beam import BatchedBeam
+        beam = BatchedBeam(n_lines, beam_width, self.tokenizer.sos_idx, self.tokenizer.eos_idx, self.cfg.decode_max_len)
         for t in range(self.cfg.decode_max_len):
-            live = [l for l in range(n_lines) if beams[l]]
-            if not live:
+            if beam.live_lines().size == 0:
                 break
-            row_line, prefixes, parents, start = [], [], [], {}
-            for l in live:
-                start[l] = len(row_line)
-                for (_, seq), pr in zip(beams[l], prev_rows[l]):
-                    row_line.append(l)
-                    prefixes.append(seq)
-                    parents.append(pr)
-            logits = self.model.beam_step_batch(row_line, np.asarray(prefixes, np.int32), None if first else parents, t)
-            first = False
+            row_line, prefixes, parents = beam.rows()
+            logits = self.model.beam_step_batch(row_line, prefixes, parents if t > 0 else None, t)
             log_probs = F.log_softmax(torch.from_numpy(logits.copy()), dim=-1)
-            # `log_probs[i].topk(beam_width)` + `.item()` of the reference (:119-122), for all rows at once: the same fp32
-            # values widened to Python floats, without ~10^5 scalar tensor reads per batch
             top_probs, top_idxs = log_probs.topk(beam_width, dim=-1)
-            top_probs, top_idxs = top_probs.tolist(), top_idxs.tolist()
-            for l in live:
-                candidates = []
-                for i, (score, seq) in enumerate(beams[l]):
-                    row = start[l] + i
-                    for k in range(beam_width):
-                        candidates.append((score + top_probs[row][k], seq + [top_idxs[row][k]], row))
-                candidates.sort(key=lambda x: x[0], reverse=True)
-                nxt, rows = [], []
-                for sc, seq, row in candidates:
-                    if seq[-1] == eos:
-                        completed[l].append((sc / len(seq), seq))
-                    elif len(nxt) < beam_width:
-                        nxt.append((sc, seq))
-                        rows.append(row)
-                # `beams = next_beams; if not beams: break` (predictor.py:131-132): an empty list ends this line; it can only
-                # be empty if every candidate ended in <eos>, so `completed` is non-empty then
-                beams[l], prev_rows[l] = nxt, rows
-        out = []
-        for l in range(n_lines):
-            if completed[l]:
-                best = sorted(completed[l], key=lambda x: x[0], reverse=True)[0][1]
-            else:
-                best = beams[l][0][1]
-            out.append(self.tokenizer.decode(best))
-        return out
+            beam.update(top_probs.numpy(), top_idxs.numpy())
+        return [self.tokenizer.decode(seq) for seq in beam.results()]
 
     def _beam_gray(self, grays, beam_width: int):
         if beam_width > 8:

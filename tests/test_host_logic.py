@@ -200,3 +200,60 @@ def test_textline_box_arithmetic_matches_reference_rules():
     assert T.textline_boxes((200, 100), Pred(), 5) == [(5, 15, 104, 45), (0, 0, 9, 14)]       # third box is outside: skipped
     assert T.textline_boxes((200, 100), [p.polygon for p in Pred.bboxes], 0) == [(10, 20, 99, 40), (0, 5, 4, 9)]
     assert T.element_boxes((200, 100), [((50, 60, 150, 90), 3), ((0, 0, 20, 10), 3)], 8) == [(0, 0, 28, 18), (42, 52, 158, 98)]
+
+
+def test_batched_beam_bookkeeping_equals_reference_loop():
+    """recognition/beam.BatchedBeam against a line-by-line transcription of the reference loop (predictor.py:104-136) on a
+    deterministic fake decoder (logits = function of the prefix), incl. score ties, early <eos>, lines that finish at
+    different positions and lines that never emit <eos>."""
+    import torch
+    import torch.nn.functional as F
+    from khmer_ocr_cnn_transformer_b200.recognition.beam import BatchedBeam
+    SOS, EOS, V, MAXLEN = 2, 3, 124, 24
+
+    def fake_logits(line, prefix):
+        rng = np.random.default_rng(abs(hash((line, tuple(int(p) for p in prefix)))) % (2 ** 32))
+        lg = np.round(rng.standard_normal(V) * 2.0, 1).astype(np.float32)        # coarse values -> frequent exact ties
+        if line % 4 != 3:                                                        # every 4th line never ends
+            lg[EOS] += 0.35 * len(prefix) - 2.0
+        else:
+            lg[EOS] = -30.0
+        return lg
+
+    def reference_loop(line, bw):
+        beams, completed = [(0.0, [SOS])], []
+        for _ in range(MAXLEN):
+            lp = F.log_softmax(torch.from_numpy(np.stack([fake_logits(line, s) for _, s in beams])), dim=-1)
+            cands = []
+            for i, (score, seq) in enumerate(beams):
+                tp, ti = lp[i].topk(bw)
+                for k in range(bw):
+                    cands.append((score + tp[k].item(), seq + [ti[k].item()]))
+            cands.sort(key=lambda x: x[0], reverse=True)
+            nxt = []
+            for sc, seq in cands:
+                if seq[-1] == EOS:
+                    completed.append((sc / len(seq), seq))
+                elif len(nxt) < bw:
+                    nxt.append((sc, seq))
+            beams = nxt
+            if not beams:
+                break
+        return sorted(completed, key=lambda x: x[0], reverse=True)[0][1] if completed else beams[0][1]
+
+    for bw in (1, 2, 3, 5):
+        n = 13
+        beam = BatchedBeam(n, bw, SOS, EOS, MAXLEN)
+        for t in range(MAXLEN):
+            if beam.live_lines().size == 0:
+                break
+            row_line, prefixes, parents = beam.rows()
+            assert prefixes.shape == (len(row_line), t + 1)
+            if t == 0:
+                assert list(row_line) == list(range(n)) and np.all(prefixes[:, 0] == SOS)
+            lg = np.stack([fake_logits(int(l), p) for l, p in zip(row_line, prefixes)])
+            tv, ti = F.log_softmax(torch.from_numpy(lg), dim=-1).topk(bw, dim=-1)
+            beam.update(tv.numpy(), ti.numpy())
+        got = beam.results()
+        for line in range(n):
+            assert got[line] == reference_loop(line, bw), (bw, line)
