@@ -5,10 +5,10 @@ Result (printed): (a) leaves all three lines identical to the oracle; (b) reprod
 EXACTLY on all three lines - the flips come from the fp16 rounding of the cross-attention K/V path, not from the CNN /
 encoder / BiLSTM upstream and not from the TF32 GEMMs; (c) operand rounding alone flips 3/3, storage rounding alone 1/3,
 a TF32 projection from fp32 memory (larger error than fp16!) 0/3 - i.e. these are chaotic near-ties (oracle margins 0.004-
-0.066 against logits of 27), not a precision ordering.    python tools/parity_rootcause.py   (about 2 minutes, CPU)"""
+0.066 against logits of 27), not a precision ordering.    python tests/parity/parity_rootcause.py   (about 2 minutes, CPU)"""
 import sys, numpy as np, time
-sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
-ROOT = __import__('pathlib').Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent.parent))
+ROOT = __import__("pathlib").Path(__file__).resolve().parent.parent.parent
 from oracle import recognizer_np as O
 from khmer_ocr_cnn_transformer_b200 import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint

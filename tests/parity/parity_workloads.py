@@ -3,13 +3,13 @@ mismatch and the CER of both sides against the ground-truth labels.
 
   workloads: c2 = the 256-line bench batch (widths 400-800, seed 0); c3 = 1024 lines of the mixed-width config
              (widths 200-1600, seed 3)
-  GPU box :  python tools/parity_c2.py dump [c2|c3]    -> gpurun_out/<w>_tokens.npz  (tokens + lengths, CUDA path)
-  anywhere:  python tools/parity_c2.py oracle [c2|c3]  -> profiles/r01/<w>_oracle_tokens.npz (numpy oracle, host cores)
-  anywhere:  python tools/parity_c2.py compare [c2|c3] -> profiles/r01/parity_<w>.json
+  GPU box :  python tests/parity/parity_workloads.py dump [c2|c3]    -> gpurun_out/<w>_tokens.npz  (tokens + lengths, CUDA path)
+  anywhere:  python tests/parity/parity_workloads.py oracle [c2|c3]  -> profiles/r01/<w>_oracle_tokens.npz (numpy oracle, host cores)
+  anywhere:  python tests/parity/parity_workloads.py compare [c2|c3] -> profiles/r01/parity_<w>.json
 """
 import json, sys, time, os
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np
 
