@@ -1,15 +1,17 @@
-// CUDA-core / HBM-bound pieces of the SE-VGG backbone (everything that is not a dense contraction):
-//   conv1 (Cin = 1, too thin for tensor cores) + BN + ReLU + 2x2 pool      se_model.py:39-40,64
-//   2x2 max-pool after conv2                                                 se_model.py:43,65
-//   SequenceSE gate (mean over H -> FC -> ReLU -> FC -> sigmoid) + (2,1) pool  se_model.py:19-30,48-49,53-54
-//   SequenceSE gate + AdaptiveAvgPool2d((2,32)) -> patch-projection operand  se_model.py:59-61,76-78
-// All activations are a16 in the padded-linear NHWC layout (common.cuh PLGeom); SE math is fp32.
+// Pieces of the backbones that are not tcgen05 GEMMs:
+//   conv1 (Cin = 1: K = 9) + BN + ReLU + 2x2 pool on mma.sync (CUDA-core version kept for A/B)   se_model.py:39-40,64
+//   2x2 max-pool after conv2                                                                       se_model.py:43,65
+//   fused SequenceSE block: mean over H -> FC -> ReLU -> FC -> sigmoid (mma.sync) -> gate * x ->
+//     (2,1) max-pool or AdaptiveAvgPool2d((2,32)) (patch-projection operand)                       se_model.py:19-30,48-61,76-78
+//   the four-kernel SE version (column means / apply+pool; the FCs then run on the GEMM) - VGG baseline pools and A/B tests
+//   16-bit -> fp32 copy for the identity shortcuts of the ResNet baseline                           resnet_model.py:17,33
+// All activations are 16-bit (act16_t) in the padded-linear NHWC layout (common.cuh PLGeom); SE math is fp32.
 #include "kernels.cuh"
 
 namespace kocr {
 
 // ------------------------------------------------------------------------------------------
-// conv1 + pool1.  grid = (4 bands of 6 pooled rows, n_chunks), block = 256.
+// conv1 + pool1 on the FP32 pipe (A/B reference of the tensor-core kernel below).  grid = (4 bands of 6 pooled rows, n_chunks), block = 256.
 // ------------------------------------------------------------------------------------------
 static constexpr int C1_BAND = 6;                 // pooled rows per CTA
 static constexpr int C1_IN_ROWS = 2 * C1_BAND + 2;

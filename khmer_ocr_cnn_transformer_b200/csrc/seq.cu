@@ -1,5 +1,7 @@
-// Sequence-side CUDA-core kernels: per-chunk attention, LayerNorm, BiLSTM recurrence, and the
-// KV-cached greedy decoder step kernels.  All softmax / LayerNorm / LSTM state math is fp32.
+// Sequence-side kernels: per-chunk attention (mma.sync; CUDA-core version kept for A/B), LayerNorm, the padded
+// memory of the teacher-forced forward, BiLSTM recurrence (mma.sync cluster kernel + CUDA-core version), and the
+// KV-cached decoder step kernels (self-attention, one-pass cross-attention, embed, argmax).  All softmax / LayerNorm /
+// LSTM state math is fp32.
 //
 // Reference ops replaced:
 //   nn.TransformerEncoderLayer self-attention over 32 tokens            se_model.py:119-126
