@@ -27,10 +27,10 @@ template <int BN, bool TF32> struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;                 // 8 / 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = TF32 ? 3 : ((BN == 256) ? 4 : 5);
+    static constexpr int NSTAGE = TF32 ? 3 : ((BN >= 192) ? 4 : 5);
     // per-epilogue-warp staging: one 4 KB tile; a second one where the fp32 addend is prefetched (16-bit, BN <= 128 only)
     static constexpr int STG_PER_WARP = (TF32 || BN == 256) ? 4096 : 8192;
-    static constexpr int TMEM_COLS = 2 * BN;                    // 128 / 256 / 512
+    static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;   // 128 / 256 / 512 (tcgen05.alloc takes powers of two)
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * STG_PER_WARP;
 };
 
@@ -395,6 +395,8 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t 
 }
 
 static std::atomic<long> g_gemm_launches{0};
+static int g_bn192 = 0;                 // 192-wide N tile for N = 1152 / 384: measured SLOWER than 128 (qkv 0.206 vs 0.161 ms), kept as an A/B option
+void set_gemm_bn192(int on) { g_bn192 = on; }
 long gemm_tc_launch_count() { return g_gemm_launches.load(); }
 
 static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
@@ -444,13 +446,15 @@ static int launch_impl(const void* a, long rowsA, const void* w, const GemmProbl
 
 int launch_gemm_tc(const void* a, long rowsA, const void* w, const GemmProblem& p, int num_sms,
                    cudaStream_t stream) {
-    const int bn = p.bn > 0 ? p.bn : (p.N % 256 == 0 ? 256 : 128);
+    // N tile: 256 where it divides N, else 128 (option gemm_bn192: 192 for N = 1152 / 384 - fewer, fatter tiles, but slower)
+    const int bn = p.bn > 0 ? p.bn : (p.N % 256 == 0 ? 256 : ((!p.tf32 && g_bn192 && p.N % 192 == 0) ? 192 : 128));
     if (p.tf32) {
         if (bn == 256) return launch_impl<256, true>(a, rowsA, w, p, num_sms, stream);
         if (bn == 128) return launch_impl<128, true>(a, rowsA, w, p, num_sms, stream);
         if (bn == 64) return launch_impl<64, true>(a, rowsA, w, p, num_sms, stream);
     } else {
         if (bn == 256) return launch_impl<256, false>(a, rowsA, w, p, num_sms, stream);
+        if (bn == 192) return launch_impl<192, false>(a, rowsA, w, p, num_sms, stream);
         if (bn == 128) return launch_impl<128, false>(a, rowsA, w, p, num_sms, stream);
     }
     KOCR_CHECK(false, "gemm: unsupported N tile %d", bn);

@@ -51,5 +51,6 @@ int launch_gemm_tc(const void* a, long rowsA, const void* w,
 int launch_gemm_simt_check(const act16_t* a, long rowsA, const act16_t* w,
                            const GemmProblem& p, cudaStream_t stream);
 long gemm_tc_launch_count();
+void set_gemm_bn192(int on);   // 1: N = 1152 / 384 16-bit GEMMs use 128 x 192 tiles (measured slower); 0 (default): 128 x 128
 
 }  // namespace kocr

@@ -941,6 +941,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "blocking_wait") == 0) { h->blocking_wait = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
+    if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
     if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }

@@ -58,6 +58,7 @@ CASES = [
     (2 * 338, 256, 9, 128, 1, (12, 25)),   # conv3-like implicit GEMM with row mask
     (5 * 104, 512, 9, 512, 1, (3, 25)),    # conv7-like, K = 4608
     (37, 128, 1, 384, 0, (0, 0)),          # decode-step sized
+    (700, 1152, 1, 384, 1, (0, 0)),        # N = 1152 = 9 x 128 (or 6 x 192 with the gemm_bn192 option)
     (148 * 128 * 2 + 77, 128, 1, 64, 0, (0, 0)),   # persistent loop: several tiles per CTA
 ]
 
