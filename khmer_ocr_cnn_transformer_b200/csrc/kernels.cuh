@@ -74,6 +74,8 @@ int launch_layernorm(const float* x, const float* g, const float* b, const float
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
                    act16_t* out_a16_lo, int rows, cudaStream_t stream);
 
+// fp32 [rows, 384] -> 16-bit [rows, 1152] = [hi | lo | hi] (split-precision GEMM operand)
+int launch_split3(const float* m, act16_t* out, long rows, cudaStream_t stream);
 // padded memory of the teacher-forced batched forward: out[b*Tmax + t] = t < T_b ? xb[src_off_b + t] : a16(global_pos[t])
 int launch_pad_memory(const act16_t* xb, const float* global_pos, const int* src_off, const int* line_T, int n_lines,
                       int Tmax, act16_t* out, cudaStream_t stream);

@@ -82,7 +82,7 @@ struct kocr_handle {
     int lstm_impl = 1;           // 1 = tensor-core recurrence (mma fragments in registers), 0 = CUDA-core / SMEM weights
     const float *dec_tok_emb, *dec_pos;
     DecLayerW dec[2];
-    const act16_t* dec_kv_w; const float* dec_out_w; const float *dec_kv_b, *dec_out_b;
+    const act16_t* dec_kv_w; const act16_t* dec_kv_w3; const float* dec_out_w; const float *dec_kv_b, *dec_out_b;
     // workspace
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
@@ -110,6 +110,7 @@ struct kocr_handle {
     bool decode_warmed = false;
     int use_graphs = 1;
     int use_pdl = 1;             // programmatic dependent launch inside the decode loop
+    int kv_split = 1;            // cross-attention K/V projection in split precision (hi + lo operands, K = 3 x 384)
     int blocking_wait = 0;       // 1: host waits sleep on a blocking-sync event (many handles / host threads per process)
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
@@ -235,6 +236,7 @@ int resolve_weights(kocr_handle* h) {
         snprintf(nm, sizeof nm, "dec%d.n3_b", l); W_F32(d.n3_b, nm, D);
     }
     W_A16(h->dec_kv_w, "dec.ca_kv_w", 4 * D * D);
+    W_A16(h->dec_kv_w3, "dec.ca_kv_w3", 4 * D * 3 * D);
     W_F32(h->dec_kv_b, "dec.ca_kv_b", 4 * D);
     W_F32(h->dec_out_w, "dec.out_w", VOCAB_PAD * D);
     W_F32(h->dec_out_b, "dec.out_b", VOCAB_PAD);
@@ -269,7 +271,7 @@ int carve_workspace(kocr_handle* h) {
         {"se_mean", NC * 25 * 512 * 2},  {"se_z", NC * 25 * 128 * 2},   {"se_gate", NC * 25 * 512 * 4},
         {"x", M * D * 4},   {"xb", M * D * 2},  {"qkv", M * 3 * D * 2}, {"ao", M * D * 2}, {"y", M * D * 4},
         {"hff", M * 1024 * 2},
-        {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2},
+        {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2}, {"kv_a3", M * 3 * D * 2},
         {"vtab", L * (size_t)preprocess_vtab_ints_per_line() * 4},
         {"tokens", L * KOCR_TOKENS_LD * 4}, {"forced", L * KOCR_TOKENS_LD * 4}, {"lengths", L * 4},
         {"finished", L * 4}, {"n_active", (DEC_MAX + 1) * 4}, {"step_base", 64},
@@ -514,6 +516,21 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     return 0;
 }
 
+// Cross-attention K/V of both decoder layers for `rows` memory rows (once per line: depends only on the memory).
+// mem_f32 / memb: the same memory in fp32 and in 16 bits.
+int project_cross_kv(kocr_handle* h, long rows, const float* mem_f32, const act16_t* memb, cudaStream_t s) {
+    GemmEpilogue e = ep_none();
+    e.bias = h->dec_kv_b; e.out_a16 = buf<act16_t>(h, "kv"); e.ld_a16 = 4 * D_MODEL;
+    if (h->kv_split) {
+        act16_t* a3 = buf<act16_t>(h, "kv_a3");
+        TIMED("cross_kv_split", 0, launch_split3(mem_f32, a3, rows, s)); ++g_launches;
+        TIMED("cross_kv_proj", 2.0 * rows * D_MODEL * 4 * D_MODEL, gemm_linear(h, a3, rows, h->dec_kv_w3, 4 * D_MODEL, 3 * D_MODEL, e, s));
+    } else {
+        TIMED("cross_kv_proj", 2.0 * rows * D_MODEL * 4 * D_MODEL, gemm_linear(h, memb, rows, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
+    }
+    return 0;
+}
+
 int stage_memory(kocr_handle* h, cudaStream_t s) {
     const long M = h->n_tok;
     if (M == 0) return 0;
@@ -531,11 +548,7 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
         ++g_launches;
         memb = buf<act16_t>(h, "memb");
     }
-    // cross-attention K/V of both decoder layers, once per line (depends only on the memory)
-    GemmEpilogue e = ep_none();
-    e.bias = h->dec_kv_b; e.out_a16 = buf<act16_t>(h, "kv"); e.ld_a16 = 4 * D_MODEL;
-    TIMED("cross_kv_proj", 2.0 * M * D_MODEL * 4 * D_MODEL, gemm_linear(h, memb, M, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));
-    return 0;
+    return project_cross_kv(h, M, buf<float>(h, h->variant == 0 ? "mem" : "x"), memb, s);
 }
 
 // Decoder GEMM for a handful of rows: TF32, 128x64 tiles and split-K so that ~50-100 CTAs each stream one
@@ -940,6 +953,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "blocking_wait") == 0) { h->blocking_wait = value; return 0; }
+    if (strcmp(name, "kv_split") == 0) { h->kv_split = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
     if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
     if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
@@ -1086,7 +1100,9 @@ int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L
         ++g_launches;
         memb = buf<act16_t>(h, "memb");
     }
-    {
+    if (h->variant == 0) {
+        KOCR_TRY(project_cross_kv(h, rows, buf<float>(h, "mem"), memb, s));
+    } else {        // the padded memory of the baselines exists in 16 bits only: plain 16-bit projection
         GemmEpilogue e = ep_none();
         e.bias = h->dec_kv_b; e.out_a16 = buf<act16_t>(h, "kv"); e.ld_a16 = 4 * D_MODEL;
         KOCR_TRY(gemm_linear(h, memb, rows, h->dec_kv_w, 4 * D_MODEL, D_MODEL, e, s));

@@ -332,6 +332,40 @@ int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* 
     return 0;
 }
 
+// Split-precision operand of the cross-attention K/V projection: row = [hi | lo | hi] with hi = a16(m), lo = a16(m - hi).
+// Against weights packed as [w_hi | w_hi | w_lo] one 16-bit GEMM with K = 3 * 384 computes hi*w_hi + lo*w_hi + hi*w_lo,
+// i.e. the fp32 product to ~20 bits - the 16-bit rounding of memory and weights in this one projection is what flips
+// near-tied argmaxes against the fp32 reference (tests/parity/parity_rootcause.py).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ m, act16_t* __restrict__ out, long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    constexpr int CG = D_MODEL / 8;
+    const int cg = (int)(idx % CG);
+    const long row = idx / CG;
+    const float4 a = reinterpret_cast<const float4*>(m + row * D_MODEL)[2 * cg];
+    const float4 b = reinterpret_cast<const float4*>(m + row * D_MODEL)[2 * cg + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = pack_a16(v[2 * j], v[2 * j + 1]);
+        lo[j] = pack_a16(v[2 * j] - a16_lo(hi[j]), v[2 * j + 1] - a16_hi(hi[j]));
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + row * (3 * D_MODEL));
+    const uint4 h4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    o[cg] = h4;
+    o[CG + cg] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    o[2 * CG + cg] = h4;
+}
+
+int launch_split3(const float* m, act16_t* out, long rows, cudaStream_t stream) {
+    const long total = rows * (D_MODEL / 8);
+    if (total == 0) return 0;
+    split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(m, out, total);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Training-time memory layout of KhmerOCR.forward (se_model.py:262-273): every line padded to Tmax rows; real rows are
 // the merged encoder output + global_pos (already in `xb`), pad rows are 0 + global_pos[t].  One thread per 8 channels.
 __global__ void __launch_bounds__(256) pad_memory_kernel(const act16_t* __restrict__ xb, const float* __restrict__ global_pos,

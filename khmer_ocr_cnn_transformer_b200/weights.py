@@ -218,7 +218,11 @@ def pack_tensors(sd: dict) -> dict:
         tf32(f"dec{l}.l2_w", sd[p + "linear2.weight"]); f32(f"dec{l}.l2_b", sd[p + "linear2.bias"])
         for k in (1, 2, 3):
             f32(f"dec{l}.n{k}_g", sd[p + f"norm{k}.weight"]); f32(f"dec{l}.n{k}_b", sd[p + f"norm{k}.bias"])
-    bf16("dec.ca_kv_w", np.concatenate(kv_w, 0))
+    kvw = np.concatenate(kv_w, 0).astype(np.float32)
+    bf16("dec.ca_kv_w", kvw)
+    # split-precision copy for the K = 3 x 384 projection: [w_hi | w_hi | w_lo] against operand rows [hi | lo | hi]
+    w_hi = a16_bits_to_f32(f32_to_a16_bits(kvw)).reshape(kvw.shape)
+    bf16("dec.ca_kv_w3", np.concatenate([w_hi, w_hi, kvw - w_hi], 1))
     f32("dec.ca_kv_b", np.concatenate(kv_b, 0))
     ow = np.zeros((128, D), np.float32); ow[:vocab] = sd["dec.out_proj.weight"]
     ob = np.zeros(128, np.float32); ob[:vocab] = sd["dec.out_proj.bias"]

@@ -1,4 +1,5 @@
-"""Root cause of the three c3 token mismatches (profiles/r01/parity_c3.json): CPU emulation of the CUDA path's roundings
+"""Root cause of the three c3 token mismatches of the all-fp16 build (before the split-precision K/V projection; lines 345,
+622, 848 of the c3 sample - with the fix only 622 remains, profiles/r01/parity_c3.json): CPU emulation of the CUDA path's roundings
 inside the numpy oracle (test tooling; imports oracle/).  With exact fp32 memory the decoder is re-run with (a) TF32
 linears, (b) + 16-bit memory operand / weights and 16-bit K/V storage of the cross-attention, (c) each of those alone.
 Result (printed): (a) leaves all three lines identical to the oracle; (b) reproduces the CUDA path's token sequences
@@ -16,7 +17,7 @@ from threadpoolctl import threadpool_limits
 sd = load_checkpoint(str(ROOT / 'tests/golden/fixture_se_ckpt.npz'))
 imgs = synth.make_lines(1024, 200, 1600, seed=3)[0]
 orc = np.load(str(ROOT / 'profiles/r01/c3_oracle_tokens.npz'))
-gpu = np.load(str(ROOT / 'profiles/r01/c3_cuda_tokens.npz'))
+gpu = np.load(str(ROOT / 'profiles/r01/c3_cuda_tokens_fp16_kv.npz'))      # tokens of the build WITHOUT the fix
 lines = [345, 622, 848]
 
 def trunc_tf32(x):
