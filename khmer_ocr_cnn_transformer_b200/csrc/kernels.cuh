@@ -110,5 +110,8 @@ int launch_dec_argmax(const float* logits /*[L,128]*/, int* tokens, int* lengths
                       const int* step_base, int step_off, int n_lines, const int* forced, float* trace,
                       cudaStream_t stream, int nsplit, const float* bias);
 int launch_dec_bump(int* step_base, int n, cudaStream_t stream);
+// row compaction of the greedy loop: pairs = int2 (src row in the tail, dst row in the head), see seq.cu
+int launch_decode_compact(const int* pairs, int n_pairs, int t, float* kcache, float* vcache, size_t layer_stride, int* tokens,
+                          int* lengths, int* finished, int* tok_off, int* line_T, cudaStream_t stream);
 
 }  // namespace kocr

@@ -332,6 +332,51 @@ int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* 
     return 0;
 }
 
+static constexpr int TOK_LD = DEC_MAX + 1;        // ints per row of the token table (<sos> + 256 ids)
+
+// Row compaction of the greedy decode loop.  Once half of the lines of a batch have emitted <eos>, the still-active
+// rows of the tail [A, n_rows) are swapped into the finished rows ("holes") of the head [0, A), A = active count rounded
+// up to the 128-row GEMM tile, and the loop continues with A rows: the 13 GEMMs of a position lose an M tile, the
+// attention / LayerNorm grids shrink.  pairs[i] = (src row in the tail, dst row in the head); the two sets are disjoint.
+// grid = (n_pairs, 5): y < 4 copies the live part [0, t) of one self-attention cache plane (layer, K|V) src -> dst (the
+// hole's cache is dead); y == 4 swaps the small per-row state so that the finished line keeps its result in the tail.
+__global__ void __launch_bounds__(256) decode_compact_kernel(const int2* __restrict__ pairs, int t, float* __restrict__ kcache,
+                                                             float* __restrict__ vcache, size_t layer_stride,
+                                                             int* __restrict__ tokens, int* __restrict__ lengths,
+                                                             int* __restrict__ finished, int* __restrict__ tok_off,
+                                                             int* __restrict__ line_T) {
+    const int2 pr = pairs[blockIdx.x];
+    const int src = pr.x, dst = pr.y;
+    if (blockIdx.y < 4) {
+        float* base = ((blockIdx.y & 1) ? vcache : kcache) + (size_t)(blockIdx.y >> 1) * layer_stride;
+        const float4* s4 = reinterpret_cast<const float4*>(base + (size_t)src * DEC_MAX * D_MODEL);
+        float4* d4 = reinterpret_cast<float4*>(base + (size_t)dst * DEC_MAX * D_MODEL);
+        for (int i = threadIdx.x; i < t * (D_MODEL / 4); i += blockDim.x) d4[i] = s4[i];
+    } else {
+        for (int i = threadIdx.x; i < TOK_LD; i += blockDim.x) {
+            const int a = tokens[(size_t)src * TOK_LD + i], b = tokens[(size_t)dst * TOK_LD + i];
+            tokens[(size_t)src * TOK_LD + i] = b;
+            tokens[(size_t)dst * TOK_LD + i] = a;
+        }
+        if (threadIdx.x == 0) {
+            int a;
+            a = lengths[src]; lengths[src] = lengths[dst]; lengths[dst] = a;
+            a = finished[src]; finished[src] = finished[dst]; finished[dst] = a;
+            a = tok_off[src]; tok_off[src] = tok_off[dst]; tok_off[dst] = a;
+            a = line_T[src]; line_T[src] = line_T[dst]; line_T[dst] = a;
+        }
+    }
+}
+
+int launch_decode_compact(const int* pairs, int n_pairs, int t, float* kcache, float* vcache, size_t layer_stride, int* tokens,
+                          int* lengths, int* finished, int* tok_off, int* line_T, cudaStream_t stream) {
+    if (n_pairs == 0) return 0;
+    decode_compact_kernel<<<dim3(n_pairs, 5), 256, 0, stream>>>(reinterpret_cast<const int2*>(pairs), t, kcache, vcache, layer_stride,
+                                                               tokens, lengths, finished, tok_off, line_T);
+    KOCR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Split-precision operand of the cross-attention K/V projection: row = [hi | lo | hi] with hi = a16(m), lo = a16(m - hi).
 // Against weights packed as [w_hi | w_hi | w_lo] one 16-bit GEMM with K = 3 * 384 computes hi*w_hi + lo*w_hi + hi*w_lo,
 // i.e. the fp32 product to ~20 bits - the 16-bit rounding of memory and weights in this one projection is what flips
@@ -703,7 +748,6 @@ int launch_bilstm_mma(const float* gin, const act16_t* whh_mma, const int* line_
 // Decoder step kernels (one launch each per generated position t, batched over lines).
 // tokens: int32 [n_lines, DEC_MAX + 1]; tokens[l][0] = <sos>.
 // ------------------------------------------------------------------------------------------
-static constexpr int TOK_LD = DEC_MAX + 1;
 
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_base, int step_off,
                                  const float* __restrict__ tok_emb,
