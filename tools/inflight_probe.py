@@ -22,7 +22,7 @@ from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
 ROOT = Path(__file__).resolve().parent.parent
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 36
-OPTS = dict(a.split("=") for a in sys.argv[3:])          # e.g. big_gemm_sms=132 dec_wide=0 straggler_threshold=8
+OPTS = dict(a.split("=") for a in sys.argv[3:])          # e.g. use_pdl=0 dec_wide=0 straggler_threshold=8 compact_rows=1
 
 blob = weights.pack_blob(load_checkpoint(ROOT / "tests/golden/fixture_se_ckpt.npz"))
 
@@ -33,9 +33,10 @@ class W:
         self.batch = _native.LineBatch(self.imgs)
         self.rec = _native.Recognizer(blob, max_lines=256, max_chunks=2816)
         self.rec.set_option("dec_wide", int(OPTS.get("dec_wide", 0)))
-        self.rec.set_option("big_gemm_sms", int(OPTS.get("big_gemm_sms", 132)))
+        self.rec.set_option("big_gemm_sms", int(OPTS.get("big_gemm_sms", 0)))
         self.rec.set_option("straggler_threshold", int(OPTS.get("straggler_threshold", 8)))
-        for k in ("use_graphs", "use_pdl", "dec_cross_impl"):
+        self.rec.set_option("blocking_wait", 1 if S > 1 else 0)
+        for k in ("use_graphs", "use_pdl", "dec_cross_impl", "compact_rows", "kv_split"):
             if k in OPTS:
                 self.rec.set_option(k, int(OPTS[k]))
         self.stream = torch.cuda.Stream()
