@@ -53,6 +53,7 @@ struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; con
 // Fused SE block: squeeze + FC1/ReLU + FC2/sigmoid + gate*x + pool in one kernel, one CTA per chunk (W = 25).
 int launch_se_fused(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks, int H, int W, int C,
                     bool final_pool, cudaStream_t stream);
+void set_se_staged(int on);   // 1: the fused SE kernel stages the chunk in shared memory (no faster); 0 (default): reads global memory twice
 int launch_se_col_mean(const act16_t* in, act16_t* means, int n_chunks, int H, int W, int C,
                        cudaStream_t stream);
 int launch_se_apply_pool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H, int W,

@@ -1019,6 +1019,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "kv_split") == 0) { h->kv_split = value; return 0; }
     if (strcmp(name, "compact_rows") == 0) { h->compact_rows = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
+    if (strcmp(name, "se_staged") == 0) { set_se_staged(value); return 0; }                               // process-wide
     if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
     if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide

@@ -295,3 +295,21 @@ def test_conv1_tensor_core_kernel_agrees_with_cuda_core_kernel(rec_seeded_se):
     err = rel_err(got[1][0], got[0][0])
     _report("conv1_mma_vs_fp32_rel_err", err)
     assert err < 2e-3, err
+
+
+def test_se_staged_variant_is_bit_identical(rec_seeded_se):
+    """Option se_staged (chunk copied to shared memory with cp.async, one CTA per SM): same arithmetic, same bits."""
+    from khmer_ocr_cnn_transformer_b200 import _native
+    rec, _ = rec_seeded_se
+    imgs = _lines(5, 100, 1200, seed=24)
+    got = {}
+    try:
+        for mode in (0, 1):
+            rec.set_option("se_staged", mode)
+            rec.gather_chunks(_native.LineBatch(imgs))
+            rec.sevgg_encoder_forward()
+            got[mode] = {k: rec.debug_read(k).copy() for k in ("pool3", "pool4", "patch_in")}
+    finally:
+        rec.set_option("se_staged", 0)
+    for k in got[0]:
+        assert np.array_equal(got[0][k], got[1][k]), k
