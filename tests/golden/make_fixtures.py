@@ -10,6 +10,7 @@ tests, `smoke()` or `bench.py` runs this; they read the files it wrote.
   python tests/golden/make_fixtures.py crops     # golden_crops.npz  (Pillow crop / paste / convert('L') of a page)
   python tests/golden/make_fixtures.py forward   # golden_forward.npz (reference KhmerOCR.forward, teacher forcing)
   python tests/golden/make_fixtures.py resnet    # golden_resnet.npz  (reference ResNet-Transformer baseline, seeded init)
+  python tests/golden/make_fixtures.py vggfix    # golden_vgg_trained.npz (reference VGG baseline, trained fixture_vgg_ckpt.npz)
 
 Why a trained checkpoint: with default random init the reference's decoder output is
 input-independent and top-1/top-2 logit gaps are ~1e-3, so token-level parity under bf16 would be
@@ -384,6 +385,59 @@ def stage_resnet(args):
     print("golden_resnet.npz", f"{(HERE / 'golden_resnet.npz').stat().st_size/1e6:.2f} MB")
 
 
+def stage_vggfix(args):
+    """Baseline VGG-Transformer (BASELINE config c5) with a TRAINED fixture (tools/train_fixture_gpu.py --variant vgg):
+    memory, greedy tokens and texts of the reference's own VGG class + OCRPredictor on short scene-text-like lines."""
+    import torch
+    from PIL import Image
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    sys.path.insert(0, str(REF))
+    from netra_ocr.recognition.config import OCRConfig
+    from netra_ocr.recognition.predictor import OCRPredictor
+    from netra_ocr.recognition.tokenizer import Tokenizer
+    from netra_ocr.recognition.model.vgg_model import KhmerOCR as VGG
+    torch.set_num_threads(args.threads)
+    sd = load_checkpoint(HERE / "fixture_vgg_ckpt.npz")
+    tmp = Path("/tmp/fixture_vgg.pth")
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, tmp)
+    cfg = OCRConfig(device="cpu", max_seq_len=MAX_GLOBAL_LEN)
+    tok = Tokenizer(REF / "netra_ocr/recognition/char2idx.json")
+    pred = OCRPredictor(tmp, tok, cfg, VGG)
+    bank = synth.WordBank()
+    imgs, lbls = synth.make_lines(8, 100, 320, seed=55, bank=bank)          # first lines of the c5 test batch
+    imgs2, lbls2 = synth.make_lines(2, 500, 900, seed=56, bank=bank)
+    imgs, lbls = imgs + imgs2, lbls + lbls2
+    g = {"n_lines": np.asarray(len(imgs))}
+    texts = pred.predict_batch([Image.fromarray(i) for i in imgs], beam_width=1, batch_size=4)
+    for li, im in enumerate(imgs):
+        chunks = pred.preprocessor.process(Image.fromarray(im))
+        with torch.no_grad():
+            f = pred.model.cnn(chunks)
+            p = pred.model.patch(f)[0]
+            e = pred.model.enc(p.transpose(0, 1).contiguous()).transpose(0, 1)
+            mem = e.reshape(1, -1, 384) + pred.model.global_pos[: e.shape[0] * 32].unsqueeze(0)
+            gen = [2]
+            mask = torch.zeros((1, mem.shape[1]), dtype=torch.bool)
+            for _ in range(cfg.decode_max_len):
+                lg = pred.model.dec(torch.LongTensor([gen]), mem, mask)
+                nx = int(torch.argmax(lg[0, -1]).item())
+                if nx == 3:
+                    break
+                gen.append(nx)
+        assert tok.decode(gen) == texts[li]
+        g[f"img{li}"] = im
+        g[f"mem{li}"] = mem[0].numpy().astype(np.float32)
+        g[f"tokens{li}"] = np.asarray(gen, np.int32)
+        g[f"label{li}"] = lbls[li]
+    g["texts"] = np.asarray(texts)
+    from oracle import recognizer_np as O
+    idx2char = {v: k for k, v in build_vocab().items()}
+    cers = [O.cer(texts[i], O.tokens_to_text([int(t) for t in lbls[i]], idx2char)) for i in range(len(imgs))]
+    print("reference VGG on the trained fixture: CER per line", [round(c, 3) for c in cers], flush=True)
+    np.savez_compressed(HERE / "golden_vgg_trained.npz", **g)
+    print("golden_vgg_trained.npz", f"{(HERE / 'golden_vgg_trained.npz').stat().st_size/1e6:.2f} MB")
+
+
 def stage_crops(args):
     """Input-side goldens.  netra_ocr/textline_detection.py imports surya (absent here), so the ten lines of
     `extract_textline_crops` (:17-47) are restated with the SAME Pillow calls - Image.crop, Image.new("RGB", ..., white),
@@ -441,7 +495,7 @@ def stage_crops(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("stage", choices=["bank", "train", "golden", "crops", "forward", "resnet"])
+    ap.add_argument("stage", choices=["bank", "train", "golden", "crops", "forward", "resnet", "vggfix"])
     ap.add_argument("--words-per-group", type=int, default=36)
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--batch", type=int, default=8)
@@ -449,4 +503,4 @@ if __name__ == "__main__":
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--threads", type=int, default=6)
     a = ap.parse_args()
-    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops, "forward": stage_forward, "resnet": stage_resnet}[a.stage](a)
+    {"bank": stage_bank, "train": stage_train, "golden": stage_golden, "crops": stage_crops, "forward": stage_forward, "resnet": stage_resnet, "vggfix": stage_vggfix}[a.stage](a)

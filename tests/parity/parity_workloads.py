@@ -2,7 +2,7 @@
 mismatch and the CER of both sides against the ground-truth labels.
 
   workloads: c2 = the 256-line bench batch (widths 400-800, seed 0); c3 = 1024 lines of the mixed-width config
-             (widths 200-1600, seed 3)
+             (widths 200-1600, seed 3); c3full = all 8192 lines of that config (the oracle takes about an hour on 8 cores)
   GPU box :  python tests/parity/parity_workloads.py dump [c2|c3]    -> gpurun_out/<w>_tokens.npz  (tokens + lengths, CUDA path)
   anywhere:  python tests/parity/parity_workloads.py oracle [c2|c3]  -> profiles/r01/<w>_oracle_tokens.npz (numpy oracle, host cores)
   anywhere:  python tests/parity/parity_workloads.py compare [c2|c3] -> profiles/r01/parity_<w>.json
@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT))
 import numpy as np
 
 WL = sys.argv[2] if len(sys.argv) > 2 else "c2"
-SPEC = {"c2": (256, 400, 800, 0), "c3": (1024, 200, 1600, 3)}[WL]
+SPEC = {"c2": (256, 400, 800, 0), "c3": (1024, 200, 1600, 3), "c3full": (8192, 200, 1600, 3)}[WL]
 ORACLE_NPZ = ROOT / "profiles" / "r01" / f"{WL}_oracle_tokens.npz"
 GPU_NPZ = ROOT / "gpurun_out" / f"{WL}_tokens.npz"
 

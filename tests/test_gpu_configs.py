@@ -98,3 +98,42 @@ def test_c5_vgg_baseline_batch_1024():
             cur += int(counts[i])
     finally:
         rec.close()
+
+
+def test_c5_vgg_trained_fixture_tokens_batch_1024():
+    """BASELINE config c5 with a TRAINED VGG fixture (tools/train_fixture_gpu.py --variant vgg; the reference's VGG class reads
+    the synthetic lines with CER 0): batch of 1024 short lines - tokens identical to the reference's own greedy outputs on
+    the golden lines, identical to the oracle on a sample, CER against the labels reported."""
+    from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import build_vocab
+    from oracle import recognizer_np as O
+    ck, gp = GOLDEN / "fixture_vgg_ckpt.npz", GOLDEN / "golden_vgg_trained.npz"
+    if not (ck.exists() and gp.exists()):
+        pytest.skip("trained VGG fixture not generated")
+    z = np.load(gp)
+    sd = load_checkpoint(ck)
+    rec = _native.Recognizer(weights.pack_blob(sd), max_lines=1024, max_chunks=4096)
+    try:
+        assert rec.variant == 1
+        imgs, labels = synth.make_lines(1024, 100, 320, seed=55)
+        tok, ln = rec.recognize_lines(_native.LineBatch(imgs))
+        for i in range(8):                                           # golden lines 0..7 are the first lines of this batch
+            assert np.array_equal(z[f"img{i}"], imgs[i])
+            assert np.array_equal(tok[i, :ln[i]], z[f"tokens{i}"]), i
+        sample = list(range(8, 1024, 64))
+        want = O.recognise_lines(sd, [imgs[i] for i in sample], "vgg")
+        same = [np.array_equal(tok[i, :ln[i]], np.asarray(w)) for i, w in zip(sample, want)]
+        idx2char = {v: k for k, v in build_vocab().items()}
+        cer = float(np.mean([O.cer(O.tokens_to_text([int(t) for t in tok[i, :ln[i]]], idx2char),
+                                   O.tokens_to_text([int(t) for t in labels[i]], idx2char)) for i in range(256)]))
+        from test_gpu_stages import _report
+        _report("c5_vgg_trained", {"oracle_sample_same": int(sum(same)), "of": len(same), "mean_cer_vs_labels_256": cer})
+        assert all(same), same
+        assert cer < 0.02
+        long_imgs = [z["img8"], z["img9"]]                          # two longer lines (500-900 px) of the golden
+        t2, l2 = rec.recognize_lines(_native.LineBatch(long_imgs))
+        for j, i in enumerate((8, 9)):
+            assert np.array_equal(t2[j, :l2[j]], z[f"tokens{i}"])
+    finally:
+        rec.close()

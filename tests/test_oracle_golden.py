@@ -182,3 +182,16 @@ def test_resnet_baseline_against_reference_outputs():
         toks = O.greedy_decode(sd, mem, max_len=24)
         want = [int(t) for t in z[f"tokens{i}"]]
         assert toks[:len(want)] == want[:len(toks)]
+
+
+def test_vgg_trained_fixture_against_reference_outputs():
+    """oracle 'vgg' variant on the TRAINED VGG fixture == the reference's VGG class + OCRPredictor (memory, greedy tokens)."""
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    z = _need("golden_vgg_trained.npz")
+    sd = load_checkpoint(GOLDEN / "fixture_vgg_ckpt.npz")
+    for i in (0, 3, 8):
+        chunks = O.preprocess_gray(z[f"img{i}"])[1]
+        enc = O.encoder_forward(sd, O.patch_forward(sd, O.cnn_forward(sd, chunks, "vgg")))
+        mem = O.memory_for_line(sd, enc, "vgg")
+        assert rel_err(mem, z[f"mem{i}"]) < 1e-4
+        assert O.greedy_decode(sd, mem) == [int(t) for t in z[f"tokens{i}"]]

@@ -116,16 +116,19 @@ def column_se(P, x, name):
 
 
 def backbone(P, x, train):
+    se = "cnn.se3.fc.0.weight" in P            # SE-VGG (se_model.py:63-79) or the plain VGG baseline (vgg_model.py:50-59)
     x = F.max_pool2d(conv_bn_relu(P, x, "cnn.conv1.0", "cnn.conv1.1", train), 2)
     x = F.max_pool2d(conv_bn_relu(P, x, "cnn.conv2.0", "cnn.conv2.1", train), 2)
     x = conv_bn_relu(P, x, "cnn.conv3.0", "cnn.conv3.1", train)
     x = conv_bn_relu(P, x, "cnn.conv4.0", "cnn.conv4.1", train)
-    x = F.max_pool2d(column_se(P, x, "cnn.se3"), (2, 1))
+    x = F.max_pool2d(column_se(P, x, "cnn.se3") if se else x, (2, 1))
     x = conv_bn_relu(P, x, "cnn.conv5.0", "cnn.conv5.1", train)
     x = conv_bn_relu(P, x, "cnn.conv6.0", "cnn.conv6.1", train)
-    x = F.max_pool2d(column_se(P, x, "cnn.se4"), (2, 1))
-    x = conv_bn_relu(P, x, "cnn.conv7", "cnn.bn7", train)
-    x = column_se(P, x, "cnn.se5")
+    x = F.max_pool2d(column_se(P, x, "cnn.se4") if se else x, (2, 1))
+    if se:
+        x = column_se(P, conv_bn_relu(P, x, "cnn.conv7", "cnn.bn7", train), "cnn.se5")
+    else:
+        x = F.conv2d(x, P["cnn.conv7.weight"], P["cnn.conv7.bias"], padding=1)      # bare conv7 (vgg_model.py:57)
     return F.adaptive_avg_pool2d(x, (2, 32))
 
 
@@ -171,7 +174,9 @@ def memory_of(P, flat, counts, train, lstm, packed=True):
         cur += c
     mem = mem + P["global_pos"][:Tm]
     lens_t = torch.tensor(lens)
-    if packed:
+    if lstm is None:                             # VGG baseline: the merged sequence + global_pos is the memory
+        pass
+    elif packed:
         pk = torch.nn.utils.rnn.pack_padded_sequence(mem, lens_t, batch_first=True, enforce_sorted=False)
         out, _ = lstm(pk)
         mem, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=Tm)
@@ -207,6 +212,8 @@ def make_tables(sd, device):
         if not (k.endswith("running_mean") or k.endswith("running_var")):
             t.requires_grad_(True)
         P[k] = t
+    if LSTM_KEYS[0] not in P:
+        return P, None
     lstm = torch.nn.LSTM(D, D // 2, 1, batch_first=True, bidirectional=True).to(device)
     with torch.no_grad():
         for k in LSTM_KEYS:
@@ -297,6 +304,7 @@ def main():
     ap.add_argument("--tok-drop", type=float, default=0.3)
     ap.add_argument("--short-frac", type=float, default=0.25, help="fraction of the budget spent on short lines only")
     ap.add_argument("--seed", type=int, default=17)
+    ap.add_argument("--variant", default="se", choices=["se", "vgg"], help="architecture when starting from the seeded init")
     ap.add_argument("--device", default="cuda")
     a = ap.parse_args()
     if a.check:
@@ -306,7 +314,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = False
     torch.manual_seed(0)
-    sd = load_checkpoint(a.init) if a.init else seeded_state_dict("se", seed=7, max_global_len=1024)
+    sd = load_checkpoint(a.init) if a.init else seeded_state_dict(a.variant, seed=7, max_global_len=1024)
     P, lstm = make_tables(sd, device)
     params = [v for v in P.values() if v.requires_grad]
     # auxiliary CTC head on the memory (NOT part of the checkpoint): makes the encoder + BiLSTM produce character
