@@ -9,7 +9,7 @@
  * a non-zero status on failure; kocr_last_error() then returns a thread-local message.  Nothing
  * throws across the boundary.  A handle owns its device weights and workspace, is bound to one
  * GPU, and must be used from one host thread at a time.  `stream` is a cudaStream_t passed as
- * void* (NULL = the legacy default stream).  There is NO CPU fallback: without a CUDA device every
+ * void* (NULL = a stream owned by the handle).  There is NO CPU fallback: without a CUDA device every
  * compute entry fails with an error.
  */
 #ifndef KOCR_H_
@@ -34,7 +34,8 @@ int kocr_abi_version(void);
 const char* kocr_last_error(void);
 
 /* Build a recogniser from a packed weight blob (see khmer_ocr_cnn_transformer_b200/weights.py:
- * reference state_dict -> BN-folded, K-major bf16 GEMM operands + fp32 vectors).
+ * reference state_dict -> BN-folded, K-major 16-bit (fp16) GEMM operands + fp32 vectors; a blob packed for the other
+ * 16-bit format of a -DKOCR_A16_BF16 build is rejected).
  * Replaces OCRPredictor.__init__/_load_weights (predictor.py:13-46).
  * max_lines / max_chunks bound one batch; the workspace is allocated here, once. */
 int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_lines, int max_chunks,
@@ -44,7 +45,7 @@ int kocr_destroy(kocr_handle* h);
 /* Bytes of device memory held by the handle (weights + workspace). */
 size_t kocr_workspace_bytes(const kocr_handle* h);
 
-/* Model facts read from the blob: variant (0 = SE-VGG + BiLSTM, 1 = VGG baseline), emb_dim,
+/* Model facts read from the blob: variant (0 = SE-VGG + BiLSTM, 1 = VGG baseline, 2 = ResNet baseline), emb_dim,
  * max_seq_len (global_pos rows), decode_max_len, vocab size.  (utils.py:14-43 autodetect_config) */
 int kocr_model_info(const kocr_handle* h, int* variant, int* emb_dim, int* max_seq_len, int* decode_max_len,
                     int* vocab_size);
@@ -60,12 +61,12 @@ int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes
                        int32_t* chunk_counts_out, void* stream);
 
 /* Stages 2-4 - model.cnn -> model.patch -> model.enc on all chunks of the batch
- * (predictor.py:166-170; se_model.py:63-79,104-117,119-126), then merge + global_pos
- * (predictor.py:174-183).  Consumes the chunks left by kocr_gather_chunks. */
+ * (predictor.py:166-170; se_model.py:63-79,104-117,119-126; vgg_model.py:50-59 / resnet_model.py:75-91 for the
+ * baselines), then merge + global_pos (predictor.py:174-183).  Consumes the chunks left by kocr_gather_chunks. */
 int kocr_sevgg_encoder_forward(kocr_handle* h, void* stream);
 
 /* Stage 5a - context_bilstm over each line's merged sequence (predictor.py:185-186;
- * se_model.py:228-234) and the decoder's cross-attention K/V precompute.  For the VGG baseline
+ * se_model.py:228-234) and the decoder's cross-attention K/V precompute.  For the VGG / ResNet baselines
  * (no BiLSTM) the merged sequence is the memory. */
 int kocr_merge_bilstm_forward(kocr_handle* h, void* stream);
 
@@ -90,6 +91,8 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
  *                       cross-attention K/V projection instead of the split-precision one
  *   "blocking_wait" 1 -> host waits inside the calls sleep (blocking-sync event) instead of spinning: for processes that
  *                        keep many handles / host threads in flight (bench.py sets it when --in-flight > 1)
+ *   A/B switches of kernel variants (process-wide): "se_fused", "se_staged", "conv1_impl", "chunk_attn_impl",
+ *                        "dec_cross_impl", "gemm_bn192", "dec_wide", "use_pdl" - see DESIGN.md section 4
  *   "kernel_timing" 1 -> per-launch CUDA-event timing (see kocr_read_kernel_timing); setting it clears the totals */
 int kocr_set_option(kocr_handle* h, const char* name, int value);
 /* Beam search support - OCRPredictor._beam_search (predictor.py:101-136).  After kocr_gather_chunks /
