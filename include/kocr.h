@@ -87,8 +87,8 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
  *   "force_tokens"  1 -> decode_greedy feeds the ids set with kocr_set_forced_tokens instead of its argmax
  *   "straggler_threshold" n -> see kocr_read_unfinished;  "lstm_impl" 0/1, "use_graphs" 0/1, "big_gemm_sms" n: tuning knobs
  *   "compact_rows" 1 -> greedy loop: once a 128-row tile of lines has emitted <eos>, swap the active rows to the front and
- *                       continue on fewer rows (same tokens; a measured +0.5 %, off by default); "kv_split" 0 -> plain 16-bit
- *                       cross-attention K/V projection instead of the split-precision one
+ *                       continue on fewer rows (same tokens; a measured +0.5 %, off by default); "kv_split" 0 / "lstm_split" 0 -> plain
+ *                       16-bit cross-attention K/V / BiLSTM input projection instead of the split-precision ones
  *   "blocking_wait" 1 -> host waits inside the calls sleep (blocking-sync event) instead of spinning: for processes that
  *                        keep many handles / host threads in flight (bench.py sets it when --in-flight > 1)
  *   A/B switches of kernel variants (process-wide): "se_fused", "se_staged", "conv1_impl", "chunk_attn_impl",

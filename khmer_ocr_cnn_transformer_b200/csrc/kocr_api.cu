@@ -75,7 +75,7 @@ struct kocr_handle {
     const act16_t* patch_w; const float *patch_b, *patch_pos;
     EncLayerW enc[2];
     const float* global_pos;
-    const act16_t *lstm_w_ih, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
+    const act16_t *lstm_w_ih, *lstm_w_ih3, *lstm_w_hh, *lstm_w_hh_mma; const float* lstm_b;
     int straggler_threshold = 0; // >0: decode_greedy returns early once <= this many lines are still active;
                                  // the caller re-submits those lines (kocr_read_unfinished) in a later batch
     int big_gemm_sms = 0;        // >0: persistent grid size of the stage 2-5a GEMMs (leave SMs to other streams)
@@ -116,6 +116,7 @@ struct kocr_handle {
     std::vector<int> row_orig;   // row -> line of the caller's batch (identity until the loop compacts)
     int32_t* out_stage = nullptr;    // pinned [max_lines][257 + 2]: tokens / lengths / finished in row order before un-permuting
     Buf compact_tab;             // device int2 pairs
+    int lstm_split = 1;          // BiLSTM input projection in split precision (same trick as kv_split; 8184 vs 8181 of 8192 c3 lines)
     int kv_split = 1;            // cross-attention K/V projection in split precision (hi + lo operands, K = 3 x 384)
     int blocking_wait = 0;       // 1: host waits sleep on a blocking-sync event (many handles / host threads per process)
     int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
@@ -195,6 +196,7 @@ int resolve_weights(kocr_handle* h) {
             snprintf(nm, sizeof nm, "se%d.b2", i + 3); W_F32(h->se[i].b2, nm, C);
         }
         W_A16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
+        W_A16(h->lstm_w_ih3, "lstm.w_ih3", 8 * LSTM_H * 3 * D);
         W_F32(h->lstm_b, "lstm.b", 8 * LSTM_H);
         W_A16(h->lstm_w_hh, "lstm.w_hh", bilstm_whh_packed_elems());
         W_A16(h->lstm_w_hh_mma, "lstm.w_hh_mma", bilstm_whh_mma_elems());
@@ -545,6 +547,11 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
     if (h->variant == 0) {
         GemmEpilogue e = ep_none();
         e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
+        if (h->lstm_split) {        // split-precision input projection: fp32 merged sequence as [hi | lo | hi] rows (see project_cross_kv)
+            act16_t* a3 = buf<act16_t>(h, "kv_a3");
+            TIMED("lstm_in_split", 0, launch_split3(buf<float>(h, "x"), a3, M, s)); ++g_launches;
+            TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, a3, M, h->lstm_w_ih3, 8 * LSTM_H, 3 * D_MODEL, e, s));
+        } else
         TIMED("lstm_in_proj", 2.0 * M * D_MODEL * 8 * LSTM_H, gemm_linear(h, buf<act16_t>(h, "xb"), M, h->lstm_w_ih, 8 * LSTM_H, D_MODEL, e, s));
         if (h->lstm_impl == 1)
             TIMED("bilstm_recurrence", 2.0 * M * 8 * LSTM_H * LSTM_H, launch_bilstm_mma(buf<float>(h, "gin"), h->lstm_w_hh_mma, h->d_line_tok_off, h->d_line_T, h->d_groups16,
@@ -1017,6 +1024,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "blocking_wait") == 0) { h->blocking_wait = value; return 0; }
     if (strcmp(name, "kv_split") == 0) { h->kv_split = value; return 0; }
+    if (strcmp(name, "lstm_split") == 0) { h->lstm_split = value; return 0; }
     if (strcmp(name, "compact_rows") == 0) { h->compact_rows = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
     if (strcmp(name, "se_staged") == 0) { set_se_staged(value); return 0; }                               // process-wide

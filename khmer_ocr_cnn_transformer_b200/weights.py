@@ -198,7 +198,10 @@ def pack_tensors(sd: dict) -> dict:
     f32("global_pos", sd["global_pos"])
     if se:
         p = "context_bilstm."
-        bf16("lstm.w_ih", np.concatenate([sd[p + "weight_ih_l0"], sd[p + "weight_ih_l0_reverse"]], 0))
+        wih = np.concatenate([sd[p + "weight_ih_l0"], sd[p + "weight_ih_l0_reverse"]], 0).astype(np.float32)
+        bf16("lstm.w_ih", wih)
+        wih_hi = a16_bits_to_f32(f32_to_a16_bits(wih)).reshape(wih.shape)      # split-precision copy, see dec.ca_kv_w3
+        bf16("lstm.w_ih3", np.concatenate([wih_hi, wih_hi, wih - wih_hi], 1))
         f32("lstm.b", np.concatenate([sd[p + "bias_ih_l0"] + sd[p + "bias_hh_l0"],
                                       sd[p + "bias_ih_l0_reverse"] + sd[p + "bias_hh_l0_reverse"]]))
         bf16("lstm.w_hh", pack_whh(sd[p + "weight_hh_l0"], sd[p + "weight_hh_l0_reverse"]))

@@ -46,6 +46,9 @@ def dump():
     from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
     sd = load_checkpoint(ROOT / "tests/golden/fixture_se_ckpt.npz")
     rec = _native.Recognizer(weights.pack_blob(sd), max_lines=256, max_chunks=5120)
+    for opt in sys.argv[3:]:                      # e.g. lstm_split=1 kv_split=0: numerics experiments against the stored oracle tokens
+        k, v = opt.split("=")
+        rec.set_option(k, int(v))
     imgs = lines()
     toks, lns = [], []
     for i in range(0, len(imgs), 256):
