@@ -1,6 +1,6 @@
 """Turn the raw ncu outputs of one round into the committed summaries under profiles/r01/ (run in the build container).
 
-  python tools/summarize_ncu.py launches gpurun_out/launches_v4.csv profiles/r01/ncu_launch_list_v4.csv
+  python tools/summarize_ncu.py launches gpurun_out/launches_v5.csv profiles/r01/ncu_launch_list_v5.csv
   python tools/summarize_ncu.py full gpurun_out/prof_conv6_v4.ncu-rep profiles/r01/conv6_ncu_v4.json
   python tools/summarize_ncu.py fullmd gpurun_out/prof_misc_v4.ncu-rep profiles/r01/ncu_full_misc_v4.md
 """
@@ -15,7 +15,8 @@ ONE_TIME = ["resize_h", "resize_vcoef", "resize_v_chunk", "conv1+pool1 (mma.sync
             "se5 fused + final pool", "patch proj (gemm)",
             "enc0 qkv (gemm)", "enc0 attention (mma.sync)", "enc0 out_proj (gemm)", "enc0 ln1", "enc0 ffn1 (gemm)", "enc0 ffn2 (gemm)", "enc0 ln2",
             "enc1 qkv (gemm)", "enc1 attention (mma.sync)", "enc1 out_proj (gemm)", "enc1 ln1", "enc1 ffn1 (gemm)", "enc1 ffn2 (gemm)",
-            "enc1 ln2+global_pos", "lstm in_proj (gemm)", "bilstm recurrence", "cross K/V proj (gemm)"]
+            "enc1 ln2+global_pos", "lstm in split3", "lstm in_proj (gemm, K = 1152)", "bilstm recurrence", "cross K/V split3",
+            "cross K/V proj (gemm, K = 1152)"]
 
 
 def short(name):
@@ -31,7 +32,7 @@ def launches(src, dst):
     gemm = sum(float(r[iv]) for r in one if "gemm_tc" in r[ik]) / 1e3
     out = io.StringIO()
     out.write("# ncu launch list (gpu__time_duration.sum, --clock-control none) of ONE pass of the hot path, final round-1 kernels\n")
-    out.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 466 -c 124 --csv python tools/profile_step.py 256 24\n")
+    out.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 470 -c 126 --csv python tools/profile_step.py 256 24\n")
     out.write("# workload: c2 batch, 256 lines = 1885 chunks; plain launches (CUDA graphs off so every kernel shows by name); "
               "cold-cache, serialised: compare SHARES\n")
     out.write(f"# one-time stages (1-5a): {len(one)} launches, {tot / 1e3:.3f} ms; gemm_tc_kernel share = {gemm / tot:.3f}\n")
