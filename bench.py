@@ -64,7 +64,7 @@ def load_state_dict():
 
 def make_batch(rank: int, n_batches: int = 1):
     """`n_batches` c2 batches of 256 lines (seeds rank, rank+1000, ...); seed 0 == the parity-test batch."""
-    from khmer_ocr_cnn_transformer_b200 import synth
+    from workloads import synth
     imgs = []
     for b in range(n_batches):
         imgs += synth.make_lines(LINES_PER_STEP, WIDTH_LO, WIDTH_HI, seed=rank + 1000 * b)[0]

@@ -26,15 +26,29 @@ def needs_build() -> bool:
         return True
     t = LIB.stat().st_mtime
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "kocr.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    return any(d.exists() and d.stat().st_mtime > t for d in deps)     # (an installed copy may lack ../include)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Serialised across processes (N ranks of a fresh checkout all call this): an exclusive flock on build/.lock, the
+    library is linked under a temporary name and renamed into place, so nobody dlopens a half-written file."""
     if not force and not needs_build():
         return LIB
-    objs = []
+    import fcntl
     build_dir = PKG / "build"
     build_dir.mkdir(exist_ok=True)
+    with open(build_dir / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():         # another process built it while we waited
+                return LIB
+            return _build_locked(build_dir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(build_dir: Path, verbose: bool) -> Path:
+    objs = []
     procs = []
     for src in SOURCES:
         obj = build_dir / (src + ".o")
@@ -49,8 +63,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
     (build_dir / "ptxas.log").write_text("\n".join(log))
-    cmd = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    tmp = LIB.with_name(LIB.name + f".tmp{os.getpid()}")
+    cmd = [_nvcc(), "-shared", "-o", str(tmp), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     if verbose:
         print("\n".join(log))
     return LIB

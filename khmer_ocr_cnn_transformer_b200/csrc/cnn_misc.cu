@@ -580,11 +580,8 @@ void set_se_staged(int on) { g_se_staged = on; }
 template <int C, int H, bool FINAL, bool STAGED>
 static int launch_se_fused_variant(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks, cudaStream_t stream) {
     const size_t smem = SeSmem<C>::BYTES + (STAGED ? (size_t)H * (SE_W + 1) * C * 2 : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(se_fused_kernel<C, H, FINAL, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, se_fused_kernel<C, H, FINAL, STAGED>, (int)smem));
     se_fused_kernel<C, H, FINAL, STAGED><<<n_chunks, SE_THREADS, smem, stream>>>(in, w.w0p, w.b0p, w.w2p, w.b2, out);
     KOCR_CUDA(cudaGetLastError());
     return 0;

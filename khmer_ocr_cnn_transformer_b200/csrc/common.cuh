@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 
 namespace kocr {
 
@@ -82,6 +83,21 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.attrs = attr;
     cfg.numAttrs = pdl_active() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: one flag per (launch site, device), so that a
+// process holding handles on several GPUs opts in on each of them.  Racing threads may both set it (harmless).
+struct PerDeviceOnce { std::atomic<unsigned char> done[64]; };
+template <typename K>
+inline cudaError_t opt_in_dynamic_smem(PerDeviceOnce& st, K kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && st.done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && tracked) st.done[dev].store(1, std::memory_order_release);
+    return e;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -432,11 +432,8 @@ static int launch_impl(const void* a, long rowsA, const void* w, const GemmProbl
     const int esize = TF32 ? 4 : 2;
     KOCR_TRY(make_tmap(&ta, a, (uint64_t)rowsA, (uint64_t)p.cin, BM, esize));
     KOCR_TRY(make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.taps * p.cin, BN, esize));
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, gemm_tc_kernel<BN, TF32>, Cfg::SMEM_BYTES));
     const int tiles = kp.num_m_tiles * kp.num_n_tiles * kp.split_k;
     const int grid = tiles < num_sms ? tiles : num_sms;
     KOCR_CUDA(launch_kernel(gemm_tc_kernel<BN, TF32>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, kp));

@@ -98,7 +98,7 @@ struct kocr_handle {
     // batch state
     int n_lines = 0, n_chunks = 0, n_tok = 0, max_T = 0, n_groups = 0, max_new_w = 0;
     std::vector<int> line_T, line_first_chunk, line_n_chunks;
-    int last_steps = 0;
+    int last_steps = 0, last_max_steps = 256;   // positions run / allowed by the last decode (kocr_read_unfinished)
     double host_launch_us = 0, host_wait_us = 0;   // decode loop: host time inside graph / kernel launches and inside stream waits
     // options
     int trace_logits = 0, force_tokens = 0;
@@ -980,7 +980,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
             }
         }
     }
-    h->last_steps = done;
+    h->last_steps = done; h->last_max_steps = max_steps;
     // results come back in row order; un-permute them into the caller's line order
     int32_t* st_tok = h->out_stage;
     int32_t* st_len = st_tok + (size_t)h->max_lines * KOCR_TOKENS_LD;
@@ -1084,6 +1084,7 @@ int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, co
     float* base = reinterpret_cast<float*>(h->beam_cache.p);
     int* tokens = buf<int>(h, "tokens");
     int* scratch = buf<int>(h, "forced");             // [0, R): parents, [R, 2R): tok_off, [2R, 3R): T  (buffer: R x 257 ints)
+    h->have_forced = false;                           // ... which overwrites any tokens set with kocr_set_forced_tokens
     std::vector<int32_t> tab((size_t)3 * R, 0);
     int max_T = 0;
     for (int r = 0; r < n_rows; ++r) {
@@ -1242,7 +1243,7 @@ int kocr_read_unfinished(kocr_handle* h, int32_t* flags_out) {
     KOCR_CHECK(h != nullptr && flags_out != nullptr, "kocr_read_unfinished: null argument");
     // a line is unfinished if it neither emitted <eos> nor used up all decode positions (host-only: the flags
     // were copied to pinned memory at the end of kocr_decode_greedy)
-    for (int i = 0; i < h->n_lines; ++i) flags_out[i] = (h->fin_host[i] == 0 && h->last_steps < h->dec_max_len) ? 1 : 0;
+    for (int i = 0; i < h->n_lines; ++i) flags_out[i] = (h->fin_host[i] == 0 && h->last_steps < h->last_max_steps) ? 1 : 0;
     return 0;
 }
 

@@ -208,22 +208,16 @@ void set_chunk_attention_impl(int impl) { g_chunk_attn_impl = impl; }
 int launch_chunk_attention(const act16_t* qkv, act16_t* out, int n_chunks, cudaStream_t stream) {
     if (n_chunks > 0 && g_chunk_attn_impl == 1) {
         const size_t smem_mma = (size_t)TOK_PER_CHUNK * CA_LD * 2;
-        static bool attr_set_mma = false;
-        if (!attr_set_mma) {
-            KOCR_CUDA(cudaFuncSetAttribute(chunk_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
-            attr_set_mma = true;
-        }
+        static PerDeviceOnce attr_once_mma;
+        KOCR_CUDA(opt_in_dynamic_smem(attr_once_mma, chunk_attention_mma_kernel, (int)smem_mma));
         chunk_attention_mma_kernel<<<n_chunks, 256, smem_mma, stream>>>(qkv, out);
         KOCR_CUDA(cudaGetLastError());
         return 0;
     }
     if (n_chunks == 0) return 0;
     const size_t smem = 8 * 2 * 32 * HEAD_DIM * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(chunk_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, chunk_attention_kernel, (int)smem));
     chunk_attention_kernel<<<n_chunks, 256, smem, stream>>>(qkv, out);
     KOCR_CUDA(cudaGetLastError());
     return 0;
@@ -562,11 +556,8 @@ int launch_bilstm(const float* gin, const act16_t* whh_packed, const int* line_t
                   act16_t* mem_a16_lo, cudaStream_t stream) {
     if (n_groups == 0) return 0;
     const size_t smem = (size_t)LSTM_KP * LSTM_ROWS * 4 + 2 * LSTM_LPG * LSTM_H * 4 + LSTM_LPG * LSTM_ROWS * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, bilstm_kernel, (int)smem));
     bilstm_kernel<<<dim3(2, n_groups * 2), LSTM_ROWS, smem, stream>>>(
         gin, reinterpret_cast<const uint32_t*>(whh_packed), line_tok_off, line_T, groups, mem_f32, mem_a16,
         mem_a16_lo);
@@ -733,11 +724,8 @@ int launch_bilstm_mma(const float* gin, const act16_t* whh_mma, const int* line_
                       act16_t* mem_a16_lo, cudaStream_t stream) {
     if (n_groups == 0) return 0;
     const size_t smem = 2 * 16 * LM_THREADS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        KOCR_CUDA(cudaFuncSetAttribute(bilstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, bilstm_mma_kernel, (int)smem));
     bilstm_mma_kernel<<<dim3(2, n_groups * 2), LM_THREADS, smem, stream>>>(
         gin, reinterpret_cast<const uint4*>(whh_mma), line_tok_off, line_T, groups, mem_f32, mem_a16, mem_a16_lo);
     KOCR_CUDA(cudaGetLastError());
@@ -1128,11 +1116,8 @@ int launch_dec_cross_attn(const float* q, const act16_t* kv, int layer, const in
     }
     const size_t smem = ((size_t)N_HEAD * max_T + 8 * D_MODEL) * sizeof(float);
     KOCR_CHECK(smem <= 200 * 1024, "cross-attention: memory length %d too long for shared memory", max_T);
-    static bool attr_set = false;
-    if (!attr_set) {     // once, outside any stream capture (the first decode group of a process runs eagerly)
-        KOCR_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;     // set outside any stream capture (the first decode group of a handle runs eagerly)
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_cross_attn_kernel, 200 * 1024));
     KOCR_CUDA(launch_kernel(dec_cross_attn_kernel, dim3(n_lines), dim3(256), smem, stream, q, kv, layer, line_tok_off,
                             line_T, max_T, finished, out, nsplit, n_lines, bias));
     return 0;
@@ -1174,6 +1159,7 @@ __global__ void __launch_bounds__(128) dec_argmax_kernel(const float* __restrict
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
     if (lane != 0) return;
+    if (bi == 0x7fffffff) bi = 3;        // no finite maximum (NaN logits): end the line instead of emitting an out-of-range id
     if (forced) {
         tokens[l * TOK_LD + t + 1] = forced[l * TOK_LD + t + 1];
         lengths[l] = t + 2;

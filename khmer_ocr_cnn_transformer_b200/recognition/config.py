@@ -1,7 +1,15 @@
 """`OCRConfig` - same seven fields and defaults as the reference dataclass
-(reference: netra_ocr/recognition/config.py:4-13).  `device` defaults to CUDA because this
-package has no CPU path; asking for anything else fails loudly in `OCRPredictor`."""
+(reference: netra_ocr/recognition/config.py:4-13), including `device`: "cuda" when a CUDA device is visible, else
+"cpu".  This package has no CPU path, so a "cpu" config fails loudly in `OCRPredictor` instead of running slowly."""
 from dataclasses import dataclass
+
+
+def _default_device() -> str:
+    try:
+        import torch
+        return "cuda" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        return "cpu"
 
 
 @dataclass
@@ -13,4 +21,4 @@ class OCRConfig:
     emb_dim: int = 384
     max_seq_len: int = 4096
     decode_max_len: int = 256
-    device: str = "cuda"
+    device: str = _default_device()

@@ -14,9 +14,11 @@ import numpy as np
 from .config import OCRConfig
 from .tokenizer import Tokenizer
 from .preprocessor import ImagePreprocessor
-from ..checkpoint import load_checkpoint, detect_variant
-from ..weights import pack_blob
-from .._native import Recognizer, LineBatch
+from . import _core
+load_checkpoint, detect_variant = _core.checkpoint.load_checkpoint, _core.checkpoint.detect_variant
+pack_blob = _core.weights.pack_blob
+Recognizer, LineBatch = _core.native.Recognizer, _core.native.LineBatch
+plan_batches = _core.scheduling.plan_batches
 
 logger = logging.getLogger(__name__)
 
@@ -30,6 +32,11 @@ class OCRPredictor:
         self.device = torch.device(self.cfg.device)
         if self.device.type != "cuda":
             raise RuntimeError("khmer_ocr_cnn_transformer_b200 has no CPU path: OCRConfig.device must be 'cuda'")
+        # the kernels hard-code the reference vocabulary layout (char2idx.json: <pad>=0, <sos>=2, <eos>=3, 124 symbols)
+        layout = (tokenizer.pad_idx, tokenizer.sos_idx, tokenizer.eos_idx, len(tokenizer))
+        if layout != (0, 2, 3, 124):
+            raise ValueError(f"vocabulary layout (pad, sos, eos, size) = {layout}; the CUDA path is specialised for the "
+                             "reference's char2idx.json layout (0, 2, 3, 124)")
         logger.info(f"Init Model: dim={self.cfg.emb_dim}, max_seq={self.cfg.max_seq_len}")
         self.model_spec = model_class(vocab_size=len(tokenizer), pad_idx=tokenizer.pad_idx,
                                       emb_dim=self.cfg.emb_dim, max_global_len=self.cfg.max_seq_len)
@@ -57,7 +64,6 @@ class OCRPredictor:
         stragglers are collected and decoded together in a final pass, so one looping line does not hold 255
         finished ones for up to 256 positions.  Greedy decoding is deterministic: results are unchanged."""
         results = [None] * len(grays)
-        from ..scheduling import plan_batches
 
         def run(indices, threshold):
             stragglers = []
@@ -78,7 +84,8 @@ class OCRPredictor:
         left = run(list(range(len(grays))), lambda n: n // 32)
         if left:
             left = run(left, lambda n: 0)
-        assert not left
+        if left:
+            raise RuntimeError(f"{len(left)} lines still undecoded after the final pass")
         return results
 
     # ------------------------------------------------------------------------------------
@@ -105,7 +112,6 @@ class OCRPredictor:
         if beam_width > 8:
             raise ValueError("beam_width > 8 is not supported by the CUDA path")
         results = [None] * len(grays)
-        from ..scheduling import plan_batches
         # every hypothesis is a row of the decode workspace: at most max_lines // beam_width lines per pass
         lines_per_pass = max(1, self._max_lines // max(beam_width, 1))
         for idxs in plan_batches([g.shape for g in grays], lines_per_pass, self._max_chunks, self.cfg.max_seq_len):
@@ -135,7 +141,8 @@ class OCRPredictor:
         """Page image + detected text-line polygons -> one greedy-decoded string per line, in detection order: the
         `extract_textline_crops` -> `recognize_batch(crops, beam_width=1)` sequence of OCREngine.process_image
         (ocr_engine.py:54-86, textline_detection.py:7-53) with the crops cut, padded and grey-converted on the GPU."""
-        from ..textline_crops import textline_boxes, crop_lines_device
+        tc = _core.textline_crops()
+        textline_boxes, crop_lines_device = tc.textline_boxes, tc.crop_lines_device
         from PIL import Image
         if isinstance(image, (str, Path)):
             image = Image.open(image).convert("RGB")
@@ -145,8 +152,7 @@ class OCRPredictor:
             return []
         crops = crop_lines_device(self.model, image, boxes, padding_px)
         shapes = list(zip(crops.batch.heights.tolist(), crops.batch.widths.tolist()))
-        from ..scheduling import plan_batches
-        from .._native import line_batch_from_shapes
+        line_batch_from_shapes = _core.native.line_batch_from_shapes
         results = [None] * len(boxes)
         self.model.set_option("straggler_threshold", 0)
         for idxs in plan_batches(shapes, self._max_lines, self._max_chunks, self.cfg.max_seq_len):

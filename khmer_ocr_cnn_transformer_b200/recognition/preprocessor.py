@@ -8,7 +8,8 @@ from pathlib import Path
 import numpy as np
 
 from .config import OCRConfig
-from .._native import LineBatch
+from . import _core
+LineBatch = _core.native.LineBatch
 
 
 class ImagePreprocessor:

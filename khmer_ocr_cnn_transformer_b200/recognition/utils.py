@@ -14,7 +14,8 @@ def setup_logging():
 def autodetect_config(model_path) -> dict:
     """Infer {max_seq_len, emb_dim, decode_max_len} from the checkpoint's `global_pos` and
     `dec.pos_emb` shapes.  Raises FileNotFoundError for a missing file, like the reference."""
-    from ..checkpoint import load_checkpoint
+    from . import _core
+    load_checkpoint = _core.checkpoint.load_checkpoint
     path = Path(model_path)
     if not path.exists():
         raise FileNotFoundError(f"Model not found at {path}")

@@ -35,7 +35,7 @@ REF = Path("/root/reference")
 sys.path.insert(0, str(REPO))
 warnings.filterwarnings("ignore")
 
-from khmer_ocr_cnn_transformer_b200 import synth                      # noqa: E402
+from workloads import synth                      # noqa: E402
 from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict  # noqa: E402
 from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import build_vocab  # noqa: E402
 
@@ -104,7 +104,7 @@ def stage_bank(args):
                 tok_flat.extend(toks); tok_off.append(tok_off[-1] + len(toks))
             space.append(sp)
             g += 1
-    out = HERE / "wordbank.npz"
+    out = REPO / "workloads" / "wordbank.npz"
     np.savez_compressed(out, pixels=np.concatenate(pix), offsets=np.asarray(offs, np.int64),
                         widths=np.asarray(widths, np.int32), heights=np.asarray(heights, np.int32),
                         group=np.asarray(group, np.int32), space=np.asarray(space, np.int32),

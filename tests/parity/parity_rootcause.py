@@ -11,12 +11,12 @@ import sys, numpy as np, time
 sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent.parent))
 ROOT = __import__("pathlib").Path(__file__).resolve().parent.parent.parent
 from oracle import recognizer_np as O
-from khmer_ocr_cnn_transformer_b200 import synth
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
 from threadpoolctl import threadpool_limits
 sd = load_checkpoint(str(ROOT / 'tests/golden/fixture_se_ckpt.npz'))
 imgs = synth.make_lines(1024, 200, 1600, seed=3)[0]
-orc = np.load(str(ROOT / 'profiles/r01/c3_oracle_tokens.npz'))
+orc = np.load(str(ROOT / 'tests/golden/oracle_tokens_c3.npz'))
 gpu = np.load(str(ROOT / 'profiles/r01/c3_cuda_tokens_fp16_kv.npz'))      # tokens of the build WITHOUT the fix
 lines = [345, 622, 848]
 

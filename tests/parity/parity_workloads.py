@@ -4,8 +4,8 @@ mismatch and the CER of both sides against the ground-truth labels.
   workloads: c2 = the 256-line bench batch (widths 400-800, seed 0); c3 = 1024 lines of the mixed-width config
              (widths 200-1600, seed 3); c3full = all 8192 lines of that config (the oracle takes about an hour on 8 cores)
   GPU box :  python tests/parity/parity_workloads.py dump [c2|c3]    -> gpurun_out/<w>_tokens.npz  (tokens + lengths, CUDA path)
-  anywhere:  python tests/parity/parity_workloads.py oracle [c2|c3]  -> profiles/r01/<w>_oracle_tokens.npz (numpy oracle, host cores)
-  anywhere:  python tests/parity/parity_workloads.py compare [c2|c3] -> profiles/r01/parity_<w>.json
+  anywhere:  python tests/parity/parity_workloads.py oracle [c2|c3]  -> tests/golden/oracle_tokens_<w>.npz (numpy oracle, host cores)
+  anywhere:  python tests/parity/parity_workloads.py compare [c2|c3] -> profiles/r02/parity_<w>.json
 """
 import json, sys, time, os
 from pathlib import Path
@@ -15,7 +15,7 @@ import numpy as np
 
 WL = sys.argv[2] if len(sys.argv) > 2 else "c2"
 SPEC = {"c2": (256, 400, 800, 0), "c3": (1024, 200, 1600, 3), "c3full": (8192, 200, 1600, 3)}[WL]
-ORACLE_NPZ = ROOT / "profiles" / "r01" / f"{WL}_oracle_tokens.npz"
+ORACLE_NPZ = ROOT / "tests" / "golden" / f"oracle_tokens_{WL}.npz"
 GPU_NPZ = ROOT / "gpurun_out" / f"{WL}_tokens.npz"
 
 
@@ -36,7 +36,7 @@ def _oracle_line(img):
 
 
 def lines(with_labels=False):
-    from khmer_ocr_cnn_transformer_b200 import synth
+    from workloads import synth
     imgs, labels = synth.make_lines(SPEC[0], SPEC[1], SPEC[2], seed=SPEC[3])
     return (imgs, labels) if with_labels else imgs
 
@@ -107,7 +107,7 @@ def compare():
            "mean_cer_vs_labels": {"cuda": cer_gpu / n, "oracle": cer_orc / n},
            "mean_decoded_len": {"cuda": float(g["lengths"].mean()), "oracle": float(o["lengths"].mean())}, "mismatches": mism,
            "oracle_margin_percentiles": {p: float(np.percentile(gaps, p)) for p in (0.1, 1, 5, 50)}}
-    (ROOT / "profiles" / "r01" / f"parity_{WL}.json").write_text(json.dumps(out, indent=1))
+    (ROOT / "profiles" / "r02" / f"parity_{WL}.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out, indent=1))
 
 

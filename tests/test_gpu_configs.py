@@ -43,7 +43,8 @@ def test_c1_single_line_batch1_matches_reference():
 
 
 def test_c3_mixed_width_batch_composition_invariance():
-    from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+    from khmer_ocr_cnn_transformer_b200 import _native, weights
+    from workloads import synth
     from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
     from khmer_ocr_cnn_transformer_b200.scheduling import shard_lines
     from oracle import recognizer_np as O
@@ -76,7 +77,8 @@ def test_c3_mixed_width_batch_composition_invariance():
 
 
 def test_c5_vgg_baseline_batch_1024():
-    from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+    from khmer_ocr_cnn_transformer_b200 import _native, weights
+    from workloads import synth
     from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict
     from oracle import recognizer_np as O
     sd = seeded_state_dict("vgg", seed=11, max_global_len=1024)
@@ -104,7 +106,8 @@ def test_c5_vgg_trained_fixture_tokens_batch_1024():
     """BASELINE config c5 with a TRAINED VGG fixture (tools/train_fixture_gpu.py --variant vgg; the reference's VGG class reads
     the synthetic lines with CER 0): batch of 1024 short lines - tokens identical to the reference's own greedy outputs on
     the golden lines, identical to the oracle on a sample, CER against the labels reported."""
-    from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+    from khmer_ocr_cnn_transformer_b200 import _native, weights
+    from workloads import synth
     from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
     from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import build_vocab
     from oracle import recognizer_np as O

@@ -47,7 +47,7 @@ def rec_seeded_vgg():
 
 
 def _lines(n, lo, hi, seed):
-    from khmer_ocr_cnn_transformer_b200 import synth
+    from workloads import synth
     return synth.make_lines(n, lo, hi, seed=seed)[0]
 
 

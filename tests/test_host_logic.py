@@ -7,7 +7,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from khmer_ocr_cnn_transformer_b200 import _native, weights, scheduling, synth
+from khmer_ocr_cnn_transformer_b200 import _native, weights, scheduling
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict, state_dict_spec, validate_state_dict
 from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import Tokenizer, build_vocab
 from khmer_ocr_cnn_transformer_b200.recognition.config import OCRConfig
@@ -257,3 +258,54 @@ def test_batched_beam_bookkeeping_equals_reference_loop():
         got = beam.results()
         for line in range(n):
             assert got[line] == reference_loop(line, bw), (bw, line)
+
+
+def test_top_level_recognition_import_like_the_reference():
+    """netra_ocr/ocr_engine.py:6-10 puts ITS package directory on sys.path and imports `recognition.recognize_text` as a
+    top-level package; INTEGRATION.md option A points that path at this repository's package directory."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from recognition.recognize_text import recognize_batch, recognize\n"
+        "from recognition.predictor import OCRPredictor\n"
+        "from recognition.tokenizer import Tokenizer\n"
+        "from recognition.config import OCRConfig\n"
+        "from recognition.utils import autodetect_config\n"
+        "assert recognize_batch([]) == []\n"
+        "assert OCRPredictor.__module__ == 'recognition.predictor'\n"
+        "print('ok')\n" % str(REPO / "khmer_ocr_cnn_transformer_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+@pytest.mark.parametrize("wrapped", [False, True])
+def test_pth_checkpoint_round_trip(tmp_path, wrapped):
+    """A reference-style `.pth` (torch.save of a state_dict with `num_batches_tracked` entries, bare or wrapped in
+    {'model_state_dict': ...}: predictor.py:38-46) loads to the same arrays, the same config and the same packed blob."""
+    import torch
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    from khmer_ocr_cnn_transformer_b200.recognition.utils import autodetect_config
+    sd = seeded_state_dict("se", seed=3, max_global_len=512)
+    state = {}
+    for k, v in sd.items():
+        state[k] = torch.from_numpy(v.copy())
+        if k.endswith("running_var"):
+            state[k.replace("running_var", "num_batches_tracked")] = torch.tensor(7, dtype=torch.int64)
+    path = tmp_path / "khmerocr_se_transformer.pth"
+    torch.save({"model_state_dict": state, "epoch": 3} if wrapped else state, path)
+    got = load_checkpoint(path)
+    assert set(got) == set(sd)
+    assert all(np.array_equal(got[k], sd[k]) for k in sd)
+    assert autodetect_config(path) == {"max_seq_len": 512, "emb_dim": 384, "decode_max_len": 256}
+    assert weights.pack_blob(got) == weights.pack_blob(sd)
+
+
+def test_build_skips_missing_dependencies(monkeypatch, tmp_path):
+    from khmer_ocr_cnn_transformer_b200 import build as B
+    if not B.LIB.exists():
+        pytest.skip("library not built")
+    monkeypatch.setattr(B, "PKG", B.PKG)        # needs_build() must not raise when ../include/kocr.h is absent
+    real = B.PKG.parent / "include" / "kocr.h"
+    assert real.exists()
+    assert isinstance(B.needs_build(), bool)

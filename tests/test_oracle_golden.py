@@ -195,3 +195,18 @@ def test_vgg_trained_fixture_against_reference_outputs():
         mem = O.memory_for_line(sd, enc, "vgg")
         assert rel_err(mem, z[f"mem{i}"]) < 1e-4
         assert O.greedy_decode(sd, mem) == [int(t) for t in z[f"tokens{i}"]]
+
+
+def test_stored_oracle_tokens_match_live_oracle():
+    """tests/golden/oracle_tokens_*.npz (what tests/test_gpu_token_identity.py compares the CUDA path with on the full c2 / c3
+    workloads) are outputs of THIS oracle: re-derive a few lines, including one beyond the first 1024 of the 8192-line set."""
+    from workloads import synth
+    sd = load_fixture_ckpt()
+    cases = {"c2": ((256, 400, 800, 0), (0, 131)), "c3": ((1024, 200, 1600, 3), (7,)), "c3full": ((8192, 200, 1600, 3), (4099,))}
+    for name, (spec, picks) in cases.items():
+        z = _need(f"oracle_tokens_{name}.npz")
+        n, lo, hi, seed = spec
+        imgs, _ = synth.make_lines(max(picks) + 1, lo, hi, seed=seed)      # the generator is sequential: a prefix is enough
+        for i in picks:
+            want = [int(t) for t in z["tokens"][i, :z["lengths"][i]]]
+            assert O.recognise_lines(sd, [imgs[i]], "se")[0] == want, (name, i)

@@ -16,7 +16,8 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 import torch
-from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+from khmer_ocr_cnn_transformer_b200 import _native, weights
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
 
 ROOT = Path(__file__).resolve().parent.parent

@@ -2,7 +2,8 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+from khmer_ocr_cnn_transformer_b200 import _native, weights
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
 sd = load_checkpoint(Path(__file__).resolve().parent.parent / "tests/golden/fixture_se_ckpt.npz")
 rec = _native.Recognizer(weights.pack_blob(sd), max_lines=64, max_chunks=640)

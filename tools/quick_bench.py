@@ -4,7 +4,8 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 import torch
-from khmer_ocr_cnn_transformer_b200 import _native, weights, synth
+from khmer_ocr_cnn_transformer_b200 import _native, weights
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import seeded_state_dict, load_checkpoint
 
 n_lines = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -4,7 +4,8 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-from khmer_ocr_cnn_transformer_b200 import _native, weights, synth, textline_crops as T
+from khmer_ocr_cnn_transformer_b200 import _native, weights, textline_crops as T
+from workloads import synth
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint, seeded_state_dict
 
 ROOT = Path(__file__).resolve().parent.parent

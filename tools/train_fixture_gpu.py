@@ -30,7 +30,7 @@ import torch.nn.functional as F
 
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
-from khmer_ocr_cnn_transformer_b200 import synth                                   # noqa: E402
+from workloads import synth                                   # noqa: E402
 from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint, seeded_state_dict  # noqa: E402
 
 D, NH, PAD, SOS, EOS, V = 384, 8, 0, 2, 3, 124

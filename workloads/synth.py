@@ -4,7 +4,7 @@ The reference renders training lines with Pillow from a corpus and the bundled f
 (scripts/generate_document_text.py:86-127: words joined by spaces, black on white, 5 px margin).
 Neither the corpus nor (on the GPU box) the fonts are available, so `tests/golden/make_fixtures.py`
 renders a bank of vocab-derived pseudo-words once, offline, with those fonts and commits it as
-`tests/golden/wordbank.npz`.  This module composes lines from that bank with a seeded RNG:
+`workloads/wordbank.npz`.  This module composes lines from that bank with a seeded RNG:
 same pixel statistics (anti-aliased black glyphs on white, native heights 20-60 px so that the
 height-48 resize is exercised), unlimited supply, deterministic.
 """
@@ -13,8 +13,7 @@ from __future__ import annotations
 from pathlib import Path
 import numpy as np
 
-GOLDEN_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
-DEFAULT_BANK = GOLDEN_DIR / "wordbank.npz"
+DEFAULT_BANK = Path(__file__).resolve().parent / "wordbank.npz"
 
 
 class WordBank:
