@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KOCR_ABI_VERSION 1
+#define KOCR_ABI_VERSION 2
 #define KOCR_TOKENS_LD 257          /* 1 <sos> + up to 256 generated ids per line */
 
 typedef struct kocr_handle kocr_handle;
@@ -91,8 +91,8 @@ int kocr_recognize_lines(kocr_handle* h, const uint8_t* pixels, size_t pixel_byt
  *                       16-bit cross-attention K/V / BiLSTM input projection instead of the split-precision ones
  *   "blocking_wait" 1 -> host waits inside the calls sleep (blocking-sync event) instead of spinning: for processes that
  *                        keep many handles / host threads in flight (bench.py sets it when --in-flight > 1)
- *   A/B switches of kernel variants (process-wide): "se_fused", "se_staged", "conv1_impl", "chunk_attn_impl",
- *                        "dec_cross_impl", "gemm_bn192", "dec_wide", "use_pdl" - see DESIGN.md section 4
+ *   A/B switches of kernel variants (process-wide): "chunk_attn_impl", "dec_cross_impl", "gemm_bn192", "dec_wide",
+ *                        "use_pdl" - see DESIGN.md section 4
  *   "kernel_timing" 1 -> per-launch CUDA-event timing (see kocr_read_kernel_timing); setting it clears the totals */
 int kocr_set_option(kocr_handle* h, const char* name, int value);
 /* Beam search support - OCRPredictor._beam_search (predictor.py:101-136).  After kocr_gather_chunks /
@@ -143,19 +143,24 @@ int kocr_read_kernel_timing(kocr_handle* h, char* text_out, size_t cap);
 int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens /* [n_lines, KOCR_TOKENS_LD] */, int n_lines);
 
 /* Copy an intermediate of the last batch to the host (tests only).  Names: "chunks" f32 (n,1,48,100);
- * "pool1" "pool2" "conv3" "conv4" "pool3" "conv5" "conv6" "pool4" "conv7" bf16 padded-linear activations;
- * "patch_in" bf16 [n*32,1024]; "enc" f32 [n*32,384] (encoder output + global_pos); "memory" f32 [tokens,384];
+ * "pool1" "conv2" "pool2" "conv3" "pool3" "conv5" "pool4" 16-bit dense NWHC activations [n][w][h][C] (pool3 / pool4 are the
+ * SE-gated, (2,1)-pooled outputs of conv4 / conv6 - the un-pooled conv4 / conv6 / conv7 outputs exist only for the ResNet
+ * baseline); "bins7" 16-bit [n*25 + w][2][512] row-bin sums of conv7; "se_mean3/4/5" f32 [n*25 + w][C] column means;
+ * "patch_in" 16-bit [n*32,1024]; "enc" f32 [n*32,384] (encoder output + global_pos); "memory" f32 [tokens,384];
  * "logits_trace" f32 [n_lines, steps, 128].  Returns the byte size through *bytes_out when dst is NULL. */
 int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t kocr_launch_count(void);
 
-/* Unit-test hook for the tcgen05 GEMM: D = A[rowsA,cin] (x taps, row-shifted) * W[N, taps*cin]^T + bias,
- * device pointers, bf16 operands.  impl 0 = tcgen05 kernel, 1 = CUDA-core check kernel. */
-int kocr_test_gemm(int impl, const void* a_bf16, int64_t rows_a, const void* w_bf16, int m, int n, int taps, int cin,
-                   const int32_t* tap_off, const float* bias, int relu, int pl_h, int pl_w, float* out_f32,
-                   void* out_bf16, void* stream);
+/* Unit-test hook for the tcgen05 GEMM: D = A * W^T + bias (device pointers, 16-bit operands; impl 2: fp32 operands as TF32).
+ * taps = 1: A = [rows_a, cin] row-major.  taps = 9: 3x3 / pad-1 convolution, A = dense NWHC activation
+ * [m / (conv_h * conv_w)][conv_w][conv_h][cin], W = [n][9 * cin] with tap = kh * 3 + kw; tile_cols > 0 selects whole-column M
+ * tiles; col_mode 1 / 2 selects the column-fused epilogue (out_pool: pooled rows / row-bin sums, out_colmean: column means;
+ * out_f32 / out_a16 unused).  impl 0 = tcgen05 kernel, 1 = CUDA-core check kernel. */
+int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a16, int m, int n, int taps, int cin,
+                   int conv_h, int conv_w, int tile_cols, int col_mode, const float* bias, int relu, float* out_f32,
+                   void* out_a16, void* out_pool, float* out_colmean, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_read_kernel_timing.argtypes = [vp, C.c_char_p, sz]
     lib.kocr_read_kernel_timing.restype = i32
     lib.kocr_launch_count.restype = i64
-    lib.kocr_test_gemm.argtypes = [i32, vp, i64, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.kocr_test_gemm.argtypes = [i32, vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]
     for f in ("kocr_create", "kocr_destroy", "kocr_model_info", "kocr_gather_chunks",
               "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward", "kocr_decode_greedy",
               "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens", "kocr_debug_read",
@@ -135,7 +135,7 @@ class Recognizer:
 
     def __init__(self, weight_blob: bytes, device: int = 0, max_lines: int = 256, max_chunks: int = 4096):
         self.lib = load_library()
-        if self.lib.kocr_abi_version() != 1:
+        if self.lib.kocr_abi_version() != 2:
             raise KocrError("ABI version mismatch between _native.py and libkocr_b200.so")
         self._h = C.c_void_p()
         buf = (C.c_char * len(weight_blob)).from_buffer_copy(weight_blob)

@@ -234,6 +234,31 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// 4D im2col-mode load (3x3 convolution operand): the tensor map describes the dense activation as (C, d1, d2, N) with
+// a bounding box of base pixels [-1, d - 1) in both spatial dims (pad 1); {crd_c, crd1, crd2, crd_n} is the first base
+// pixel (output position - 1), {off1, off2} in [0, 3) the filter tap added to every base pixel.  The hardware walks
+// `pixelsPerColumn` consecutive output pixels (d1 fastest, wrapping into d2 and N), zero-fills the halo and the tail past
+// the tensor, and always signals pixelsPerColumn * 128 bytes (verified on B200 by tools/im2col_probe.cu).
+__device__ __forceinline__ void tma_load_im2col_4d(const void* desc, uint64_t* bar, void* smem_dst, int32_t crd_c,
+                                                   int32_t crd1, int32_t crd2, int32_t crd_n, uint16_t off1, uint16_t off2) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
+          "r"(crd_c), "r"(crd1), "r"(crd2), "r"(crd_n), "h"(off1), "h"(off2)
+        : "memory");
+}
+
+// named barrier over `nthreads` threads of the CTA (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- tcgen05 -----------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -34,32 +34,24 @@ int preprocess_vtab_ints_per_line();
 int preprocess_kmax();
 
 // ---- stage 2 helpers -------------------------------------------------------------------
-// conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool: f32 chunks -> a16 padded-linear (24x50, 64).
-int launch_conv1_pool(const float* d_chunks, const float* w /*[64][9]*/, const float* b /*[64]*/,
-                      act16_t* out, int n_chunks, cudaStream_t stream);
-// Tensor-core version (mma.sync, K = 9 taps padded to 16): w16 = a16 [64][16].  set_conv1_impl(0) selects the CUDA-core kernel.
+// Activations: 16-bit dense NWHC [chunk][w][h][C] (pixel index (n*W + w)*H + h; see cnn_misc.cu).
+// conv1 (Cin=1) + folded BN + ReLU + 2x2 max-pool on mma.sync (K = 9 taps padded to 16): f32 chunks -> (50 x 24, 64);
+// w16 = a16 [64][16].
 int launch_conv1_pool_mma(const float* d_chunks, const act16_t* w16, const float* b, act16_t* out, int n_chunks,
                           cudaStream_t stream);
-void set_conv1_impl(int impl);
-int conv1_impl();
 // 16-bit -> fp32 copy (n_elems multiple of 8)
 int launch_a16_to_f32(const act16_t* in, float* out, long n_elems, cudaStream_t stream);
-// 2x2 max-pool between padded-linear layouts (C multiple of 8).
+// 2x2 and (2,1) max-pools (C multiple of 8).
 int launch_pool2x2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
-// 1D-SE: squeeze -> column means a16 [n*W + w][C]; the excitation FCs run on the tcgen05 GEMM;
-// gate fp32 [n*W + w][C] (null = no SE) * (2,1) max-pool -> padded-linear (H/2, W, C), or
-// gate * x -> AdaptiveAvgPool2d((2,32)) -> patch GEMM operand [n*32 + k][kh*C + c].
+int launch_pool_h2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, int C, cudaStream_t stream);
+// AdaptiveAvgPool2d((2,32)) of a (3, W) map without a gate -> patch GEMM operand [n*32 + k][kh*C + c];
+// rows_in = 2: `in` = row-bin sums [col][2][C] from the conv7 epilogue, rows_in = 3: raw rows [col][3][C].
+int launch_finalpool(const act16_t* in, int rows_in, act16_t* out, int n_chunks, int W, int C, cudaStream_t stream);
+// 1D-SE excitation on the column means fp32 [n*W + w][C] written by the conv epilogue: gate = sigmoid(FC2(relu(FC1(mean))));
+// pooled [col][rows][C] *= gate in place, or (final_pool) gate * row-bin sums -> AdaptiveAvgPool2d((2,32)) -> out.
 struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; const float* b2; };
-// Fused SE block: squeeze + FC1/ReLU + FC2/sigmoid + gate*x + pool in one kernel, one CTA per chunk (W = 25).
-int launch_se_fused(const act16_t* in, const SEWeights& w, act16_t* out, int n_chunks, int H, int W, int C,
-                    bool final_pool, cudaStream_t stream);
-void set_se_staged(int on);   // 1: the fused SE kernel stages the chunk in shared memory (no faster); 0 (default): reads global memory twice
-int launch_se_col_mean(const act16_t* in, act16_t* means, int n_chunks, int H, int W, int C,
-                       cudaStream_t stream);
-int launch_se_apply_pool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H, int W,
-                         int C, cudaStream_t stream);
-int launch_se_apply_finalpool(const act16_t* in, const float* gate, act16_t* out, int n_chunks, int H,
-                              int W, int C, cudaStream_t stream);
+int launch_se_excite(const float* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
+                     int C, bool final_pool, cudaStream_t stream);
 
 // ---- stage 4/5 helpers -----------------------------------------------------------------
 // per-chunk 32-token, 8-head attention: qkv a16 [M, 1152] -> out a16 [M, 384].

@@ -119,7 +119,6 @@ struct kocr_handle {
     int lstm_split = 1;          // BiLSTM input projection in split precision (same trick as kv_split; 8184 vs 8181 of 8192 c3 lines)
     int kv_split = 1;            // cross-attention K/V projection in split precision (hi + lo operands, K = 3 x 384)
     int blocking_wait = 0;       // 1: host waits sleep on a blocking-sync event (many handles / host threads per process)
-    int se_fused = 1;            // 1: one fused kernel per SE block; 0: squeeze / FC GEMMs / apply kernels (A/B tests)
     static const int BEAM_MAX = 8;
     Buf tf_x, tf_tab;             // kocr_forward_teacher_forced: padded memory operand, per-line tables
     Buf crop_page, crop_tab;      // kocr_crop_lines: device copy of a host page, boxes + offsets
@@ -251,8 +250,10 @@ int resolve_weights(kocr_handle* h) {
     return 0;
 }
 
-// activation geometry per stage of the backbone
-const PLGeom G1 = make_pl(24, 50), G2 = make_pl(12, 25), G3 = make_pl(6, 25), G4 = make_pl(3, 25);
+// activation geometry per stage of the backbone (dense NWHC: [chunk][W][H][C]); cols = whole columns per GEMM M tile
+struct StageGeom { int H, W, cols; };
+const StageGeom G1 = {24, 50, 5}, G2 = {12, 25, 10}, G3 = {6, 25, 21}, G4 = {3, 25, 42};
+inline size_t px(const StageGeom& g) { return (size_t)g.H * g.W; }
 
 struct WsItem { const char* name; size_t bytes; };
 
@@ -272,11 +273,11 @@ int carve_workspace(kocr_handle* h) {
     const size_t D = D_MODEL;
     std::vector<WsItem> items = {
         {"chunks", NC * IMG_H * CHUNK_W * 4},
-        {"pool1", NC * G1.S * 64 * 2},   {"conv2", NC * G1.S * 128 * 2}, {"pool2", NC * G2.S * 128 * 2},
-        {"conv3", NC * G2.S * 256 * 2},  {"conv4", NC * G2.S * 256 * 2}, {"pool3", NC * G3.S * 256 * 2},
-        {"conv5", NC * G3.S * 512 * 2},  {"conv6", NC * G3.S * 512 * 2}, {"pool4", NC * G4.S * 512 * 2},
-        {"conv7", NC * G4.S * 512 * 2},  {"patch_in", M * 1024 * 2},
-        {"se_mean", NC * 25 * 512 * 2},  {"se_z", NC * 25 * 128 * 2},   {"se_gate", NC * 25 * 512 * 4},
+        {"pool1", NC * px(G1) * 64 * 2},   {"conv2", NC * px(G1) * 128 * 2}, {"pool2", NC * px(G2) * 128 * 2},
+        {"conv3", NC * px(G2) * 256 * 2},  {"pool3", NC * px(G3) * 256 * 2},
+        {"conv5", NC * px(G3) * 512 * 2},  {"pool4", NC * px(G4) * 512 * 2},
+        {"bins7", NC * 25 * 2 * 512 * 2},  {"patch_in", M * 1024 * 2},
+        {"se_mean3", NC * 25 * 256 * 4},   {"se_mean4", NC * 25 * 512 * 4}, {"se_mean5", NC * 25 * 512 * 4},
         {"x", M * D * 4},   {"xb", M * D * 2},  {"qkv", M * 3 * D * 2}, {"ao", M * D * 2}, {"y", M * D * 4},
         {"hff", M * 1024 * 2},
         {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2}, {"kv_a3", M * 3 * D * 2},
@@ -288,9 +289,12 @@ int carve_workspace(kocr_handle* h) {
         {"dparts", 8 * L * 3 * D * 4},
         {"kcache", 2 * L * DEC_MAX * D * 4}, {"vcache", 2 * L * DEC_MAX * D * 4},
     };
-    if (h->variant == 2) {      // ResNet baseline: second 24x50x128 activation + the fp32 shortcut (largest: layer1)
-        items.push_back({"res_t1", NC * G1.S * 128 * 2});
-        items.push_back({"res_add", NC * G1.S * 128 * 4});
+    if (h->variant == 2) {      // ResNet baseline: un-pooled block outputs, second 24x50x128 activation, the fp32 shortcut (largest: layer1)
+        items.push_back({"conv4", NC * px(G2) * 256 * 2});
+        items.push_back({"conv6", NC * px(G3) * 512 * 2});
+        items.push_back({"conv7", NC * px(G4) * 512 * 2});
+        items.push_back({"res_t1", NC * px(G1) * 128 * 2});
+        items.push_back({"res_add", NC * px(G1) * 128 * 4});
     }
     size_t total = 0;
     for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -368,54 +372,49 @@ int gemm_linear(kocr_handle* h, const void* a, long rows, const void* w, int N, 
     return launch_gemm_tc(a, rows, w, p, sms, s);
 }
 
-int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, const PLGeom& g, int Cin,
+// 3x3 / pad-1 convolution + folded BN (+ ReLU) as an implicit GEMM over the dense NWHC activation (TMA im2col mode).
+// Standard form: out = act(conv + bias (+ addend)) [chunk][W][H][Cout].
+int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, const StageGeom& g, int Cin,
               int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s, const float* addend = nullptr) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
-    p.M = n_chunks * g.S; p.N = Cout; p.taps = 9; p.cin = Cin;
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) p.tap_off[r * 3 + c] = (r - 1) * g.P + (c - 1);
+    p.M = n_chunks * g.H * g.W; p.N = Cout; p.taps = 9; p.cin = Cin;
+    p.conv_H = g.H; p.conv_W = g.W; p.n_img = n_chunks; p.tile_cols = 0;      // 128 consecutive pixels per tile
     p.ep = ep_none();
     p.ep.bias = b; p.ep.relu = relu;
-    p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W;
     p.ep.out_a16 = out; p.ep.ld_a16 = Cout;
     if (addend) {               // residual connection: out = act(conv + bias + addend); the addend path needs the 128-wide N tile
         p.ep.addend = addend; p.ep.ld_add = Cout; p.ep.add_period = 0;
         p.bn = 128;
     }
     const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
-    return launch_gemm_tc(in, (long)n_chunks * g.S, w, p, sms, s);
+    return launch_gemm_tc(in, (long)p.M, w, p, sms, s);
 }
 
-// SequenceSE excitation for every column of the batch: means -> FC1+ReLU (width padded to 128) -> FC2+sigmoid.
-// Returns the fp32 gate [n*W + w][C] in the workspace (null for the VGG baseline).
-int se_gate(kocr_handle* h, const act16_t* act, int NC, int H, int W, int C, const SEWeights& w, const char* site,
-            const float** gate_out, cudaStream_t s) {
-    act16_t* means = buf<act16_t>(h, "se_mean");
-    act16_t* z = buf<act16_t>(h, "se_z");
-    float* gate = buf<float>(h, "se_gate");
-    const long rows = (long)NC * W;
-    char nm[64];
-    snprintf(nm, sizeof nm, "%s_squeeze", site);
-    TIMED(nm, 0, launch_se_col_mean(act, means, NC, H, W, C, s)); ++g_launches;
-    GemmEpilogue e = ep_none();
-    e.bias = w.b0p; e.relu = 1; e.out_a16 = z; e.ld_a16 = 128;
-    snprintf(nm, sizeof nm, "%s_fc", site);
-    TIMED(nm, 2.0 * rows * C * (C / 16), gemm_linear(h, means, rows, w.w0p, 128, C, e, s));
-    e = ep_none();
-    e.bias = w.b2; e.relu = 2; e.out_f32 = gate; e.ld_f32 = C;
-    TIMED(nm, 2.0 * rows * C * (C / 16), gemm_linear(h, z, rows, w.w2p, C, 128, e, s));
-    *gate_out = gate;
-    return 0;
+// The same convolution with the column-fused epilogue (whole-column M tiles): writes the (2,1)-max-pooled rows
+// (mode 1: [col][H/2][Cout]) or the AdaptiveAvgPool row-bin sums (mode 2, H = 3: [col][2][Cout]) and, if `colmean` is
+// given, the SequenceSE column means [col][Cout] fp32 - the un-pooled conv output is never stored.
+int gemm_conv_colfused(kocr_handle* h, const act16_t* in, act16_t* out_pool, float* colmean, int mode, int n_chunks,
+                       const StageGeom& g, int Cin, int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s) {
+    GemmProblem p;
+    memset(&p, 0, sizeof p);
+    p.M = n_chunks * g.H * g.W; p.N = Cout; p.taps = 9; p.cin = Cin;
+    p.conv_H = g.H; p.conv_W = g.W; p.n_img = n_chunks; p.tile_cols = g.cols;
+    p.ep = ep_none();
+    p.ep.bias = b; p.ep.relu = relu;
+    p.ep.col_mode = mode; p.ep.out_pool = out_pool; p.ep.out_colmean = colmean;
+    p.bn = 256;
+    const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
+    return launch_gemm_tc(in, (long)p.M, w, p, sms, s);
 }
 
 // One BasicBlock (model/resnet_model.py:28-37) on the implicit-GEMM kernel: c1 = relu(bn1(conv1 x)); shortcut as an
 // fp32 tensor (1x1 conv + BN as a per-position linear layer, or a widening copy of x); out = relu(bn2(conv2 c1) + shortcut)
 // through the GEMM's fp32 addend.  `out` may alias `in` for an identity block (the addend was copied out before).
-int resnet_block(kocr_handle* h, int bi, const act16_t* in, act16_t* tmp, act16_t* out, int NC, const PLGeom& g, cudaStream_t s) {
+int resnet_block(kocr_handle* h, int bi, const act16_t* in, act16_t* tmp, act16_t* out, int NC, const StageGeom& g, cudaStream_t s) {
     const int ci = RES_CIN[bi], co = RES_COUT[bi];
     const ResBlockW& r = h->res[bi];
-    const long rows = (long)NC * g.S;
+    const long rows = (long)NC * g.H * g.W;
     float* add = buf<float>(h, "res_add");
     char nm[32];
     snprintf(nm, sizeof nm, "res%d_conv1", bi);
@@ -436,19 +435,18 @@ int resnet_block(kocr_handle* h, int bi, const act16_t* in, act16_t* tmp, act16_
 int stage_resnet_backbone(kocr_handle* h, cudaStream_t s) {
     const int NC = h->n_chunks;
     auto B = [&](const char* n) { return buf<act16_t>(h, n); };
-    if (conv1_impl() == 1) TIMED("conv1_pool1", 2.0 * NC * 48 * 100 * 9.0 * 64, launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
-    else TIMED("conv1_pool1", 2.0 * NC * 48 * 100 * 9.0 * 64, launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s));
+    TIMED("conv1_pool1", 2.0 * NC * 48 * 100 * 9.0 * 64, launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
     ++g_launches;
     KOCR_TRY(resnet_block(h, 0, B("pool1"), B("res_t1"), B("conv2"), NC, G1, s));                    // layer1
     TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
     KOCR_TRY(resnet_block(h, 1, B("pool2"), B("conv3"), B("conv4"), NC, G2, s));                     // layer2.0
     KOCR_TRY(resnet_block(h, 2, B("conv4"), B("conv3"), B("conv4"), NC, G2, s));                     // layer2.1 (identity)
-    TIMED("pool3", 0, launch_se_apply_pool(B("conv4"), nullptr, B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
+    TIMED("pool3", 0, launch_pool_h2(B("conv4"), B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
     KOCR_TRY(resnet_block(h, 3, B("pool3"), B("conv5"), B("conv6"), NC, G3, s));                     // layer3.0
     KOCR_TRY(resnet_block(h, 4, B("conv6"), B("conv5"), B("conv6"), NC, G3, s));                     // layer3.1 (identity)
-    TIMED("pool4", 0, launch_se_apply_pool(B("conv6"), nullptr, B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
+    TIMED("pool4", 0, launch_pool_h2(B("conv6"), B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
     KOCR_TRY(resnet_block(h, 5, B("pool4"), B("conv7"), B("pool4"), NC, G4, s));                     // layer4 (identity)
-    TIMED("final_pool", 0, launch_se_apply_finalpool(B("pool4"), nullptr, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
+    TIMED("final_pool", 0, launch_finalpool(B("pool4"), 3, B("patch_in"), NC, 25, 512, s)); ++g_launches;
     return 0;
 }
 
@@ -462,34 +460,26 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     if (h->variant == 2) {
         KOCR_TRY(stage_resnet_backbone(h, s));
     } else {
-    if (conv1_impl() == 1) TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
-    else TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool(buf<float>(h, "chunks"), h->conv1_w, h->conv1_b, B("pool1"), NC, s));
+    // SE-VGG (se_model.py:63-79) / VGG baseline (vgg_model.py:50-59).  conv4 / conv6 / conv7 never store their un-pooled
+    // output: their epilogue emits the (2,1)-max-pooled rows (conv7: the adaptive-pool row bins) plus the SE column means;
+    // the SE excitation then scales the pooled tensor in place (gate > 0 commutes with the max).
+    TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
     ++g_launches;
     TIMED("conv2", cf(24, 50, 64, 128), gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
     TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
     TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
-    TIMED("conv4", cf(12, 25, 256, 256), gemm_conv(h, B("conv3"), B("conv4"), NC, G2, 256, 256, h->conv_w[4], h->conv_b[4], 1, s));
-    const float* gate = nullptr;
-    const bool fused = se && h->se_fused;     // one kernel per SE block (squeeze + FCs + gate + pool)
-    if (fused) { TIMED("se3_fused_pool3", 4.0 * nc * 25 * 256 * 16, launch_se_fused(B("conv4"), h->se[0], B("pool3"), NC, 12, 25, 256, false, s)); ++g_launches; }
-    else {
-    if (se) KOCR_TRY(se_gate(h, B("conv4"), NC, 12, 25, 256, h->se[0], "se3", &gate, s));
-    TIMED("se3_apply_pool3", 0, launch_se_apply_pool(B("conv4"), gate, B("pool3"), NC, 12, 25, 256, s)); ++g_launches;
-    }
+    TIMED("conv4", cf(12, 25, 256, 256), gemm_conv_colfused(h, B("conv3"), B("pool3"), se ? buf<float>(h, "se_mean3") : nullptr, 1, NC, G2, 256, 256,
+                                                            h->conv_w[4], h->conv_b[4], 1, s));
+    if (se) { TIMED("se3_excite", 4.0 * nc * 25 * 256 * 16, launch_se_excite(buf<float>(h, "se_mean3"), h->se[0], B("pool3"), nullptr, NC, 6, 25, 256, false, s)); ++g_launches; }
     TIMED("conv5", cf(6, 25, 256, 512), gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
-    TIMED("conv6", cf(6, 25, 512, 512), gemm_conv(h, B("conv5"), B("conv6"), NC, G3, 512, 512, h->conv_w[6], h->conv_b[6], 1, s));
-    if (fused) { TIMED("se4_fused_pool4", 4.0 * nc * 25 * 512 * 32, launch_se_fused(B("conv6"), h->se[1], B("pool4"), NC, 6, 25, 512, false, s)); ++g_launches; }
-    else {
-    if (se) KOCR_TRY(se_gate(h, B("conv6"), NC, 6, 25, 512, h->se[1], "se4", &gate, s));
-    TIMED("se4_apply_pool4", 0, launch_se_apply_pool(B("conv6"), gate, B("pool4"), NC, 6, 25, 512, s)); ++g_launches;
-    }
+    TIMED("conv6", cf(6, 25, 512, 512), gemm_conv_colfused(h, B("conv5"), B("pool4"), se ? buf<float>(h, "se_mean4") : nullptr, 1, NC, G3, 512, 512,
+                                                           h->conv_w[6], h->conv_b[6], 1, s));
+    if (se) { TIMED("se4_excite", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<float>(h, "se_mean4"), h->se[1], B("pool4"), nullptr, NC, 3, 25, 512, false, s)); ++g_launches; }
     // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
-    TIMED("conv7", cf(3, 25, 512, 512), gemm_conv(h, B("pool4"), B("conv7"), NC, G4, 512, 512, h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
-    if (fused) { TIMED("se5_fused_finalpool", 4.0 * nc * 25 * 512 * 32, launch_se_fused(B("conv7"), h->se[2], B("patch_in"), NC, 3, 25, 512, true, s)); ++g_launches; }
-    else {
-    if (se) KOCR_TRY(se_gate(h, B("conv7"), NC, 3, 25, 512, h->se[2], "se5", &gate, s));
-    TIMED("se5_apply_finalpool", 0, launch_se_apply_finalpool(B("conv7"), gate, B("patch_in"), NC, 3, 25, 512, s)); ++g_launches;
-    }
+    TIMED("conv7", cf(3, 25, 512, 512), gemm_conv_colfused(h, B("pool4"), B("bins7"), se ? buf<float>(h, "se_mean5") : nullptr, 2, NC, G4, 512, 512,
+                                                           h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
+    if (se) { TIMED("se5_excite_finalpool", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<float>(h, "se_mean5"), h->se[2], B("bins7"), B("patch_in"), NC, 2, 25, 512, true, s)); ++g_launches; }
+    else { TIMED("final_pool", 0, launch_finalpool(B("bins7"), 2, B("patch_in"), NC, 25, 512, s)); ++g_launches; }
     }   // SE / VGG backbone
 
     const long M = (long)NC * TOK_PER_CHUNK;
@@ -1021,15 +1011,12 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "force_tokens") == 0) { h->force_tokens = value; return 0; }
     if (strcmp(name, "use_graphs") == 0) { h->use_graphs = value; return 0; }
     if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value; return 0; }
-    if (strcmp(name, "se_fused") == 0) { h->se_fused = value; return 0; }
     if (strcmp(name, "blocking_wait") == 0) { h->blocking_wait = value; return 0; }
     if (strcmp(name, "kv_split") == 0) { h->kv_split = value; return 0; }
     if (strcmp(name, "lstm_split") == 0) { h->lstm_split = value; return 0; }
     if (strcmp(name, "compact_rows") == 0) { h->compact_rows = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
-    if (strcmp(name, "se_staged") == 0) { set_se_staged(value); return 0; }                               // process-wide
     if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
-    if (strcmp(name, "conv1_impl") == 0) { set_conv1_impl(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
@@ -1275,18 +1262,21 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
     const void* src = nullptr;
     size_t bytes = 0;
     std::string n(name);
-    auto plb = [&](const char* b, const PLGeom& g, int C) { src = h->named[b].p; bytes = NC * g.S * C * 2; };
+    auto act = [&](const char* b, const StageGeom& g, int C) { auto it = h->named.find(b); if (it != h->named.end()) { src = it->second.p; bytes = NC * px(g) * C * 2; } };
     if (n == "chunks") { src = h->named["chunks"].p; bytes = NC * IMG_H * CHUNK_W * 4; }
-    else if (n == "pool1") plb("pool1", G1, 64);
-    else if (n == "conv2") plb("conv2", G1, 128);
-    else if (n == "pool2") plb("pool2", G2, 128);
-    else if (n == "conv3") plb("conv3", G2, 256);
-    else if (n == "conv4") plb("conv4", G2, 256);
-    else if (n == "pool3") plb("pool3", G3, 256);
-    else if (n == "conv5") plb("conv5", G3, 512);
-    else if (n == "conv6") plb("conv6", G3, 512);
-    else if (n == "pool4") plb("pool4", G4, 512);
-    else if (n == "conv7") plb("conv7", G4, 512);
+    else if (n == "pool1") act("pool1", G1, 64);
+    else if (n == "conv2") act("conv2", G1, 128);
+    else if (n == "pool2") act("pool2", G2, 128);
+    else if (n == "conv3") act("conv3", G2, 256);
+    else if (n == "conv4") act("conv4", G2, 256);            // ResNet baseline only (the SE / VGG conv4 is pooled in its epilogue)
+    else if (n == "pool3") act("pool3", G3, 256);
+    else if (n == "conv5") act("conv5", G3, 512);
+    else if (n == "conv6") act("conv6", G3, 512);            // ResNet baseline only
+    else if (n == "pool4") act("pool4", G4, 512);
+    else if (n == "conv7") act("conv7", G4, 512);            // ResNet baseline only
+    else if (n == "bins7") { src = h->named["bins7"].p; bytes = NC * 25 * 2 * 512 * 2; }
+    else if (n == "se_mean3") { src = h->named["se_mean3"].p; bytes = NC * 25 * 256 * 4; }
+    else if (n == "se_mean4" || n == "se_mean5") { src = h->named[n].p; bytes = NC * 25 * 512 * 4; }
     else if (n == "patch_in") { src = h->named["patch_in"].p; bytes = M * 1024 * 2; }
     else if (n == "enc") { src = h->named["x"].p; bytes = M * D_MODEL * 4; }
     else if (n == "memory") { src = h->named[h->variant == 0 ? "mem" : "x"].p; bytes = M * D_MODEL * 4; }
@@ -1308,16 +1298,20 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
 }
 
 int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a16, int m, int n, int taps, int cin,
-                   const int32_t* tap_off, const float* bias, int relu, int pl_h, int pl_w, float* out_f32,
-                   void* out_a16, void* stream) {
+                   int conv_h, int conv_w, int tile_cols, int col_mode, const float* bias, int relu, float* out_f32,
+                   void* out_a16, void* out_pool, float* out_colmean, void* stream) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = m; p.N = n; p.taps = taps; p.cin = cin;
-    for (int i = 0; i < taps && i < 9; ++i) p.tap_off[i] = tap_off ? tap_off[i] : 0;
+    if (taps == 9) {
+        KOCR_CHECK(conv_h > 0 && conv_w > 0 && m % (conv_h * conv_w) == 0, "kocr_test_gemm: M = %d is not a whole number of %d x %d images", m, conv_w, conv_h);
+        p.conv_H = conv_h; p.conv_W = conv_w; p.n_img = m / (conv_h * conv_w); p.tile_cols = tile_cols;
+    }
     p.ep.bias = bias; p.ep.relu = relu;
-    if (pl_h > 0) { const PLGeom g = make_pl(pl_h, pl_w); p.ep.pl_S = g.S; p.ep.pl_P = g.P; p.ep.pl_H = g.H; p.ep.pl_W = g.W; }
     p.ep.out_f32 = out_f32; p.ep.ld_f32 = n;
     p.ep.out_a16 = reinterpret_cast<act16_t*>(out_a16); p.ep.ld_a16 = n;
+    p.ep.col_mode = col_mode; p.ep.out_pool = reinterpret_cast<act16_t*>(out_pool); p.ep.out_colmean = out_colmean;
+    if (col_mode) p.bn = 256;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     p.tf32 = impl == 2 ? 1 : 0;          // impl 2: fp32 operands consumed as TF32
     if (impl == 1)

@@ -14,12 +14,10 @@ def bf16_u16_to_f32(a: np.ndarray) -> np.ndarray:
     return a16_bits_to_f32(a)
 
 
-def pl_to_nchw(buf_u16: np.ndarray, n: int, H: int, W: int, C: int) -> np.ndarray:
-    """padded-linear 16-bit buffer [(n*(H+1)*(W+1)), C] -> fp32 (n, C, H, W) plus the pad values."""
-    x = bf16_u16_to_f32(buf_u16).reshape(n, H + 1, W + 1, C)
-    valid = x[:, :H, :W, :].transpose(0, 3, 1, 2)
-    pads = np.concatenate([x[:, H, :, :].reshape(-1), x[:, :, W, :].reshape(-1)])
-    return np.ascontiguousarray(valid), pads
+def nwhc_to_nchw(buf_u16: np.ndarray, n: int, H: int, W: int, C: int) -> np.ndarray:
+    """dense NWHC 16-bit activation of the library [(n*W + w)*H + h][C] -> fp32 (n, C, H, W)."""
+    x = bf16_u16_to_f32(buf_u16).reshape(n, W, H, C)
+    return np.ascontiguousarray(x.transpose(0, 3, 2, 1))
 
 
 def rel_err(a: np.ndarray, b: np.ndarray) -> float:

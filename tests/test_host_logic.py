@@ -152,7 +152,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _native.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.kocr_abi_version() == 1
+    assert lib.kocr_abi_version() == 2
 
 
 def test_no_cpu_fallback_fails_loudly():

@@ -13,7 +13,7 @@ imgs = synth.make_lines(5, 90, 700, seed=4)[0] + [np.full((20, 30), 255, np.uint
 for variant in ("se", "vgg", "resnet"):
     sd = load_checkpoint(ROOT / "tests/golden/fixture_se_ckpt.npz") if variant == "se" else seeded_state_dict(variant, 3, max_global_len=1024)
     rec = _native.Recognizer(weights.pack_blob(sd), max_lines=8, max_chunks=96)
-    for opts in ({}, {"se_fused": 0, "conv1_impl": 0, "chunk_attn_impl": 0, "dec_cross_impl": 0, "kv_split": 0, "dec_wide": 0, "use_graphs": 0}):
+    for opts in ({}, {"chunk_attn_impl": 0, "dec_cross_impl": 0, "kv_split": 0, "dec_wide": 0, "use_graphs": 0}):
         for k, v in opts.items():
             rec.set_option(k, v)
         tok, ln = rec.recognize_lines(_native.LineBatch(imgs), max_steps=20)
