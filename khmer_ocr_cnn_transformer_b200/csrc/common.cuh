@@ -141,6 +141,15 @@ __device__ __forceinline__ float a16_hi(uint32_t v) { return __half2float(__usho
 __device__ __forceinline__ act16_t to_a16(float x) { return __ushort_as_half((unsigned short)(pack_a16(x, 0.f) & 0xffffu)); }
 __device__ __forceinline__ float from_a16(act16_t x) { return __half2float(x); }
 #endif
+// fp32 -> TF32 with round-to-nearest (ties away).  tcgen05.mma.kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits
+// (a biased error of up to 2^-10); kernels that produce a TF32 GEMM operand round it here instead, which halves the
+// error and removes the bias - 6 of the 8 lines of the 8192-line c3 set that decoded differently from the fp32
+// reference came from that truncation (tests/parity/parity_rootcause8.py, profiles/r02/parity_rootcause8_fixes.json).
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ uint32_t a16x2_max(uint32_t a, uint32_t b) {
     act16x2_t r = __hmax2(*reinterpret_cast<act16x2_t*>(&a), *reinterpret_cast<act16x2_t*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);

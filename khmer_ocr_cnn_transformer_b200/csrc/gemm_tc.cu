@@ -294,6 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     return;
                 }
                 if (ep.out_f32) {
+                    if (ep.round_tf32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = rna_tf32(f[j]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         st_shared_v4(stg_u32 + own32 + ((j ^ sw32) << 4), make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
@@ -413,7 +417,7 @@ __global__ void gemm_simt_check_kernel(const act16_t* __restrict__ a, long rowsA
     const int n = (int)(idx - row * p.N);
     const GemmEpilogue& ep = p.ep;
     const float acc = check_act(check_dot(a, rowsA, w, p, row, n), ep, row, n);
-    if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + n] = acc;
+    if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + n] = ep.round_tf32 ? rna_tf32(acc) : acc;
     if (ep.out_a16) {
         ep.out_a16[row * ep.ld_a16 + n] = to_a16(acc);
         if (ep.out_a16_lo)

@@ -15,6 +15,7 @@ namespace kocr {
 struct GemmEpilogue {
     const float* bias;        // [N] or nullptr
     int relu;                 // activation: 0 none, 1 max(x, 0), 2 sigmoid
+    int round_tf32;           // 1: out_f32 is the A operand of a TF32 GEMM: round it to TF32 (nearest) here, see rna_tf32()
     // optional fp32 addend: out += addend[(period ? row % period : row) * ld_add + n]
     const float* addend;
     int ld_add;

@@ -62,7 +62,7 @@ void set_chunk_attention_impl(int impl);   // 1 = mma.sync kernel (default), 0 =
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
                      float* out_f32, act16_t* out_a16, act16_t* out_a16_lo, int rows,
                      cudaStream_t stream, int nsplit = 1, const float* in_bias = nullptr,
-                     const float* resid = nullptr);
+                     const float* resid = nullptr, float* out_tf32 = nullptr);
 // f32 [rows, 384] (+ pos[row_pos[row]]) -> f32 + a16 copies (VGG merge path without LN).
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
                    act16_t* out_a16_lo, int rows, cudaStream_t stream);
@@ -89,8 +89,8 @@ size_t bilstm_whh_mma_elems();
 // The generated position of a step is t = *step_base + step_off: step_base lives on the device so that a
 // captured CUDA graph of 8 steps can be replayed for every group of 8 positions.
 int launch_dec_embed(const int* tokens /*[L, DEC_MAX+1]*/, const int* step_base, int step_off, const float* tok_emb,
-                     const float* pos_emb, float* x, act16_t* xb, act16_t* xb_lo, int n_lines,
-                     cudaStream_t stream);
+                     const float* pos_emb, float* x, float* x_tf32 /* TF32-rounded copy, GEMM operand */, act16_t* xb,
+                     act16_t* xb_lo, int n_lines, cudaStream_t stream);
 int launch_dec_self_attn(const float* qkv /*[L,1152]*/, float* kcache,
                          float* vcache /*[L, DEC_MAX, 384]*/, const int* tokens, const int* step_base,
                          int step_off, const int* finished, float* out, int n_lines, cudaStream_t stream,

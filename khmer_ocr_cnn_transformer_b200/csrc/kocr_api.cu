@@ -587,37 +587,38 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     int* tokens = buf<int>(h, "tokens");
     const int* sb = buf<int>(h, "step_base");
     const int* fin = buf<int>(h, "finished");
-    float* dx = buf<float>(h, "dx");
+    float* dx = buf<float>(h, "dx");                 // residual stream, exact fp32
+    float* dxt = buf<float>(h, "dq");                // the same rows rounded to TF32 (nearest): A operand of the next GEMM
     float* parts = buf<float>(h, "dparts");          // split-K partial results of the current projection
     float* dao = buf<float>(h, "daof");
     float* dh = buf<float>(h, "dh");
     const int S2 = h->dec_wide ? 2 : 1, S8 = h->dec_wide ? 8 : 1;   // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8
-    DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, nullptr, nullptr, L, s)); ++g_launches;
+    DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches;
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         float* kc = rows ? rows->kcache + l * rows->layer_stride : buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         float* vc = rows ? rows->vcache + l * rows->layer_stride : buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        DSTEP(gemm_dec(h, dx, L, w.sa_in_w, 3 * D, D, S2, parts, s));
+        DSTEP(gemm_dec(h, dxt, L, w.sa_in_w, 3 * D, D, S2, parts, s));
         DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
-        DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx)); ++g_launches;
-        DSTEP(gemm_dec(h, dx, L, w.ca_q_w, D, D, S2, parts, s));
+        DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx, dxt)); ++g_launches;
+        DSTEP(gemm_dec(h, dxt, L, w.ca_q_w, D, D, S2, parts, s));
         DSTEP(launch_dec_cross_attn(parts, buf<act16_t>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
                                     rows ? rows->T : h->d_line_T, max_T, fin,
                                     dao, L, s, S2, w.ca_q_b)); ++g_launches;
         DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s));
-        DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx)); ++g_launches;
+        DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx, dxt)); ++g_launches;
         {   // FFN1 keeps its ReLU epilogue (no split): N = 1536 already gives 48 CTAs
             GemmProblem p;
             memset(&p, 0, sizeof p);
             p.M = L; p.N = 4 * D; p.taps = 1; p.cin = D; p.tf32 = 1; p.bn = h->dec_wide ? 64 : 256;
-            p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D;
-            DSTEP(launch_gemm_tc(dx, L, w.l1_w, p, h->num_sms, s));
+            p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D; p.ep.round_tf32 = 1;
+            DSTEP(launch_gemm_tc(dxt, L, w.l1_w, p, h->num_sms, s));
         }
         DSTEP(gemm_dec(h, dh, L, w.l2_w, D, 4 * D, S8, parts, s));
-        DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx)); ++g_launches;
+        DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx, dxt)); ++g_launches;
     }
-    DSTEP(gemm_dec(h, dx, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s));
+    DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s));
     const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
     float* trace = (h->trace_logits || rows) ? reinterpret_cast<float*>(h->trace.p) : nullptr;
     DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,

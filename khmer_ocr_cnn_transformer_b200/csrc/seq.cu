@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const int* __restrict__ row_pos, float* out_f32,
                                                         act16_t* out_a16, act16_t* out_lo, int rows,
                                                         int nsplit, const float* __restrict__ in_bias,
-                                                        const float* resid) {
+                                                        const float* resid, float* out_tf32) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     pdl_trigger();
@@ -307,21 +307,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         }
     }
     store_row_outputs(v, row, lane, out_f32, out_a16, out_lo);
+    if (out_tf32) {         // copy of the row as TF32 GEMM operand, rounded to nearest (the exact row stays the residual)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            *reinterpret_cast<float4*>(out_tf32 + row * D_MODEL + j * 128 + lane * 4) =
+                make_float4(rna_tf32(v[4 * j]), rna_tf32(v[4 * j + 1]), rna_tf32(v[4 * j + 2]), rna_tf32(v[4 * j + 3]));
+    }
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, const float* pos, const int* row_pos,
                      float* out_f32, act16_t* out_a16, act16_t* out_a16_lo, int rows,
-                     cudaStream_t stream, int nsplit, const float* in_bias, const float* resid) {
+                     cudaStream_t stream, int nsplit, const float* in_bias, const float* resid, float* out_tf32) {
     if (rows == 0) return 0;
     KOCR_CUDA(launch_kernel(layernorm_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, stream, x, g, b, pos, row_pos,
-                            out_f32, out_a16, out_a16_lo, rows, nsplit, in_bias, resid));
+                            out_f32, out_a16, out_a16_lo, rows, nsplit, in_bias, resid, out_tf32));
     return 0;
 }
 int launch_add_pos(const float* x, const float* pos, const int* row_pos, float* out_f32, act16_t* out_a16,
                    act16_t* out_a16_lo, int rows, cudaStream_t stream) {
     if (rows == 0) return 0;
     layernorm_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(x, nullptr, nullptr, pos, row_pos, out_f32, out_a16,
-                                                                out_a16_lo, rows, 1, nullptr, nullptr);
+                                                                out_a16_lo, rows, 1, nullptr, nullptr, nullptr);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -739,7 +745,7 @@ int launch_bilstm_mma(const float* gin, const act16_t* whh_mma, const int* line_
 
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_base, int step_off,
                                  const float* __restrict__ tok_emb,
-                                 const float* __restrict__ pos_emb, float* __restrict__ x,
+                                 const float* __restrict__ pos_emb, float* __restrict__ x, float* __restrict__ x_tf32,
                                  act16_t* __restrict__ xb, act16_t* __restrict__ xb_lo, int n_lines) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // n_lines * 96 float4
     pdl_trigger();
@@ -752,6 +758,7 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __re
     const float4 p = reinterpret_cast<const float4*>(pos_emb + (long)t * D_MODEL)[c4];
     const float4 v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
     reinterpret_cast<float4*>(x)[idx] = v;
+    if (x_tf32) reinterpret_cast<float4*>(x_tf32)[idx] = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
     if (xb == nullptr) return;
     const uint32_t p0 = pack_a16(v.x, v.y), p1 = pack_a16(v.z, v.w);
     reinterpret_cast<uint2*>(xb)[idx] = make_uint2(p0, p1);
@@ -761,15 +768,16 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const int* __re
 }
 
 int launch_dec_embed(const int* tokens, const int* step_base, int step_off, const float* tok_emb,
-                     const float* pos_emb, float* x, act16_t* xb, act16_t* xb_lo, int n_lines,
+                     const float* pos_emb, float* x, float* x_tf32, act16_t* xb, act16_t* xb_lo, int n_lines,
                      cudaStream_t stream) {
     const int total = n_lines * (D_MODEL / 4);
     KOCR_CUDA(launch_kernel(dec_embed_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, tokens, step_base, step_off,
-                            tok_emb, pos_emb, x, xb, xb_lo, n_lines));
+                            tok_emb, pos_emb, x, x_tf32, xb, xb_lo, n_lines));
     return 0;
 }
 
-__device__ __forceinline__ void store_attn_out(float o, long idx, float* out) { out[idx] = o; }
+// attention outputs are consumed only as the A operand of the TF32 out-projection GEMM: round to nearest here
+__device__ __forceinline__ void store_attn_out(float o, long idx, float* out) { out[idx] = rna_tf32(o); }
 
 // Causal self-attention for the newest position t against the cache (keys 0..t); keys whose token is
 // <pad> are masked (tgt_key_padding_mask, se_model.py:190).  CTA per line, warp per head.

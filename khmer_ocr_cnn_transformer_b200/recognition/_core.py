@@ -33,3 +33,7 @@ scheduling = _sub("scheduling")
 
 def textline_crops():            # imported lazily (predict_page only)
     return _sub("textline_crops")
+
+
+def pipeline():
+    return _sub("pipeline")

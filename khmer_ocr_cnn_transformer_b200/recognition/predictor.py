@@ -25,7 +25,7 @@ logger = logging.getLogger(__name__)
 
 class OCRPredictor:
     def __init__(self, model_path, tokenizer: Tokenizer, config: OCRConfig, model_class,
-                 max_lines: int = 256, max_chunks: int = 4096):
+                 max_lines: int = 256, max_chunks: int = 2816, in_flight: int = 6):
         self.cfg = config
         self.tokenizer = tokenizer
         import torch
@@ -40,7 +40,7 @@ class OCRPredictor:
         logger.info(f"Init Model: dim={self.cfg.emb_dim}, max_seq={self.cfg.max_seq_len}")
         self.model_spec = model_class(vocab_size=len(tokenizer), pad_idx=tokenizer.pad_idx,
                                       emb_dim=self.cfg.emb_dim, max_global_len=self.cfg.max_seq_len)
-        self._max_lines, self._max_chunks = max_lines, max_chunks
+        self._max_lines, self._max_chunks, self._in_flight = max_lines, max_chunks, in_flight
         self._load_weights(model_path)
         self.preprocessor = ImagePreprocessor(config, self.model)
 
@@ -51,42 +51,28 @@ class OCRPredictor:
         if variant != want:
             logger.warning(f"checkpoint looks like '{variant}' but model_class is '{want}'; using the checkpoint")
         index = self.device.index if self.device.index is not None else 0
-        self.model = Recognizer(pack_blob(sd), device=index, max_lines=self._max_lines, max_chunks=self._max_chunks)
+        # `in_flight` recognisers (handle + workspace + stream each, ~2 MB of workspace per chunk of capacity) behind one
+        # pipeline: greedy batches stream through all of them; `self.model` is the first one (beam search, page crops,
+        # teacher-forced forward and the stage-level calls use it alone)
+        self._pipe = _core.pipeline().LinePipeline(pack_blob(sd), device=index, in_flight=self._in_flight,
+                                                   max_lines=self._max_lines, max_chunks=self._max_chunks)
+        self.model = self._pipe.recs[0]
+
+    def close(self):
+        """Release every device handle of the predictor (weights, workspaces, streams)."""
+        self._pipe.close()
 
     # ------------------------------------------------------------------------------------
     def _decode_ids(self, tokens, lengths):
         return [self.tokenizer.decode([int(t) for t in tokens[i, :lengths[i]]]) for i in range(tokens.shape[0])]
 
     def _recognize_gray(self, grays):
-        """Greedy recognition of grey uint8 lines, batched to the handle's capacity.
-
-        Long tail: a batch returns as soon as only a few lines (<= 1/32 of the batch) are still decoding; those
-        stragglers are collected and decoded together in a final pass, so one looping line does not hold 255
-        finished ones for up to 256 positions.  Greedy decoding is deterministic: results are unchanged."""
-        results = [None] * len(grays)
-
-        def run(indices, threshold):
-            stragglers = []
-            for idxs in plan_batches([grays[i].shape for i in indices], self._max_lines, self._max_chunks,
-                                     self.cfg.max_seq_len):
-                idxs = [indices[j] for j in idxs]
-                batch = LineBatch([grays[i] for i in idxs])
-                self.model.set_option("straggler_threshold", threshold(len(idxs)))
-                tokens, lengths = self.model.recognize_lines(batch, max_steps=self.cfg.decode_max_len)
-                todo = self.model.unfinished(len(idxs))
-                for j, (i, text) in enumerate(zip(idxs, self._decode_ids(tokens, lengths))):
-                    if todo[j]:
-                        stragglers.append(i)
-                    else:
-                        results[i] = text
-            return stragglers
-
-        left = run(list(range(len(grays))), lambda n: n // 32)
-        if left:
-            left = run(left, lambda n: 0)
-        if left:
-            raise RuntimeError(f"{len(left)} lines still undecoded after the final pass")
-        return results
+        """Greedy recognition of grey uint8 lines through the pipeline: batches within the handles' capacity (sorted by
+        length, results in input order), several passes in flight, the long tail of every pass pooled and decoded
+        together (pipeline.py).  Greedy decoding is deterministic and lines are independent: results do not depend on
+        the batching."""
+        tokens, lengths = self._pipe.recognize(grays, max_steps=self.cfg.decode_max_len)
+        return self._decode_ids(tokens, lengths)
 
     # ------------------------------------------------------------------------------------
     def _beam_search_batch(self, n_lines: int, beam_width: int) -> list:

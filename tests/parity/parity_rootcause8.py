@@ -11,7 +11,14 @@ from multiprocessing import Pool
 
 LINES = [m["line"] for m in json.loads((ROOT / "profiles/r01/parity_c3full.json").read_text())["mismatches"]]
 CONFIGS = {"tf32+kv16 (the CUDA decoder)": (True, "kv16"), "tf32 only": (True, "exact"), "kv16 only": (False, "kv16"),
-           "tf32+k32v16": (True, "k32v16"), "tf32+k16v32": (True, "k16v32")}
+           "tf32+k32v16": (True, "k32v16"), "tf32+k16v32": (True, "k16v32"),
+           # candidate fixes: activations rounded-to-nearest (not truncated) to TF32 by the producing kernel; exact (two-term)
+           # activations against TF32 weights; fp16 weights (what a 16-bit split-activation GEMM would use)
+           "x rn-tf32, w tf32 + kv16": ("xrn", "kv16"), "x exact, w tf32 + kv16": ("xexact", "kv16"),
+           "x exact, w fp16 + kv16": ("wf16", "kv16")}
+import os
+if os.environ.get("ONLY"):
+    CONFIGS = {k: v for k, v in CONFIGS.items() if any(t in k for t in os.environ["ONLY"].split("|"))}
 
 
 def work(args):
@@ -38,7 +45,14 @@ def work(args):
         def lin(x, w, b=None):
             if not tf32:
                 return orig_linear(x, w, b)
-            y = trunc(x) @ rna(w).T
+            if tf32 == "xrn":
+                y = rna(x) @ rna(w).T
+            elif tf32 == "xexact":
+                y = np.asarray(x, np.float32) @ rna(w).T
+            elif tf32 == "wf16":
+                y = np.asarray(x, np.float32) @ np.asarray(w, np.float32).astype(np.float16).astype(np.float32).T
+            else:
+                y = trunc(x) @ rna(w).T
             return (y + b).astype(np.float32) if b is not None else y.astype(np.float32)
 
         f16 = lambda x: np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
@@ -76,4 +90,4 @@ if __name__ == "__main__":
         out[c] = {"equal_oracle": eq_o, "equal_cuda": eq_g}
         print(c, "-> equal to oracle:", eq_o, "| reproduces CUDA:", eq_g, flush=True)
     (ROOT / "profiles/r02").mkdir(exist_ok=True)
-    (ROOT / "profiles/r02/parity_rootcause8.json").write_text(json.dumps({"lines": LINES, "configs": out}, indent=1))
+    (ROOT / ("profiles/r02/parity_rootcause8" + ("_fixes" if os.environ.get("ONLY") else "") + ".json")).write_text(json.dumps({"lines": LINES, "configs": out}, indent=1))

@@ -65,4 +65,4 @@ def test_predict_page_equals_recognition_of_the_pillow_crops():
         assert got == want and len(got) == 9
         assert sum(len(t) > 3 for t in got) >= 7          # the seven synthetic lines are actually read
     finally:
-        pred.model.close()
+        pred.close()
