@@ -127,6 +127,8 @@ struct kocr_handle {
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
+    int dec_skip = 0;            // diagnosis (tools/inflight_probe.py): bit mask of kernel classes a decode step does NOT launch
+                                 // (1 cross-attention, 2 self-attention, 4 LayerNorm, 8 GEMMs, 16 embed + argmax); results are garbage
     // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
     int kernel_timing = 0;
     struct Site { std::string name; double flops = 0; double ms = 0; int count = 0; };
@@ -584,6 +586,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     const int D = D_MODEL;
     int n_launched = 0;
 #define DSTEP(call) do { if (h->debug_stop <= 0 || n_launched < h->debug_stop) { KOCR_TRY(call); } ++n_launched; } while (0)
+#define DSKIP(bit, stmt) do { if (!(h->dec_skip & (bit))) { stmt; } } while (0)
     int* tokens = buf<int>(h, "tokens");
     const int* sb = buf<int>(h, "step_base");
     const int* fin = buf<int>(h, "finished");
@@ -593,37 +596,38 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     float* dao = buf<float>(h, "daof");
     float* dh = buf<float>(h, "dh");
     const int S2 = h->dec_wide ? 2 : 1, S8 = h->dec_wide ? 8 : 1;   // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8
-    DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches;
+    DSKIP(16, DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches);
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         float* kc = rows ? rows->kcache + l * rows->layer_stride : buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         float* vc = rows ? rows->vcache + l * rows->layer_stride : buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
-        DSTEP(gemm_dec(h, dxt, L, w.sa_in_w, 3 * D, D, S2, parts, s));
-        DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches;
-        DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s));
-        DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx, dxt)); ++g_launches;
-        DSTEP(gemm_dec(h, dxt, L, w.ca_q_w, D, D, S2, parts, s));
-        DSTEP(launch_dec_cross_attn(parts, buf<act16_t>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
+        DSKIP(8, DSTEP(gemm_dec(h, dxt, L, w.sa_in_w, 3 * D, D, S2, parts, s)));
+        DSKIP(2, DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches);
+        DSKIP(8, DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s)));
+        DSKIP(4, DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx, dxt)); ++g_launches);
+        DSKIP(8, DSTEP(gemm_dec(h, dxt, L, w.ca_q_w, D, D, S2, parts, s)));
+        DSKIP(1, DSTEP(launch_dec_cross_attn(parts, buf<act16_t>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
                                     rows ? rows->T : h->d_line_T, max_T, fin,
-                                    dao, L, s, S2, w.ca_q_b)); ++g_launches;
-        DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s));
-        DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx, dxt)); ++g_launches;
+                                    dao, L, s, S2, w.ca_q_b)); ++g_launches);
+        DSKIP(8, DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s)));
+        DSKIP(4, DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx, dxt)); ++g_launches);
         {   // FFN1 keeps its ReLU epilogue (no split): N = 1536 already gives 48 CTAs
             GemmProblem p;
             memset(&p, 0, sizeof p);
             p.M = L; p.N = 4 * D; p.taps = 1; p.cin = D; p.tf32 = 1; p.bn = h->dec_wide ? 64 : 256;
             p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D; p.ep.round_tf32 = 1;
-            DSTEP(launch_gemm_tc(dxt, L, w.l1_w, p, h->num_sms, s));
+            DSKIP(8, DSTEP(launch_gemm_tc(dxt, L, w.l1_w, p, h->num_sms, s)));
         }
-        DSTEP(gemm_dec(h, dh, L, w.l2_w, D, 4 * D, S8, parts, s));
-        DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx, dxt)); ++g_launches;
+        DSKIP(8, DSTEP(gemm_dec(h, dh, L, w.l2_w, D, 4 * D, S8, parts, s)));
+        DSKIP(4, DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx, dxt)); ++g_launches);
     }
-    DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s));
+    DSKIP(8, DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s)));
     const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
     float* trace = (h->trace_logits || rows) ? reinterpret_cast<float*>(h->trace.p) : nullptr;
-    DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,
-                            off, L, forced, trace, s, S2, h->dec_out_b)); ++g_launches;
+    DSKIP(16, DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,
+                            off, L, forced, trace, s, S2, h->dec_out_b)); ++g_launches);
 #undef DSTEP
+#undef DSKIP
     return 0;
 }
 
@@ -639,7 +643,7 @@ int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
 
 // The same 8 positions as one CUDA graph (captured once per (n_lines, max_T bucket, options)).
 int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
-    auto key = std::make_tuple(h->dec_rows, max_T, h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
+    auto key = std::make_tuple(h->dec_rows, max_T, h->dec_skip * 8 + h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
         cudaGraph_t graph = nullptr;
@@ -1020,6 +1024,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
+    if (strcmp(name, "dec_skip") == 0) { h->dec_skip = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }

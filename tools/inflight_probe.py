@@ -37,7 +37,7 @@ class W:
         self.rec.set_option("big_gemm_sms", int(OPTS.get("big_gemm_sms", 0)))
         self.rec.set_option("straggler_threshold", int(OPTS.get("straggler_threshold", 8)))
         self.rec.set_option("blocking_wait", 1 if S > 1 else 0)
-        for k in ("use_graphs", "use_pdl", "dec_cross_impl", "compact_rows", "kv_split"):
+        for k in ("use_graphs", "use_pdl", "dec_cross_impl", "compact_rows", "kv_split", "dec_skip"):
             if k in OPTS:
                 self.rec.set_option(k, int(OPTS[k]))
         self.stream = torch.cuda.Stream()
@@ -52,7 +52,7 @@ class W:
         self.stream.synchronize()
 
     def decode(self):
-        _native.check(self.rec.lib.kocr_decode_greedy(self.rec._h, 0, self.tok.ctypes.data, self.ln.ctypes.data, None))
+        _native.check(self.rec.lib.kocr_decode_greedy(self.rec._h, int(OPTS.get("max_steps", 0)), self.tok.ctypes.data, self.ln.ctypes.data, None))
 
     def full(self):
         self.rec.recognize_lines(self.batch, tokens_out=self.tok, lengths_out=self.ln)
@@ -61,6 +61,13 @@ class W:
 workers = [W(i) for i in range(S)]
 for w in workers:
     w.full()
+if "forced" in OPTS:        # every line stays active for exactly max_steps positions (work attribution with dec_skip)
+    for w in workers:
+        forced = np.full((256, _native.TOKENS_LD), 5, np.int32); forced[:, 0] = 2
+        w.rec.set_forced_tokens(forced)
+        w.rec.set_option("force_tokens", 1)
+        w.rec.set_option("straggler_threshold", 0)
+KINDS = OPTS.get("kinds", "heavy,decode,full").split(",")
 torch.cuda.synchronize()
 
 
@@ -87,7 +94,7 @@ def run(kind, steps):
     return (time.perf_counter() - t0) * 1e3 / steps
 
 
-for kind in (("heavy", "decode", "full") if STEPS > 0 else ()):
+for kind in (KINDS if STEPS > 0 else ()):
     run(kind, S)
     ms = run(kind, STEPS)
     hl = sum(int(w.rec.debug_read("host_launch_us")) for w in workers) / 1e3
