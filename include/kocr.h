@@ -145,7 +145,7 @@ int kocr_set_forced_tokens(kocr_handle* h, const int32_t* tokens /* [n_lines, KO
 /* Copy an intermediate of the last batch to the host (tests only).  Names: "chunks" f32 (n,1,48,100);
  * "pool1" "conv2" "pool2" "conv3" "pool3" "conv5" "pool4" 16-bit dense NWHC activations [n][w][h][C] (pool3 / pool4 are the
  * SE-gated, (2,1)-pooled outputs of conv4 / conv6 - the un-pooled conv4 / conv6 / conv7 outputs exist only for the ResNet
- * baseline); "bins7" 16-bit [n*25 + w][2][512] row-bin sums of conv7; "se_mean3/4/5" f32 [n*25 + w][C] column means;
+ * baseline); "bins7" 16-bit [n*25 + w][2][512] row-bin sums of conv7; "se_mean3/4/5" 16-bit [n*25 + w][C] column means;
  * "patch_in" 16-bit [n*32,1024]; "enc" f32 [n*32,384] (encoder output + global_pos); "memory" f32 [tokens,384];
  * "logits_trace" f32 [n_lines, steps, 128].  Returns the byte size through *bytes_out when dst is NULL. */
 int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out);
@@ -160,7 +160,7 @@ int64_t kocr_launch_count(void);
  * out_f32 / out_a16 unused).  impl 0 = tcgen05 kernel, 1 = CUDA-core check kernel. */
 int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a16, int m, int n, int taps, int cin,
                    int conv_h, int conv_w, int tile_cols, int col_mode, const float* bias, int relu, float* out_f32,
-                   void* out_a16, void* out_pool, float* out_colmean, void* stream);
+                   void* out_a16, void* out_pool, void* out_colmean, void* stream);
 
 #ifdef __cplusplus
 }

@@ -131,8 +131,7 @@ class Recognizer:
 
     DEBUG_DTYPES = {"chunks": np.float32, "enc": np.float32, "memory": np.float32, "logits_trace": np.float32,
                     "dx": np.float32, "dy": np.float32, "daof": np.float32, "dq": np.float32, "dqkv": np.float32,
-                    "dh": np.float32, "logits": np.float32, "se_mean3": np.float32, "se_mean4": np.float32,
-                    "se_mean5": np.float32}
+                    "dh": np.float32, "logits": np.float32}
 
     def __init__(self, weight_blob: bytes, device: int = 0, max_lines: int = 256, max_chunks: int = 4096):
         self.lib = load_library()

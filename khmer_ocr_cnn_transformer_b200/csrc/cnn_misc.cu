@@ -214,7 +214,7 @@ int launch_finalpool(const act16_t* in, int rows_in, act16_t* out, int n_chunks,
 // or, for the last block, gate * row-bin sums -> AdaptiveAvgPool2d((2,32)) -> patch operand.
 // ONE CTA per chunk; the contractions are far below a tcgen05 tile, so they run on mma.sync.m16n8k16 (a16, fp32
 // accumulate) with the means / hidden vector as A operands in shared memory and the weights read from L2 as B fragments.
-// HBM traffic per chunk: 25*C*4 B of means + one read and one write of the POOLED tensor (the r01 kernel read the
+// HBM traffic per chunk: 25*C*2 B of means + one read and one write of the POOLED tensor (the r01 kernel read the
 // un-pooled conv output twice).
 // ------------------------------------------------------------------------------------------
 
@@ -232,14 +232,17 @@ template <int C> struct SeSmem {
     static constexpr size_t A_BYTES = 32 * LDA * 2;
     static constexpr size_t Z_BYTES = 32 * LDZ * 2;
     static constexpr size_t G_BYTES = (size_t)SE_W * C * 4;
-    // the gate (written by FC2) re-uses the storage of the column means (dead once FC1 is done)
-    static constexpr size_t BYTES = Z_BYTES + (A_BYTES > G_BYTES ? A_BYTES : G_BYTES);
+    // the gate (written by FC2) re-uses the storage of the column means (dead once FC1 is done); the final-pool variant
+    // adds room for the chunk's 25 x 2 row-bin sums
+    static constexpr size_t AG_BYTES = A_BYTES > G_BYTES ? A_BYTES : G_BYTES;
+    static constexpr size_t BYTES = Z_BYTES + AG_BYTES;
+    static constexpr size_t BINS_BYTES = (size_t)SE_W * 2 * C * 2;
 };
 
 // ROWS = pooled rows per column (H/2) - or 2 row-bin sums when FINAL.  FINAL = false: pooled is scaled in place;
 // FINAL = true: pooled = bins [col][2][C], out = patch operand [n*32 + k][kh*C + c].
 template <int C, int ROWS, bool FINAL>
-__global__ void __launch_bounds__(SE_THREADS, 3) se_excite_kernel(const float* __restrict__ means /*[n*25 + w][C]*/,
+__global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t* __restrict__ means /*[n*25 + w][C]*/,
                                                                   const act16_t* __restrict__ w0p /*[128][C]*/,
                                                                   const float* __restrict__ b0p,
                                                                   const act16_t* __restrict__ w2p /*[C][128]*/,
@@ -253,17 +256,23 @@ __global__ void __launch_bounds__(SE_THREADS, 3) se_excite_kernel(const float* _
     float* sG = reinterpret_cast<float*>(se_smem + S::Z_BYTES);          // aliases sA (see SeSmem)
     const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- column means (fp32, written by the conv epilogue) -> a16 A operand [32][C] (rows 25..31 zero) ----
+    // ---- the chunk's pooled block (ROWS * 25 * C 16-bit values, contiguous) starts streaming into REGISTERS now: its HBM
+    //      latency is hidden behind the two small contractions below instead of following them ----
+    constexpr int TOTAL = SE_W * ROWS * CG;                 // 16-byte pieces of the block
+    constexpr int PER_THREAD = (TOTAL + SE_THREADS - 1) / SE_THREADS;
+    const uint4* blk_in = reinterpret_cast<const uint4*>(pooled + (long)n * SE_W * ROWS * C);
+    uint4 pre[PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; ++i) {
+        const int idx = tid + i * SE_THREADS;
+        pre[i] = idx < TOTAL ? __ldg(blk_in + idx) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- column means (16-bit, written by the conv epilogue from its fp32 accumulators) -> A operand [32][C] (rows 25..31 zero) ----
     {
-        const float4* msrc = reinterpret_cast<const float4*>(means + (long)n * SE_W * C);
+        const uint4* msrc = reinterpret_cast<const uint4*>(means + (long)n * SE_W * C);
         for (int i = tid; i < 32 * CG; i += SE_THREADS) {
             const int w = i / CG, cg = i - w * CG;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (w < SE_W) {
-                const float4 a = __ldg(msrc + (long)w * (C / 4) + 2 * cg), b = __ldg(msrc + (long)w * (C / 4) + 2 * cg + 1);
-                v = make_uint4(pack_a16(a.x, a.y), pack_a16(a.z, a.w), pack_a16(b.x, b.y), pack_a16(b.z, b.w));
-            }
-            *reinterpret_cast<uint4*>(sA + w * LDA + cg * 8) = v;
+            *reinterpret_cast<uint4*>(sA + w * LDA + cg * 8) = w < SE_W ? __ldg(msrc + i) : make_uint4(0, 0, 0, 0);
         }
     }
     __syncthreads();
@@ -339,21 +348,31 @@ __global__ void __launch_bounds__(SE_THREADS, 3) se_excite_kernel(const float* _
     __syncthreads();
     // ---- excite ----
     if (!FINAL) {
-        uint4* blk = reinterpret_cast<uint4*>(pooled + (long)n * SE_W * ROWS * C);    // the chunk's pooled block is contiguous
-        constexpr int TOTAL = SE_W * ROWS * CG;
-#pragma unroll 4
-        for (int idx = tid; idx < TOTAL; idx += SE_THREADS) {
-            const int cg = idx % CG, w = idx / (ROWS * CG);
-            const uint4 o = blk[idx];
-            const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
-            const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
-            blk[idx] = make_uint4(pack_a16(a16_lo(o.x) * ga.x, a16_hi(o.x) * ga.y),
-                                  pack_a16(a16_lo(o.y) * ga.z, a16_hi(o.y) * ga.w),
-                                  pack_a16(a16_lo(o.z) * gb.x, a16_hi(o.z) * gb.y),
-                                  pack_a16(a16_lo(o.w) * gb.z, a16_hi(o.w) * gb.w));
+        uint4* blk = reinterpret_cast<uint4*>(pooled + (long)n * SE_W * ROWS * C);    // scaled in place
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * SE_THREADS;
+            if (idx < TOTAL) {
+                const int cg = idx % CG, w = idx / (ROWS * CG);
+                const uint4 o = pre[i];
+                const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
+                const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
+                blk[idx] = make_uint4(pack_a16(a16_lo(o.x) * ga.x, a16_hi(o.x) * ga.y),
+                                      pack_a16(a16_lo(o.y) * ga.z, a16_hi(o.y) * ga.w),
+                                      pack_a16(a16_lo(o.z) * gb.x, a16_hi(o.z) * gb.y),
+                                      pack_a16(a16_lo(o.w) * gb.z, a16_hi(o.w) * gb.w));
+            }
         }
     } else {
-        const uint4* bins = reinterpret_cast<const uint4*>(pooled + (long)n * SE_W * 2 * C);
+        // the prefetched row-bin sums go to shared memory: the adaptive pool below reads 1-2 columns per output bin
+        uint4* sB = reinterpret_cast<uint4*>(se_smem + S::BYTES);                     // [25 * 2 * CG] pieces
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * SE_THREADS;
+            if (idx < TOTAL) sB[idx] = pre[i];
+        }
+        __syncthreads();
+        const uint4* bins = sB;
         uint4* dst = reinterpret_cast<uint4*>(out + (long)n * TOK_PER_CHUNK * 2 * C);
 #pragma unroll 4
         for (int idx = tid; idx < TOK_PER_CHUNK * 2 * CG; idx += SE_THREADS) {
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__(SE_THREADS, 3) se_excite_kernel(const float* _
             for (int w = w0; w < w1; ++w) {
                 const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
                 const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
-                const uint4 a = __ldg(bins + (long)(w * 2 + kh) * CG + cg);
+                const uint4 a = bins[(w * 2 + kh) * CG + cg];
                 acc[0] += a16_lo(a.x) * ga.x; acc[1] += a16_hi(a.x) * ga.y;
                 acc[2] += a16_lo(a.y) * ga.z; acc[3] += a16_hi(a.y) * ga.w;
                 acc[4] += a16_lo(a.z) * gb.x; acc[5] += a16_hi(a.z) * gb.y;
@@ -377,9 +396,9 @@ __global__ void __launch_bounds__(SE_THREADS, 3) se_excite_kernel(const float* _
 }
 
 template <int C, int ROWS, bool FINAL>
-static int launch_se_excite_impl(const float* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks,
+static int launch_se_excite_impl(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks,
                                  cudaStream_t stream) {
-    const size_t smem = SeSmem<C>::BYTES;
+    const size_t smem = SeSmem<C>::BYTES + (FINAL ? SeSmem<C>::BINS_BYTES : 0);
     static PerDeviceOnce attr_once;
     KOCR_CUDA(opt_in_dynamic_smem(attr_once, se_excite_kernel<C, ROWS, FINAL>, (int)smem));
     se_excite_kernel<C, ROWS, FINAL><<<n_chunks, SE_THREADS, smem, stream>>>(means, w.w0p, w.b0p, w.w2p, w.b2, pooled, out);
@@ -388,7 +407,7 @@ static int launch_se_excite_impl(const float* means, const SEWeights& w, act16_t
 }
 
 // The three SE sites of the backbone (se_model.py:47,53,59): (C, pooled rows) = (256, 6), (512, 3) and (512, 2 bins) + final pool.
-int launch_se_excite(const float* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
+int launch_se_excite(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
                      int C, bool final_pool, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
     if (W == SE_W && C == 256 && rows == 6 && !final_pool) return launch_se_excite_impl<256, 6, false>(means, w, pooled, out, n_chunks, stream);

@@ -54,7 +54,7 @@ struct GemmKernelParams {
 // lane = channel, warp = every 4th column, and emit the pooled rows and the column mean of each whole column.
 template <int H, int MODE>
 __device__ __forceinline__ void column_phase(uint32_t hs_base, int wq, int lane, int kc, long col0, long total_cols,
-                                             act16_t* __restrict__ out_pool, float* __restrict__ out_colmean, int N, int nc) {
+                                             act16_t* __restrict__ out_pool, act16_t* __restrict__ out_colmean, int N, int nc) {
     constexpr int HO = MODE == 1 ? H / 2 : 2;
     const uint32_t lane_off = (uint32_t)(lane & 3) << 2;
     const int piece = lane >> 2;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void column_phase(uint32_t hs_base, int wq, int lane,
             float sum = 0.f;
 #pragma unroll
             for (int h = 0; h < H; ++h) sum += v[h];
-            out_colmean[gcol * N + nc + lane] = sum * (1.f / (float)H);
+            out_colmean[gcol * N + nc + lane] = to_a16(sum * (1.f / (float)H));
         }
         act16_t* o = out_pool + (gcol * HO) * (long)N + nc + lane;
 #pragma unroll
@@ -81,6 +81,25 @@ __device__ __forceinline__ void column_phase(uint32_t hs_base, int wq, int lane,
 }
 
 // BK is 128 bytes of K per row in both precisions: 64 a16 or 32 fp32 (TF32) elements.
+// 2x2 max-pool variant (conv2, H = 24): the tile holds an even number of columns; pooled pixel (column pair j2, row pair i)
+// is the max over rows 2i, 2i+1 of columns 2*j2, 2*j2+1.  Output [pooled column][H/2][N].
+template <int H>
+__device__ __forceinline__ void column_phase_2x2(uint32_t hs_base, int wq, int lane, int kc, long col0, long total_cols,
+                                                 act16_t* __restrict__ out_pool, int N, int nc) {
+    constexpr int HO = H / 2;
+    const uint32_t lane_off = (uint32_t)(lane & 3) << 2;
+    const int piece = lane >> 2;
+    auto ld = [&](int r) { return ld_shared_f32(hs_base + r * 128 + (((piece ^ (r & 7)) << 4) | lane_off)); };
+    for (int pp = wq; pp < (kc / 2) * HO; pp += 4) {
+        const int j2 = pp / HO, i = pp - j2 * HO;
+        const long gcol = col0 + 2 * j2;
+        if (gcol + 1 >= total_cols) continue;
+        const int r0 = (2 * j2) * H + 2 * i, r1 = r0 + H;
+        const float v = fmaxf(fmaxf(ld(r0), ld(r0 + 1)), fmaxf(ld(r1), ld(r1 + 1)));
+        out_pool[((gcol >> 1) * HO + i) * (long)N + nc + lane] = to_a16(v);
+    }
+}
+
 template <int BN, bool TF32, bool COLF>
 __global__ void __launch_bounds__((GemmCfg<BN, TF32>::THREADS), (GemmCfg<BN, TF32>::MIN_CTAS))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -288,7 +307,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
                     named_bar_sync(1 + half, 128);                  // all 128 rows of the block are in shared memory
                     const long col0 = (long)m_tile * p.tile_cols;
-                    if (p.conv_H == 12) column_phase<12, 1>(hs_base, quad, lane, p.tile_cols, col0, p.total_cols, ep.out_pool, ep.out_colmean, p.N, nc);
+                    if (p.conv_H == 24) column_phase_2x2<24>(hs_base, quad, lane, p.tile_cols, col0, p.total_cols, ep.out_pool, p.N, nc);
+                    else if (p.conv_H == 12) column_phase<12, 1>(hs_base, quad, lane, p.tile_cols, col0, p.total_cols, ep.out_pool, ep.out_colmean, p.N, nc);
                     else if (p.conv_H == 6) column_phase<6, 1>(hs_base, quad, lane, p.tile_cols, col0, p.total_cols, ep.out_pool, ep.out_colmean, p.N, nc);
                     else column_phase<3, 2>(hs_base, quad, lane, p.tile_cols, col0, p.total_cols, ep.out_pool, ep.out_colmean, p.N, nc);
                     return;
@@ -435,15 +455,25 @@ __global__ void gemm_simt_check_col_kernel(const act16_t* __restrict__ a, long r
     const int n = (int)(idx - col * p.N);
     const GemmEpilogue& ep = p.ep;
     const int H = p.conv_H;
-    float y[12];
+    float y[24];
     float sum = 0.f;
     for (int h = 0; h < H; ++h) {
         const long row = col * H + h;
         y[h] = check_act(check_dot(a, rowsA, w, p, row, n), ep, row, n);
         sum += y[h];
     }
-    if (ep.out_colmean) ep.out_colmean[col * p.N + n] = sum / (float)H;
-    if (ep.col_mode == 1) {
+    if (ep.out_colmean) ep.out_colmean[col * p.N + n] = to_a16(sum / (float)H);
+    if (ep.col_mode == 3) {          // 2x2 max-pool: this thread owns the pooled column col / 2 (even columns only)
+        if ((col & 1) || col + 1 >= p.total_cols) return;
+        for (int i = 0; i < H / 2; ++i) {
+            float m = fmaxf(y[2 * i], y[2 * i + 1]);
+            for (int r = 0; r < 2; ++r) {
+                const long row = (col + 1) * H + 2 * i + r;
+                m = fmaxf(m, check_act(check_dot(a, rowsA, w, p, row, n), ep, row, n));
+            }
+            ep.out_pool[((col >> 1) * (H / 2) + i) * p.N + n] = to_a16(m);
+        }
+    } else if (ep.col_mode == 1) {
         for (int i = 0; i < H / 2; ++i) ep.out_pool[(col * (H / 2) + i) * p.N + n] = to_a16(fmaxf(y[2 * i], y[2 * i + 1]));
     } else {
         for (int i = 0; i < 2; ++i) ep.out_pool[(col * 2 + i) * p.N + n] = to_a16(y[i] + y[i + 1]);
@@ -570,10 +600,11 @@ static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
         }
     }
     if (p.ep.col_mode) {
-        KOCR_CHECK(p.taps == 9 && p.tile_cols > 0 && BN == 256 && !p.tf32 && p.ep.out_pool && !p.ep.addend,
-                   "gemm: the column-fused epilogue needs a conv with whole-column tiles, the 256-wide N tile and out_pool");
-        KOCR_CHECK((p.ep.col_mode == 1 && (p.conv_H == 12 || p.conv_H == 6)) || (p.ep.col_mode == 2 && p.conv_H == 3),
-                   "gemm: column-fused epilogue: unsupported (mode %d, H %d)", p.ep.col_mode, p.conv_H);
+        KOCR_CHECK(p.taps == 9 && p.tile_cols > 0 && (BN == 256 || BN == 128) && !p.tf32 && p.ep.out_pool && !p.ep.addend,
+                   "gemm: the column-fused epilogue needs a conv with whole-column tiles, a 128 / 256-wide N tile and out_pool");
+        KOCR_CHECK((p.ep.col_mode == 1 && (p.conv_H == 12 || p.conv_H == 6)) || (p.ep.col_mode == 2 && p.conv_H == 3) ||
+                   (p.ep.col_mode == 3 && p.conv_H == 24 && p.tile_cols % 2 == 0 && p.conv_W % 2 == 0),
+                   "gemm: column-fused epilogue: unsupported (mode %d, H %d, %d columns per tile)", p.ep.col_mode, p.conv_H, p.tile_cols);
     }
     kp.num_m_tiles = (p.M + kp.tile_rows - 1) / kp.tile_rows;
     kp.num_n_tiles = p.N / BN;
@@ -614,7 +645,8 @@ int launch_gemm_tc(const void* a, long rowsA, const void* w, const GemmProblem& 
     // N tile: 256 where it divides N, else 128 (option gemm_bn192: 192 for N = 1152 / 384 - fewer, fatter tiles, but slower)
     const int bn = p.bn > 0 ? p.bn : (p.N % 256 == 0 ? 256 : ((!p.tf32 && g_bn192 && p.N % 192 == 0) ? 192 : 128));
     if (p.ep.col_mode) {
-        KOCR_CHECK(bn == 256 && !p.tf32, "gemm: the column-fused epilogue needs the 256-wide 16-bit tile");
+        KOCR_CHECK((bn == 256 || bn == 128) && !p.tf32, "gemm: the column-fused epilogue needs a 128 / 256-wide 16-bit tile");
+        if (bn == 128) return launch_impl<128, false, true>(a, rowsA, w, p, num_sms, stream);
         return launch_impl<256, false, true>(a, rowsA, w, p, num_sms, stream);
     }
     if (p.tf32) {
@@ -634,7 +666,7 @@ int launch_gemm_simt_check(const act16_t* a, long rowsA, const act16_t* w, const
                            cudaStream_t stream) {
     KOCR_CHECK(!p.tf32, "gemm check kernel: a16 operands only");
     GemmKernelParams kp;
-    KOCR_TRY(fill_params(kp, p, p.ep.col_mode ? 256 : 128));
+    KOCR_TRY(fill_params(kp, p, (p.ep.col_mode && p.N % 256 == 0) ? 256 : 128));
     if (p.ep.col_mode) {
         const long total = kp.total_cols * p.N;
         gemm_simt_check_col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, rowsA, w, kp);

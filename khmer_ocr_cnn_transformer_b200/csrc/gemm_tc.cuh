@@ -32,11 +32,12 @@ struct GemmEpilogue {
     //   col_mode 1: (2,1) max-pool over the row pairs of every column  -> out_pool [col][H/2][N]   (se_model.py:69-73 pool3/pool4)
     //   col_mode 2: H == 3: the two overlapping row bins of AdaptiveAvgPool2d((2, .)), as SUMS y0+y1, y1+y2
     //                                                                   -> out_pool [col][2][N]     (se_model.py:61,78)
-    //   both also write the column means over H (the SequenceSE squeeze, se_model.py:20-22) -> out_colmean [col][N] fp32,
-    //   computed from the fp32 accumulators.  out_a16 / out_f32 are not written in these modes.
+    //   col_mode 3: H == 24: 2x2 max-pool over column PAIRS (tile_cols even)        -> out_pool [col/2][12][N]  (se_model.py:65 pool2)
+    //   modes 1 / 2 also write the column means over H (the SequenceSE squeeze, se_model.py:20-22) -> out_colmean [col][N],
+    //   16-bit, computed from the fp32 accumulators.  out_a16 / out_f32 are not written in these modes.
     int col_mode;
     act16_t* out_pool;
-    float* out_colmean;       // may be null (baselines without SE)
+    act16_t* out_colmean;     // may be null (baselines without SE)
 };
 
 struct GemmProblem {

@@ -47,10 +47,10 @@ int launch_pool_h2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, 
 // AdaptiveAvgPool2d((2,32)) of a (3, W) map without a gate -> patch GEMM operand [n*32 + k][kh*C + c];
 // rows_in = 2: `in` = row-bin sums [col][2][C] from the conv7 epilogue, rows_in = 3: raw rows [col][3][C].
 int launch_finalpool(const act16_t* in, int rows_in, act16_t* out, int n_chunks, int W, int C, cudaStream_t stream);
-// 1D-SE excitation on the column means fp32 [n*W + w][C] written by the conv epilogue: gate = sigmoid(FC2(relu(FC1(mean))));
+// 1D-SE excitation on the 16-bit column means [n*W + w][C] written by the conv epilogue: gate = sigmoid(FC2(relu(FC1(mean))));
 // pooled [col][rows][C] *= gate in place, or (final_pool) gate * row-bin sums -> AdaptiveAvgPool2d((2,32)) -> out.
 struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; const float* b2; };
-int launch_se_excite(const float* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
+int launch_se_excite(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
                      int C, bool final_pool, cudaStream_t stream);
 
 // ---- stage 4/5 helpers -----------------------------------------------------------------

@@ -127,6 +127,7 @@ struct kocr_handle {
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
+    int pool2_fused = 1;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue; 0: separate kernel (A/B tests)
     int dec_skip = 0;            // diagnosis (tools/inflight_probe.py): bit mask of kernel classes a decode step does NOT launch
                                  // (1 cross-attention, 2 self-attention, 4 LayerNorm, 8 GEMMs, 16 embed + argmax); results are garbage
     // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
@@ -254,7 +255,7 @@ int resolve_weights(kocr_handle* h) {
 
 // activation geometry per stage of the backbone (dense NWHC: [chunk][W][H][C]); cols = whole columns per GEMM M tile
 struct StageGeom { int H, W, cols; };
-const StageGeom G1 = {24, 50, 5}, G2 = {12, 25, 10}, G3 = {6, 25, 21}, G4 = {3, 25, 42};
+const StageGeom G1 = {24, 50, 4}, G2 = {12, 25, 10}, G3 = {6, 25, 21}, G4 = {3, 25, 42};
 inline size_t px(const StageGeom& g) { return (size_t)g.H * g.W; }
 
 struct WsItem { const char* name; size_t bytes; };
@@ -279,7 +280,7 @@ int carve_workspace(kocr_handle* h) {
         {"conv3", NC * px(G2) * 256 * 2},  {"pool3", NC * px(G3) * 256 * 2},
         {"conv5", NC * px(G3) * 512 * 2},  {"pool4", NC * px(G4) * 512 * 2},
         {"bins7", NC * 25 * 2 * 512 * 2},  {"patch_in", M * 1024 * 2},
-        {"se_mean3", NC * 25 * 256 * 4},   {"se_mean4", NC * 25 * 512 * 4}, {"se_mean5", NC * 25 * 512 * 4},
+        {"se_mean3", NC * 25 * 256 * 2},   {"se_mean4", NC * 25 * 512 * 2}, {"se_mean5", NC * 25 * 512 * 2},
         {"x", M * D * 4},   {"xb", M * D * 2},  {"qkv", M * 3 * D * 2}, {"ao", M * D * 2}, {"y", M * D * 4},
         {"hff", M * 1024 * 2},
         {"gin", M * 8 * LSTM_H * 4}, {"mem", M * D * 4}, {"memb", M * D * 2}, {"kv", M * 4 * D * 2}, {"kv_a3", M * 3 * D * 2},
@@ -396,7 +397,7 @@ int gemm_conv(kocr_handle* h, const act16_t* in, act16_t* out, int n_chunks, con
 // The same convolution with the column-fused epilogue (whole-column M tiles): writes the (2,1)-max-pooled rows
 // (mode 1: [col][H/2][Cout]) or the AdaptiveAvgPool row-bin sums (mode 2, H = 3: [col][2][Cout]) and, if `colmean` is
 // given, the SequenceSE column means [col][Cout] fp32 - the un-pooled conv output is never stored.
-int gemm_conv_colfused(kocr_handle* h, const act16_t* in, act16_t* out_pool, float* colmean, int mode, int n_chunks,
+int gemm_conv_colfused(kocr_handle* h, const act16_t* in, act16_t* out_pool, act16_t* colmean, int mode, int n_chunks,
                        const StageGeom& g, int Cin, int Cout, const act16_t* w, const float* b, int relu, cudaStream_t s) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
@@ -405,7 +406,7 @@ int gemm_conv_colfused(kocr_handle* h, const act16_t* in, act16_t* out_pool, flo
     p.ep = ep_none();
     p.ep.bias = b; p.ep.relu = relu;
     p.ep.col_mode = mode; p.ep.out_pool = out_pool; p.ep.out_colmean = colmean;
-    p.bn = 256;
+    p.bn = Cout % 256 == 0 ? 256 : 128;
     const int sms = h->big_gemm_sms > 0 ? std::min(h->big_gemm_sms, h->num_sms) : h->num_sms;
     return launch_gemm_tc(in, (long)p.M, w, p, sms, s);
 }
@@ -467,20 +468,24 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     // the SE excitation then scales the pooled tensor in place (gate > 0 commutes with the max).
     TIMED("conv1_pool1", cf(48, 100, 1, 64), launch_conv1_pool_mma(buf<float>(h, "chunks"), h->conv1_w16, h->conv1_b, B("pool1"), NC, s));
     ++g_launches;
-    TIMED("conv2", cf(24, 50, 64, 128), gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
-    TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
+    if (h->pool2_fused) {       // conv2 + 2x2 max-pool in one kernel (4 whole columns per M tile): the 24x50x128 conv output never reaches HBM
+        TIMED("conv2", cf(24, 50, 64, 128), gemm_conv_colfused(h, B("pool1"), B("pool2"), nullptr, 3, NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
+    } else {
+        TIMED("conv2", cf(24, 50, 64, 128), gemm_conv(h, B("pool1"), B("conv2"), NC, G1, 64, 128, h->conv_w[2], h->conv_b[2], 1, s));
+        TIMED("pool2", 0, launch_pool2x2(B("conv2"), B("pool2"), NC, 24, 50, 128, s)); ++g_launches;
+    }
     TIMED("conv3", cf(12, 25, 128, 256), gemm_conv(h, B("pool2"), B("conv3"), NC, G2, 128, 256, h->conv_w[3], h->conv_b[3], 1, s));
-    TIMED("conv4", cf(12, 25, 256, 256), gemm_conv_colfused(h, B("conv3"), B("pool3"), se ? buf<float>(h, "se_mean3") : nullptr, 1, NC, G2, 256, 256,
+    TIMED("conv4", cf(12, 25, 256, 256), gemm_conv_colfused(h, B("conv3"), B("pool3"), se ? buf<act16_t>(h, "se_mean3") : nullptr, 1, NC, G2, 256, 256,
                                                             h->conv_w[4], h->conv_b[4], 1, s));
-    if (se) { TIMED("se3_excite", 4.0 * nc * 25 * 256 * 16, launch_se_excite(buf<float>(h, "se_mean3"), h->se[0], B("pool3"), nullptr, NC, 6, 25, 256, false, s)); ++g_launches; }
+    if (se) { TIMED("se3_excite", 4.0 * nc * 25 * 256 * 16, launch_se_excite(buf<act16_t>(h, "se_mean3"), h->se[0], B("pool3"), nullptr, NC, 6, 25, 256, false, s)); ++g_launches; }
     TIMED("conv5", cf(6, 25, 256, 512), gemm_conv(h, B("pool3"), B("conv5"), NC, G3, 256, 512, h->conv_w[5], h->conv_b[5], 1, s));
-    TIMED("conv6", cf(6, 25, 512, 512), gemm_conv_colfused(h, B("conv5"), B("pool4"), se ? buf<float>(h, "se_mean4") : nullptr, 1, NC, G3, 512, 512,
+    TIMED("conv6", cf(6, 25, 512, 512), gemm_conv_colfused(h, B("conv5"), B("pool4"), se ? buf<act16_t>(h, "se_mean4") : nullptr, 1, NC, G3, 512, 512,
                                                            h->conv_w[6], h->conv_b[6], 1, s));
-    if (se) { TIMED("se4_excite", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<float>(h, "se_mean4"), h->se[1], B("pool4"), nullptr, NC, 3, 25, 512, false, s)); ++g_launches; }
+    if (se) { TIMED("se4_excite", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<act16_t>(h, "se_mean4"), h->se[1], B("pool4"), nullptr, NC, 3, 25, 512, false, s)); ++g_launches; }
     // conv7: SE model = conv + bn7 + relu7 (se_model.py:75); VGG baseline = bare conv (vgg_model.py:57)
-    TIMED("conv7", cf(3, 25, 512, 512), gemm_conv_colfused(h, B("pool4"), B("bins7"), se ? buf<float>(h, "se_mean5") : nullptr, 2, NC, G4, 512, 512,
+    TIMED("conv7", cf(3, 25, 512, 512), gemm_conv_colfused(h, B("pool4"), B("bins7"), se ? buf<act16_t>(h, "se_mean5") : nullptr, 2, NC, G4, 512, 512,
                                                            h->conv_w[7], h->conv_b[7], se ? 1 : 0, s));
-    if (se) { TIMED("se5_excite_finalpool", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<float>(h, "se_mean5"), h->se[2], B("bins7"), B("patch_in"), NC, 2, 25, 512, true, s)); ++g_launches; }
+    if (se) { TIMED("se5_excite_finalpool", 4.0 * nc * 25 * 512 * 32, launch_se_excite(buf<act16_t>(h, "se_mean5"), h->se[2], B("bins7"), B("patch_in"), NC, 2, 25, 512, true, s)); ++g_launches; }
     else { TIMED("final_pool", 0, launch_finalpool(B("bins7"), 2, B("patch_in"), NC, 25, 512, s)); ++g_launches; }
     }   // SE / VGG backbone
 
@@ -1025,6 +1030,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_skip") == 0) { h->dec_skip = value; return 0; }
+    if (strcmp(name, "pool2_fused") == 0) { h->pool2_fused = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
@@ -1281,8 +1287,8 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
     else if (n == "pool4") act("pool4", G4, 512);
     else if (n == "conv7") act("conv7", G4, 512);            // ResNet baseline only
     else if (n == "bins7") { src = h->named["bins7"].p; bytes = NC * 25 * 2 * 512 * 2; }
-    else if (n == "se_mean3") { src = h->named["se_mean3"].p; bytes = NC * 25 * 256 * 4; }
-    else if (n == "se_mean4" || n == "se_mean5") { src = h->named[n].p; bytes = NC * 25 * 512 * 4; }
+    else if (n == "se_mean3") { src = h->named["se_mean3"].p; bytes = NC * 25 * 256 * 2; }
+    else if (n == "se_mean4" || n == "se_mean5") { src = h->named[n].p; bytes = NC * 25 * 512 * 2; }
     else if (n == "patch_in") { src = h->named["patch_in"].p; bytes = M * 1024 * 2; }
     else if (n == "enc") { src = h->named["x"].p; bytes = M * D_MODEL * 4; }
     else if (n == "memory") { src = h->named[h->variant == 0 ? "mem" : "x"].p; bytes = M * D_MODEL * 4; }
@@ -1305,7 +1311,7 @@ int kocr_debug_read(kocr_handle* h, const char* name, void* dst, size_t dst_byte
 
 int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a16, int m, int n, int taps, int cin,
                    int conv_h, int conv_w, int tile_cols, int col_mode, const float* bias, int relu, float* out_f32,
-                   void* out_a16, void* out_pool, float* out_colmean, void* stream) {
+                   void* out_a16, void* out_pool, void* out_colmean, void* stream) {
     GemmProblem p;
     memset(&p, 0, sizeof p);
     p.M = m; p.N = n; p.taps = taps; p.cin = cin;
@@ -1316,8 +1322,8 @@ int kocr_test_gemm(int impl, const void* a_a16, int64_t rows_a, const void* w_a1
     p.ep.bias = bias; p.ep.relu = relu;
     p.ep.out_f32 = out_f32; p.ep.ld_f32 = n;
     p.ep.out_a16 = reinterpret_cast<act16_t*>(out_a16); p.ep.ld_a16 = n;
-    p.ep.col_mode = col_mode; p.ep.out_pool = reinterpret_cast<act16_t*>(out_pool); p.ep.out_colmean = out_colmean;
-    if (col_mode) p.bn = 256;
+    p.ep.col_mode = col_mode; p.ep.out_pool = reinterpret_cast<act16_t*>(out_pool); p.ep.out_colmean = reinterpret_cast<act16_t*>(out_colmean);
+    if (col_mode) p.bn = n % 256 == 0 ? 256 : 128;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     p.tf32 = impl == 2 ? 1 : 0;          // impl 2: fp32 operands consumed as TF32
     if (impl == 1)

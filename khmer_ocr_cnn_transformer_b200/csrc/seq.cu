@@ -588,14 +588,14 @@ static constexpr int LM_THREADS = 384;
 
 size_t bilstm_whh_mma_elems() { return (size_t)2 * 2 * 12 * 2 * 12 * 32 * 8; }   // a16 elements
 
-// Fast gate non-linearities for the tensor-core recurrence: ex2/rcp and tanh.approx MUFU ops (relative error
-// ~2^-11, far below the a16 rounding of the memory that feeds the decoder); the accurate expf/tanhf sequences
-// were the longest part of a recurrence step.
+// Gate non-linearities of the tensor-core recurrence on the MUFU ex2 / rcp units (errors ~1e-6).  The branchy accurate
+// expf / tanhf sequences were the longest part of a recurrence step; `tanh.approx.f32` (one MUFU op, but a relative error
+// of 2^-11 = 5e-4 on every cell and hidden value) was as large as the whole 16-bit error budget of the memory, so tanh is
+// computed as 1 - 2 / (1 + e^2x) instead: two MUFU ops, absolute error ~1e-7.
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+    const float e = __expf(2.f * fminf(x, 15.f));            // (e^30 is finite; tanh(15) == 1 in fp32)
+    return 1.f - __fdividef(2.f, 1.f + e);
 }
 
 __device__ __forceinline__ void mma_a16_16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {

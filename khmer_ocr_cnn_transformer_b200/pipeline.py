@@ -106,11 +106,13 @@ class LinePipeline:
                 on_done(job)
 
         def straggler_pass(rec, part):
-            ids = [i for i, _ in part]
             rec.set_option("straggler_threshold", 0)
-            tok, ln = rec.recognize_lines(_native.LineBatch([image_of(i) for i in ids]), max_steps=max_steps)
-            tokens[ids] = tok
-            lengths[ids] = ln
+            imgs = [image_of(i) for i, _ in part]
+            for sub in self.plan([im.shape for im in imgs]):          # (a pool of long lines can exceed one pass's chunk capacity)
+                ids = [part[k][0] for k in sub]
+                tok, ln = rec.recognize_lines(_native.LineBatch([imgs[k] for k in sub]), max_steps=max_steps)
+                tokens[ids] = tok
+                lengths[ids] = ln
             done = []
             with self._lock:
                 self.stats["straggler_passes"] += 1

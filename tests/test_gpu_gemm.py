@@ -20,14 +20,14 @@ def _run(impl, a, w, M, N, taps, cin, bias, relu, conv=(0, 0), tile_cols=0, col_
     H, W = conv
     if col_mode:
         cols = M // H
-        rows_out = cols * (H // 2 if col_mode == 1 else 2)
+        rows_out = {1: cols * (H // 2), 2: cols * 2, 3: (cols // 2) * (H // 2)}[col_mode]
         pool = torch.zeros(rows_out, N, dtype=_a16(), device="cuda")
-        mean = torch.zeros(cols, N, dtype=torch.float32, device="cuda")
+        mean = torch.zeros(cols, N, dtype=_a16(), device="cuda")
         _native.check(lib.kocr_test_gemm(impl, a.data_ptr(), a.shape[0], w.data_ptr(), M, N, taps, cin, H, W, tile_cols, col_mode,
                                          b.data_ptr() if b is not None else None, relu, None, None, pool.data_ptr(),
                                          mean.data_ptr(), None))
         torch.cuda.synchronize()
-        return pool.float().cpu().numpy(), mean.cpu().numpy()
+        return pool.float().cpu().numpy(), mean.float().cpu().numpy()
     out32 = torch.zeros(M, N, dtype=torch.float32, device="cuda")
     out16 = torch.zeros(M, N, dtype=_a16(), device="cuda")
     _native.check(lib.kocr_test_gemm(impl, a.data_ptr(), a.shape[0], w.data_ptr(), M, N, taps, cin, H, W, tile_cols, 0,
@@ -101,6 +101,7 @@ COL_CASES = [
     (7, (6, 25), 21, 512, 512, 1, 1),           # conv6: 21 columns x 6 rows (126 of 128 MMA rows), tiles straddle images
     (9, (3, 25), 42, 512, 512, 2, 1),           # conv7 (SE model): 42 columns x 3 rows, adaptive-pool row-bin sums
     (4, (3, 25), 42, 512, 512, 2, 0),           # conv7 of the VGG baseline: no ReLU
+    (3, (24, 50), 4, 64, 128, 3, 1),            # conv2: 4 columns x 24 rows per tile, 2x2 max-pool (N tile 128)
 ]
 
 
@@ -119,13 +120,17 @@ def test_gemm_column_fused_epilogue(n_img, conv, tile_cols, cin, N, col_mode, re
     want_mean = y.mean(axis=1)
     if col_mode == 1:
         want_pool = np.maximum(y[:, 0::2], y[:, 1::2]).reshape(-1, N)
-    else:
+    elif col_mode == 2:
         want_pool = np.stack([y[:, 0] + y[:, 1], y[:, 1] + y[:, 2]], axis=1).reshape(-1, N)
+    else:
+        want_pool = y.reshape(n_img * W // 2, 2, H // 2, 2, N).max(axis=(1, 3)).reshape(-1, N)
+    ulp = 2.0 ** -10 if _a16() == torch.float16 else 2.0 ** -7
     for impl in (1, 0):
         pool, mean = _run(impl, a, w, M, N, 9, cin, bias, relu, conv, tile_cols, col_mode)
-        assert np.abs(mean - want_mean).max() < 2e-3, f"impl {impl}: column means"
+        if col_mode != 3:       # (the 2x2 pool after conv2 has no SE block behind it: no column means)
+            assert np.all(np.abs(mean - want_mean) <= 2e-3 + np.abs(want_mean) * ulp), f"impl {impl}: column means"
         # pooled values are rounded to 16 bits once: compare within one 16-bit ulp of the fp64 result
-        tol = 2e-3 + np.abs(want_pool) * (2.0 ** -10 if _a16() == torch.float16 else 2.0 ** -7)
+        tol = 2e-3 + np.abs(want_pool) * ulp
         assert np.all(np.abs(pool - want_pool) <= tol), f"impl {impl}: pooled rows, max err {np.abs(pool - want_pool).max()}"
 
 

@@ -120,7 +120,7 @@ def _check_backbone(rec, sd, variant, imgs, tag):
         worst[name] = rel_err(nwhc_to_nchw(rec.debug_read(name), n, H, W, C), taps[name])
     if variant == "se":
         for name, tap, C in (("se_mean3", "conv4", 256), ("se_mean4", "conv6", 512)):
-            got = rec.debug_read(name).reshape(n, 25, C)                       # [n][w][c]
+            got = bf16_u16_to_f32(rec.debug_read(name)).reshape(n, 25, C)      # [n][w][c]
             worst[name] = rel_err(got, taps[tap].mean(axis=2).transpose(0, 2, 1))
     else:           # VGG baseline: conv7 is a bare conv; its epilogue writes the two adaptive-pool row bins as sums
         y = taps["conv7"]                                                      # (n, 512, 3, 25)

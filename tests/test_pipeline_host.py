@@ -24,6 +24,8 @@ class FakeRecognizer:
     def recognize_lines(self, batch, max_steps=0, stream=None, pixels_dev_ptr=None, tokens_out=None, lengths_out=None):
         self.calls += 1
         assert batch.n <= self.max_lines
+        from khmer_ocr_cnn_transformer_b200.scheduling import chunks_for
+        assert sum(chunks_for(int(h), int(w)) for h, w in zip(batch.heights, batch.widths)) <= self.max_chunks
         tok = np.zeros((batch.n, _native.TOKENS_LD), np.int32)
         ln = np.zeros(batch.n, np.int32)
         flags = np.zeros(batch.n, np.int32)
