@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libkocr_b200.so"
-SOURCES = ["kocr_api.cu", "gemm_tc.cu", "preprocess.cu", "cnn_misc.cu", "seq.cu"]
+SOURCES = ["kocr_api.cu", "gemm_tc.cu", "dec_fused.cu", "preprocess.cu", "cnn_misc.cu", "seq.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -578,6 +578,10 @@ static std::atomic<long> g_gemm_launches{0};
 static int g_bn192 = 0;                 // 192-wide N tile for N = 1152 / 384: measured SLOWER than 128 (qkv 0.206 vs 0.161 ms), kept as an A/B option
 void set_gemm_bn192(int on) { g_bn192 = on; }
 long gemm_tc_launch_count() { return g_gemm_launches.load(); }
+void gemm_tc_count_launch() { ++g_gemm_launches; }
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esize) {
+    return make_tmap(out, ptr, rows, cols, box_rows, esize);
+}
 
 static int fill_params(GemmKernelParams& kp, const GemmProblem& p, int BN) {
     const int bke = p.tf32 ? 32 : 64;

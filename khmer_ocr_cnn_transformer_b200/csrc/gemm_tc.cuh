@@ -64,6 +64,10 @@ int launch_gemm_tc(const void* a, long rowsA, const void* w,
 int launch_gemm_simt_check(const act16_t* a, long rowsA, const act16_t* w,
                            const GemmProblem& p, cudaStream_t stream);
 long gemm_tc_launch_count();
+void gemm_tc_count_launch();          // other tcgen05 kernels (dec_fused.cu) add their launches to the same counter
+// Cached 2-D tiled tensor map of a row-major [rows, cols] matrix (esize 2: a16, 4: fp32): box = {128 bytes of K, box_rows},
+// 128-byte swizzle, zero fill out of bounds.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esize);
 void set_gemm_bn192(int on);   // 1: N = 1152 / 384 16-bit GEMMs use 128 x 192 tiles (measured slower); 0 (default): 128 x 128
 
 }  // namespace kocr

@@ -127,7 +127,9 @@ struct kocr_handle {
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
-    int pool2_fused = 1;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue; 0: separate kernel (A/B tests)
+    int dec_fused = 1;           // 1: GEMM+LayerNorm and out_proj+argmax+embed kernels of dec_fused.cu (17 launches per position); 0: 25 launches
+    int pool2_fused = 0;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue (4 whole columns = 96 of 128 MMA rows per tile:
+                                 // measured 5 % SLOWER than conv2 + pool2x2_kernel, profiles/r02); 0 (default): separate kernel
     int dec_skip = 0;            // diagnosis (tools/inflight_probe.py): bit mask of kernel classes a decode step does NOT launch
                                  // (1 cross-attention, 2 self-attention, 4 LayerNorm, 8 GEMMs, 16 embed + argmax); results are garbage
     // optional per-launch CUDA-event timing of the one-time stages (bench.py roofline)
@@ -586,7 +588,7 @@ struct DecRows {
     const int *tok_off, *T;          // device arrays [n_rows]
 };
 
-int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRows* rows = nullptr) {
+int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRows* rows = nullptr, bool embed_first = true) {
     const int L = rows ? rows->n_rows : h->dec_rows;
     const int D = D_MODEL;
     int n_launched = 0;
@@ -601,21 +603,29 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     float* dao = buf<float>(h, "daof");
     float* dh = buf<float>(h, "dh");
     const int S2 = h->dec_wide ? 2 : 1, S8 = h->dec_wide ? 8 : 1;   // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8
-    DSKIP(16, DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches);
+    const bool fused = h->dec_fused != 0;
+    // fused path: the embedding of this position was written by the previous position's out_proj + argmax kernel
+    if (!fused || embed_first) DSKIP(16, DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches);
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         float* kc = rows ? rows->kcache + l * rows->layer_stride : buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         float* vc = rows ? rows->vcache + l * rows->layer_stride : buf<float>(h, "vcache") + (size_t)l * h->max_lines * DEC_MAX * D;
         DSKIP(8, DSTEP(gemm_dec(h, dxt, L, w.sa_in_w, 3 * D, D, S2, parts, s)));
         DSKIP(2, DSTEP(launch_dec_self_attn(parts, kc, vc, tokens, sb, off, fin, dao, L, s, S2, w.sa_in_b)); ++g_launches);
+        if (fused) DSKIP(8, DSTEP(launch_dec_gemm_ln(dao, L, D, w.sa_out_w, w.sa_out_b, dx, w.n1_g, w.n1_b, dx, dxt, s)));
+        else {
         DSKIP(8, DSTEP(gemm_dec(h, dao, L, w.sa_out_w, D, D, S2, parts, s)));
         DSKIP(4, DSTEP(launch_layernorm(parts, w.n1_g, w.n1_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.sa_out_b, dx, dxt)); ++g_launches);
+        }
         DSKIP(8, DSTEP(gemm_dec(h, dxt, L, w.ca_q_w, D, D, S2, parts, s)));
         DSKIP(1, DSTEP(launch_dec_cross_attn(parts, buf<act16_t>(h, "kv"), l, rows ? rows->tok_off : h->d_line_tok_off,
                                     rows ? rows->T : h->d_line_T, max_T, fin,
                                     dao, L, s, S2, w.ca_q_b)); ++g_launches);
+        if (fused) DSKIP(8, DSTEP(launch_dec_gemm_ln(dao, L, D, w.ca_out_w, w.ca_out_b, dx, w.n2_g, w.n2_b, dx, dxt, s)));
+        else {
         DSKIP(8, DSTEP(gemm_dec(h, dao, L, w.ca_out_w, D, D, S2, parts, s)));
         DSKIP(4, DSTEP(launch_layernorm(parts, w.n2_g, w.n2_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S2, w.ca_out_b, dx, dxt)); ++g_launches);
+        }
         {   // FFN1 keeps its ReLU epilogue (no split): N = 1536 already gives 48 CTAs
             GemmProblem p;
             memset(&p, 0, sizeof p);
@@ -623,12 +633,20 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
             p.ep.bias = w.l1_b; p.ep.relu = 1; p.ep.out_f32 = dh; p.ep.ld_f32 = 4 * D; p.ep.round_tf32 = 1;
             DSKIP(8, DSTEP(launch_gemm_tc(dxt, L, w.l1_w, p, h->num_sms, s)));
         }
+        if (fused) DSKIP(8, DSTEP(launch_dec_gemm_ln(dh, L, 4 * D, w.l2_w, w.l2_b, dx, w.n3_g, w.n3_b, dx, dxt, s)));
+        else {
         DSKIP(8, DSTEP(gemm_dec(h, dh, L, w.l2_w, D, 4 * D, S8, parts, s)));
         DSKIP(4, DSTEP(launch_layernorm(parts, w.n3_g, w.n3_b, nullptr, nullptr, dx, nullptr, nullptr, L, s, S8, w.l2_b, dx, dxt)); ++g_launches);
+        }
     }
-    DSKIP(8, DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s)));
     const int* forced = (h->force_tokens && h->have_forced) ? buf<int>(h, "forced") : nullptr;
     float* trace = (h->trace_logits || rows) ? reinterpret_cast<float*>(h->trace.p) : nullptr;
+    if (fused) {
+        DSKIP(8, DSTEP(launch_dec_out_argmax(dxt, L, h->dec_out_w, h->dec_out_b, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"),
+                                             buf<int>(h, "n_active"), sb, off, forced, trace, h->dec_tok_emb, h->dec_pos, dx, dxt, s)));
+        return 0;
+    }
+    DSKIP(8, DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s)));
     DSKIP(16, DSTEP(launch_dec_argmax(parts, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"), buf<int>(h, "n_active"), sb,
                             off, L, forced, trace, s, S2, h->dec_out_b)); ++g_launches);
 #undef DSTEP
@@ -641,14 +659,14 @@ static const int DEC_GROUP = 8;     // positions per captured graph / per early-
 // `n` consecutive positions followed by the step_base bump, eagerly on stream s.
 int decode_group_eager(kocr_handle* h, int n, int max_T, cudaStream_t s) {
     struct PdlScope { PdlScope(bool on) { pdl_set_active(on); } ~PdlScope() { pdl_set_active(false); } } scope(h->use_pdl != 0);
-    for (int i = 0; i < n; ++i) KOCR_TRY(decode_step(h, i, max_T, s));
+    for (int i = 0; i < n; ++i) KOCR_TRY(decode_step(h, i, max_T, s, nullptr, /*embed_first=*/false));
     KOCR_TRY(launch_dec_bump(buf<int>(h, "step_base"), n, s)); ++g_launches;
     return 0;
 }
 
 // The same 8 positions as one CUDA graph (captured once per (n_lines, max_T bucket, options)).
 int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
-    auto key = std::make_tuple(h->dec_rows, max_T, h->dec_skip * 8 + h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
+    auto key = std::make_tuple(h->dec_rows, max_T, h->dec_skip * 16 + h->dec_fused * 8 + h->trace_logits * 4 + h->use_pdl * 2 + h->dec_wide, (h->force_tokens && h->have_forced) ? 1 : 0);
     auto it = h->dec_graphs.find(key);
     if (it == h->dec_graphs.end()) {
         cudaGraph_t graph = nullptr;
@@ -924,10 +942,15 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         KOCR_CUDA(cudaMemsetAsync(h->trace.p, 0, (size_t)L * DEC_MAX * VOCAB_PAD * 4, s));
     }
     const bool forcing = h->force_tokens && h->have_forced;
+    if (h->dec_fused) {     // position 0 (<sos>); every later position is embedded by the previous position's argmax kernel
+        KOCR_TRY(launch_dec_embed(tokens, buf<int>(h, "step_base"), 0, h->dec_tok_emb, h->dec_pos, buf<float>(h, "dx"), buf<float>(h, "dq"),
+                                  nullptr, nullptr, L, s));
+        ++g_launches;
+    }
     const int max_T = (h->max_T + 127) / 128 * 128;      // bucketed: only sizes the cross-attention scratch
     // Row compaction (see decode_compact_kernel): plain greedy decoding only - the logits trace and forced tokens are
     // indexed by the caller's line numbers
-    const bool may_compact = h->compact_rows && !forcing && !h->trace_logits;
+    const bool may_compact = h->compact_rows && !forcing && !h->trace_logits && !h->dec_fused;   // (the fused path keeps the next position's embedding per row)
     h->dec_rows = L;
     h->row_orig.resize(L);
     for (int i = 0; i < L; ++i) h->row_orig[i] = i;
@@ -1031,6 +1054,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }
     if (strcmp(name, "dec_skip") == 0) { h->dec_skip = value; return 0; }
     if (strcmp(name, "pool2_fused") == 0) { h->pool2_fused = value; return 0; }
+    if (strcmp(name, "dec_fused") == 0) { h->dec_fused = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }
