@@ -4,7 +4,10 @@
 // whole GPU's time (profiles/r02/decode_attribution.md).  Two fusions take the count to 17:
 //
 //   dec_gemm_ln_kernel        out-projection (self-attention / cross-attention) or FFN2  +  bias + residual + LayerNorm
-//                             = post-norm sub-layer tail  x <- LN(x + W a + b)   (replaces: split-K GEMM, LayerNorm kernel)
+//                             = post-norm sub-layer tail  x <- LN(x + W a + b)   (replaces: split-K GEMM, LayerNorm kernel).
+//                             A cluster of 3 CTAs owns a 128-row tile, one 128-column slab of the 384 outputs each (one CTA
+//                             for all 384 columns was tried first: a single SM cannot stream the weights fast enough);
+//                             the row statistics are combined through distributed shared memory.
 //   dec_out_argmax_kernel     output projection (384 -> 124)  +  argmax  +  greedy bookkeeping (stop BEFORE <eos>)
 //                             +  token + positional embedding of the NEXT position
 //                             (replaces: split-K GEMM, dec_argmax_kernel, dec_embed_kernel)
@@ -14,6 +17,8 @@
 // LayerNorm / argmax wants: no cross-thread reduction at all.
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace kocr {
 
@@ -41,7 +46,7 @@ struct DfCommon {          // producer / MMA halves shared by the two kernels
 // row m0; returns in the epilogue warps with the accumulator complete (tmem_full waited).  N is a multiple of 128: the B
 // tile is loaded and multiplied as N / 128 slabs of 128 weight rows (TMA boxes hold at most 256 rows).
 template <int N>
-__device__ __forceinline__ bool df_mainloop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int m0, int num_kb,
+__device__ __forceinline__ bool df_mainloop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int m0, int b_row0, int num_kb,
                                             uint8_t* smem_raw, DfCommon& c) {
     using Cfg = DfCfg<N>;
     c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,7 +78,7 @@ __device__ __forceinline__ bool df_mainloop(const CUtensorMap& tmap_a, const CUt
                 tma_load_2d(&tmap_a, &c.full_bar[stage], sa, kb * DF_KE, m0);
 #pragma unroll
                 for (int j = 0; j < N / 128; ++j)
-                    tma_load_2d(&tmap_b, &c.full_bar[stage], sa + Cfg::A_BYTES + j * (128 * 128), kb * DF_KE, j * 128);
+                    tma_load_2d(&tmap_b, &c.full_bar[stage], sa + Cfg::A_BYTES + j * (128 * 128), kb * DF_KE, b_row0 + j * 128);
                 if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -119,62 +124,82 @@ __device__ __forceinline__ void df_finish(const DfCommon& c) {
 // x <- LayerNorm(resid + A W^T + bias) * gamma + beta over rows of 384 (eps 1e-5, two-pass variance like nn.LayerNorm);
 // writes the exact fp32 row (residual stream) and its TF32-rounded copy (A operand of the next GEMM).
 // A = [L][K] fp32 (already TF32-rounded by its producer), W = [384][K] fp32 (TF32-rounded on the host).
+// grid = (3, m tiles), cluster (3,1,1): CTA `slab` computes output columns [slab*128, +128) of a 128-row tile.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DF_THREADS, 1)
+static constexpr int LN_SLABS = D_MODEL / 128;     // 3
+
+__global__ void __cluster_dims__(LN_SLABS, 1, 1) __launch_bounds__(DF_THREADS, 2)
 dec_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int L, int num_kb,
                    const float* __restrict__ bias, const float* resid, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* out_x, float* out_xt) {
     extern __shared__ uint8_t df_smem[];
+    __shared__ float s_stat[2][DF_BM];             // per row of the tile: partial sum / partial sum of squared deviations of this slab
+    cg::cluster_group cluster = cg::this_cluster();
     DfCommon c;
-    const int m0 = blockIdx.x * DF_BM;
-    if (df_mainloop<D_MODEL>(tmap_a, tmap_b, m0, num_kb, df_smem, c)) {
-        const int quad = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
-        const long row = (long)m0 + quad * 32 + lane;
-        const bool valid = row < L;
-        const uint32_t t_row = c.tmem_base + (uint32_t(quad * 32) << 16);
-        const float* rrow = resid + (valid ? row : 0) * D_MODEL;
-        uint32_t v[32];
-        // pass 1: v = acc + bias + residual, written back to TMEM; row sum
+    const int slab = (int)cluster.block_rank();
+    const int m0 = blockIdx.y * DF_BM;
+    const int col0 = slab * 128;
+    const bool epi = df_mainloop<128>(tmap_a, tmap_b, m0, col0, num_kb, df_smem, c);
+    const int quad = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;                // row inside the tile (epilogue threads)
+    const long row = (long)m0 + r;
+    const bool valid = row < L;
+    const uint32_t t_row = c.tmem_base + (uint32_t(quad * 32) << 16);
+    uint32_t v[32];
+    if (epi) {      // pass 1: v = acc + bias + residual, written back to TMEM; partial row sum of this slab
+        const float* rrow = resid + (valid ? row : 0) * D_MODEL + col0;
         float sum = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < D_MODEL / 32; ++ch) {
+        for (int ch = 0; ch < 4; ++ch) {
             tmem_ld32(t_row + ch * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + ch * 32 + j));
-                const float4 r = __ldcg(reinterpret_cast<const float4*>(rrow + ch * 32 + j));     // written by a predecessor under PDL
-                const float f0 = __uint_as_float(v[j]) + b.x + r.x, f1 = __uint_as_float(v[j + 1]) + b.y + r.y;
-                const float f2 = __uint_as_float(v[j + 2]) + b.z + r.z, f3 = __uint_as_float(v[j + 3]) + b.w + r.w;
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + ch * 32 + j));
+                const float4 rr = __ldcg(reinterpret_cast<const float4*>(rrow + ch * 32 + j));    // written by a predecessor under PDL
+                const float f0 = __uint_as_float(v[j]) + b.x + rr.x, f1 = __uint_as_float(v[j + 1]) + b.y + rr.y;
+                const float f2 = __uint_as_float(v[j + 2]) + b.z + rr.z, f3 = __uint_as_float(v[j + 3]) + b.w + rr.w;
                 sum += (f0 + f1) + (f2 + f3);
                 v[j] = __float_as_uint(f0); v[j + 1] = __float_as_uint(f1); v[j + 2] = __float_as_uint(f2); v[j + 3] = __float_as_uint(f3);
             }
             tmem_st32(t_row + ch * 32, v);
         }
         tmem_st_wait();
-        const float mean = sum * (1.f / D_MODEL);
-        // pass 2: variance around the mean
-        float q = 0.f;
+        s_stat[0][r] = sum;
+    }
+    cluster.sync();                                 // every slab's partial sums are visible
+    float mean = 0.f;
+    if (epi) {
+#pragma unroll
+        for (int k = 0; k < LN_SLABS; ++k) mean += cluster.map_shared_rank(&s_stat[0][0], k)[r];
+        mean *= (1.f / D_MODEL);
+        float q = 0.f;                              // pass 2: squared deviations of this slab around the row mean
 #pragma unroll 1
-        for (int ch = 0; ch < D_MODEL / 32; ++ch) {
+        for (int ch = 0; ch < 4; ++ch) {
             tmem_ld32(t_row + ch * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(v[j]) - mean; q = fmaf(d, d, q); }
         }
+        s_stat[1][r] = q;
+    }
+    cluster.sync();
+    if (epi) {      // pass 3: normalise, scale, shift; exact row + TF32-rounded copy
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_SLABS; ++k) q += cluster.map_shared_rank(&s_stat[1][0], k)[r];
         const float rstd = rsqrtf(q * (1.f / D_MODEL) + 1e-5f);
-        // pass 3: normalise, scale, shift; exact row + TF32-rounded copy
 #pragma unroll 1
-        for (int ch = 0; ch < D_MODEL / 32; ++ch) {
+        for (int ch = 0; ch < 4; ++ch) {
             tmem_ld32(t_row + ch * 32, v);
             tmem_ld_wait();
             if (valid) {
-                float4* ox = reinterpret_cast<float4*>(out_x + row * D_MODEL + ch * 32);
-                float4* ot = reinterpret_cast<float4*>(out_xt + row * D_MODEL + ch * 32);
+                float4* ox = reinterpret_cast<float4*>(out_x + row * D_MODEL + col0 + ch * 32);
+                float4* ot = reinterpret_cast<float4*>(out_xt + row * D_MODEL + col0 + ch * 32);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + ch * 32 + j));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + ch * 32 + j));
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0 + ch * 32 + j));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col0 + ch * 32 + j));
                     float4 y;
                     y.x = (__uint_as_float(v[j]) - mean) * rstd * g.x + b.x;
                     y.y = (__uint_as_float(v[j + 1]) - mean) * rstd * g.y + b.y;
@@ -186,7 +211,8 @@ dec_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     }
-    df_finish<D_MODEL>(c);
+    cluster.sync();                                 // nobody exits while a peer may still read its s_stat
+    df_finish<128>(c);
 }
 
 int launch_dec_gemm_ln(const float* a, int L, int K, const float* w, const float* bias, const float* resid,
@@ -196,8 +222,8 @@ int launch_dec_gemm_ln(const float* a, int L, int K, const float* w, const float
     KOCR_TRY(make_tmap_2d(&ta, a, (uint64_t)L, (uint64_t)K, DF_BM, 4));
     KOCR_TRY(make_tmap_2d(&tb, w, (uint64_t)D_MODEL, (uint64_t)K, 128, 4));
     static PerDeviceOnce attr_once;
-    KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_gemm_ln_kernel, DfCfg<D_MODEL>::SMEM_BYTES));
-    KOCR_CUDA(launch_kernel(dec_gemm_ln_kernel, dim3((L + DF_BM - 1) / DF_BM), dim3(DF_THREADS), DfCfg<D_MODEL>::SMEM_BYTES,
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_gemm_ln_kernel, DfCfg<128>::SMEM_BYTES));
+    KOCR_CUDA(launch_kernel(dec_gemm_ln_kernel, dim3(LN_SLABS, (L + DF_BM - 1) / DF_BM), dim3(DF_THREADS), DfCfg<128>::SMEM_BYTES,
                             stream, ta, tb, L, K / DF_KE, bias, resid, gamma, beta, out_x, out_xt));
     gemm_tc_count_launch();
     return 0;
@@ -216,7 +242,7 @@ dec_out_argmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     extern __shared__ uint8_t df_smem[];
     DfCommon c;
     const int m0 = blockIdx.x * DF_BM;
-    if (df_mainloop<VOCAB_PAD>(tmap_a, tmap_b, m0, num_kb, df_smem, c)) {
+    if (df_mainloop<VOCAB_PAD>(tmap_a, tmap_b, m0, 0, num_kb, df_smem, c)) {
         const int quad = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
         const int l = m0 + quad * 32 + lane;
         const int t = __ldcg(step_base) + step_off;
