@@ -93,6 +93,7 @@ struct kocr_handle {
     size_t staging_bytes = 0;
     cudaEvent_t staging_done = nullptr;
     cudaEvent_t sync_event = nullptr;     // cudaEventBlockingSync: host waits sleep instead of spinning
+    cudaEvent_t flag_event[2] = {nullptr, nullptr};   // decode loop: "the n_active copy of group g has landed" (look-ahead ring)
     int32_t* pinned_flag = nullptr;    // pinned int for early-exit polling
     int32_t* fin_host = nullptr;       // pinned copy of the per-line finished flags of the last decode
     // batch state
@@ -127,7 +128,8 @@ struct kocr_handle {
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
-    int dec_fused = 1;           // 1: GEMM+LayerNorm and out_proj+argmax+embed kernels of dec_fused.cu (17 launches per position); 0: 25 launches
+    int dec_fused = 0;           // 1: GEMM+LayerNorm and out_proj+argmax+embed kernels of dec_fused.cu (17 launches per position); 0: 25 launches
+                                 // (measured, 12 passes in flight: the fused kernels' thread-per-row epilogues are latency-bound - decode 5.8 vs 4.3 ms)
     int pool2_fused = 0;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue (4 whole columns = 96 of 128 MMA rows per tile:
                                  // measured 5 % SLOWER than conv2 + pool2x2_kernel, profiles/r02); 0 (default): separate kernel
     int dec_skip = 0;            // diagnosis (tools/inflight_probe.py): bit mask of kernel classes a decode step does NOT launch
@@ -322,6 +324,7 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaMallocHost(&h->out_stage, (size_t)h->max_lines * (KOCR_TOKENS_LD + 2) * 4));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming | cudaEventBlockingSync));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
+    for (int i = 0; i < 2; ++i) KOCR_CUDA(cudaEventCreateWithFlags(&h->flag_event[i], cudaEventDisableTiming | cudaEventBlockingSync));
     KOCR_CUDA(cudaStreamCreate(&h->own_stream));
     // input staging sized for the handle's capacity up front (4x the bytes of the height-48 chunks: source lines are
     // rarely more than 2x oversampled): a cudaMalloc in the middle of a run would synchronise every in-flight batch
@@ -788,6 +791,7 @@ int kocr_destroy(kocr_handle* h) {
     if (h->compact_tab.p) cudaFree(h->compact_tab.p);
     if (h->staging_done) cudaEventDestroy(h->staging_done);
     if (h->sync_event) cudaEventDestroy(h->sync_event);
+    for (int i = 0; i < 2; ++i) if (h->flag_event[i]) cudaEventDestroy(h->flag_event[i]);
     for (auto& g : h->dec_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -956,24 +960,54 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
     for (int i = 0; i < L; ++i) h->row_orig[i] = i;
     bool compacted = false;
     int done = 0;
-    while (done < max_steps) {
+    // One group = DEC_GROUP positions (a CUDA-graph replay) followed by a 4-byte copy of "lines still active" to the host.
+    auto enqueue_group = [&](int slot) -> int {
         const int n = std::min(DEC_GROUP, max_steps - done);
-        // the first group of a process runs eagerly (it sets the kernels' function attributes)
+        // the first group of a handle runs eagerly (it sets the kernels' function attributes)
         const auto t0 = std::chrono::steady_clock::now();
         if (n == DEC_GROUP && h->use_graphs && h->decode_warmed) KOCR_TRY(decode_group_graph(h, max_T, s));
         else KOCR_TRY(decode_group_eager(h, n, max_T, s));
-        const auto t1 = std::chrono::steady_clock::now();
-        h->host_launch_us += std::chrono::duration<double, std::micro>(t1 - t0).count();
+        h->host_launch_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         h->decode_warmed = true;
         done += n;
         if (!forcing && done < max_steps) {
-            KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
-            KOCR_CUDA(wait_stream(h, s));
-            h->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
-            const int n_active = *h->pinned_flag;
+            KOCR_CUDA(cudaMemcpyAsync(h->pinned_flag + slot, buf<int>(h, "n_active") + (done - 1), 4, cudaMemcpyDeviceToHost, s));
+            KOCR_CUDA(cudaEventRecord(h->flag_event[slot], s));
+        }
+        return 0;
+    };
+    auto wait_flag = [&](int slot) -> cudaError_t {
+        const auto t1 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaSuccess;
+        if (h->blocking_wait) e = cudaEventSynchronize(h->flag_event[slot]);
+        else while ((e = cudaEventQuery(h->flag_event[slot])) == cudaErrorNotReady) {}
+        h->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
+        return e;
+    };
+    if (!may_compact) {
+        // Look-ahead: group g + 1 is enqueued BEFORE the host learns how group g ended, so the stream never idles on the
+        // host round trip (a blocking-sync wake-up is 0.1-0.4 ms, x 13 groups per batch).  A group that starts after every
+        // line has finished costs little: all per-line kernels exit at once.  Tokens are unaffected (a finished line
+        // stays finished; stragglers are re-decoded from scratch by the caller).
+        int slot = 0;
+        KOCR_TRY(enqueue_group(slot));
+        while (!forcing && done < max_steps) {
+            const int polled_slot = slot;               // the group whose outcome we are about to read
+            slot ^= 1;
+            KOCR_TRY(enqueue_group(slot));              // ... after the next one is already in the stream
+            KOCR_CUDA(wait_flag(polled_slot));
+            if (h->pinned_flag[polled_slot] <= h->straggler_threshold) break;   // every line (or all but a few stragglers) has emitted <eos>
+        }
+        while (forcing && done < max_steps) KOCR_TRY(enqueue_group(0));
+    } else
+    while (done < max_steps) {
+        KOCR_TRY(enqueue_group(0));
+        if (!forcing && done < max_steps) {
+            KOCR_CUDA(wait_flag(0));
+            const int n_active = h->pinned_flag[0];
             if (n_active <= h->straggler_threshold) break;     // every line (or all but a few stragglers) has emitted <eos>
             const int target = (n_active + 127) / 128 * 128;
-            if (may_compact && target < h->dec_rows) {
+            if (target < h->dec_rows) {
                 const int R = h->dec_rows;
                 int32_t* fin = h->out_stage;                    // pinned scratch
                 KOCR_CUDA(cudaMemcpyAsync(fin, buf<int>(h, "finished"), (size_t)R * 4, cudaMemcpyDeviceToHost, s));
