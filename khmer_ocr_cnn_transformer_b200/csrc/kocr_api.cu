@@ -128,6 +128,7 @@ struct kocr_handle {
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
+    int dec_lookahead = 0;       // 1: enqueue decode group g+1 before polling the outcome of group g
     int dec_fused = 0;           // 1: GEMM+LayerNorm and out_proj+argmax+embed kernels of dec_fused.cu (17 launches per position); 0: 25 launches
                                  // (measured, 12 passes in flight: the fused kernels' thread-per-row epilogues are latency-bound - decode 5.8 vs 4.3 ms)
     int pool2_fused = 0;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue (4 whole columns = 96 of 128 MMA rows per tile:
@@ -984,8 +985,9 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         h->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
         return e;
     };
-    if (!may_compact) {
-        // Look-ahead: group g + 1 is enqueued BEFORE the host learns how group g ended, so the stream never idles on the
+    if (!may_compact && h->dec_lookahead) {
+        // Look-ahead (option, off by default - measured slightly slower with 12-18 passes in flight: the speculative group's GEMMs
+        // still run on every row, and the decode phase is bound by total work, not by the host round trip): group g + 1 is enqueued BEFORE the host learns how group g ended, so the stream never idles on the
         // host round trip (a blocking-sync wake-up is 0.1-0.4 ms, x 13 groups per batch).  A group that starts after every
         // line has finished costs little: all per-line kernels exit at once.  Tokens are unaffected (a finished line
         // stays finished; stragglers are re-decoded from scratch by the caller).
@@ -1007,7 +1009,7 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
             const int n_active = h->pinned_flag[0];
             if (n_active <= h->straggler_threshold) break;     // every line (or all but a few stragglers) has emitted <eos>
             const int target = (n_active + 127) / 128 * 128;
-            if (target < h->dec_rows) {
+            if (may_compact && target < h->dec_rows) {
                 const int R = h->dec_rows;
                 int32_t* fin = h->out_stage;                    // pinned scratch
                 KOCR_CUDA(cudaMemcpyAsync(fin, buf<int>(h, "finished"), (size_t)R * 4, cudaMemcpyDeviceToHost, s));
@@ -1089,6 +1091,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "dec_skip") == 0) { h->dec_skip = value; return 0; }
     if (strcmp(name, "pool2_fused") == 0) { h->pool2_fused = value; return 0; }
     if (strcmp(name, "dec_fused") == 0) { h->dec_fused = value; return 0; }
+    if (strcmp(name, "dec_lookahead") == 0) { h->dec_lookahead = value; return 0; }
     if (strcmp(name, "dec_wide") == 0) { h->dec_wide = value; return 0; }
     if (strcmp(name, "lstm_impl") == 0) { h->lstm_impl = value; return 0; }
     if (strcmp(name, "big_gemm_sms") == 0) { h->big_gemm_sms = value; return 0; }

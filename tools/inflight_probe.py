@@ -37,7 +37,7 @@ class W:
         self.rec.set_option("big_gemm_sms", int(OPTS.get("big_gemm_sms", 0)))
         self.rec.set_option("straggler_threshold", int(OPTS.get("straggler_threshold", 8)))
         self.rec.set_option("blocking_wait", 1 if S > 1 else 0)
-        for k in ("use_graphs", "use_pdl", "dec_cross_impl", "compact_rows", "kv_split", "dec_skip", "dec_fused"):
+        for k in ("use_graphs", "use_pdl", "dec_cross_impl", "compact_rows", "kv_split", "dec_skip", "dec_fused", "dec_lookahead"):
             if k in OPTS:
                 self.rec.set_option(k, int(OPTS[k]))
         self.stream = torch.cuda.Stream()
