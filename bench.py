@@ -85,6 +85,23 @@ def make_lines(cfg, seed_offset=0):
     return synth.make_lines(cfg["lines"], cfg["lo"], cfg["hi"], seed=cfg["seed"] + seed_offset)[0]
 
 
+class stdout_to_stderr:
+    """fd-level redirect: whatever C libraries print to stdout inside the block (NCCL's "NCCL version ..." banner at
+    communicator creation) goes to stderr, so that stdout carries exactly ONE line, the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -263,6 +280,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-side-c2", action="store_true", help="skip the c2 side measurement of the default c3 run")
+    ap.add_argument("--no-api", action="store_true", help="skip the OCRPredictor.predict_batch measurement (N = 1 only)")
     ap.add_argument("--no-incumbent", action="store_true", help="reference arm: skip the device='cuda' run of the reference")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the bounded cpu_baseline sample")
     ap.add_argument("--straggler-threshold", type=int, default=8,
@@ -292,9 +310,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps "NCCL version ..." out of stdout (one JSON line)
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()          # NCCL creates its communicator (and prints its banner) on the first collective
 
     cfg = WORKLOADS[args.config]
     sd, wname = load_state_dict(cfg["variant"])
@@ -490,6 +508,30 @@ def main():
         cpu = {"value": done_lines / t_used, "unit": "lines/s", "cores": os.cpu_count(), "kind": kind,
                "sample": f"{done_lines} lines of this rank's {args.config} set in {t_used:.1f} s; {note}"}
 
+    # ---- the drop-in API itself: OCRPredictor.predict_batch on a list of grey images (host packing, H2D, recognition, D2H
+    #      and Tokenizer.decode to str inside), same engine, own handles (the bench's are released first)
+    api = None
+    if rank == 0 and world == 1 and not args.no_api and cfg["variant"] == "se":
+        pipe.close()
+        from khmer_ocr_cnn_transformer_b200.recognition.predictor import OCRPredictor
+        from khmer_ocr_cnn_transformer_b200.recognition.tokenizer import Tokenizer
+        from khmer_ocr_cnn_transformer_b200.recognition.config import OCRConfig
+        from khmer_ocr_cnn_transformer_b200.recognition.utils import autodetect_config
+        from khmer_ocr_cnn_transformer_b200.recognition.model.se_model import KhmerOCR
+        ck = REPO / "tests" / "golden" / "fixture_se_ckpt.npz"
+        pkg = REPO / "khmer_ocr_cnn_transformer_b200" / "recognition"
+        pred = OCRPredictor(ck, Tokenizer(pkg / "char2idx.json"), OCRConfig(**autodetect_config(ck)), KhmerOCR,
+                            max_lines=max_lines, max_chunks=max_chunks, in_flight=S)
+        imgs = wl.images if wl.scaling == "strong" else [im for k in range(16) for im in make_lines(cfg, seed_offset=100 + k)]
+        pred.predict_batch(imgs[:min(len(imgs), 12 * max_lines)])           # creates the handles, captures the decode graphs
+        t0 = time.perf_counter()
+        texts = pred.predict_batch(imgs, beam_width=1, batch_size=8)
+        dt = time.perf_counter() - t0
+        api = {"value": len(imgs) / dt, "unit": "lines/s", "lines": len(imgs), "seconds": dt,
+               "call": "OCRPredictor.predict_batch(list of grey uint8 arrays, beam_width=1, batch_size=8) -> list[str]",
+               "frac_of_e2e": (len(imgs) / dt) / e2e, "non_empty": int(sum(1 for t in texts if t))}
+        pred.close()
+
     if rank == 0:
         line = {
             "metric": "text_lines_per_s", "value": value, "unit": "lines/s", "n_gpus": world, "steps": args.steps,
@@ -534,6 +576,8 @@ def main():
             line["c2"] = side_c2
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if api is not None:
+            line["api"] = api
         print(json.dumps(line), flush=True)
     pipe.close()
     if world > 1:

@@ -64,7 +64,23 @@ class OCRPredictor:
 
     # ------------------------------------------------------------------------------------
     def _decode_ids(self, tokens, lengths):
-        return [self.tokenizer.decode([int(t) for t in tokens[i, :lengths[i]]]) for i in range(tokens.shape[0])]
+        """`Tokenizer.decode` (tokenizer.py:26-35: skip <sos> / <pad>, stop at <eos>, unknown ids -> "") for every row,
+        through a lookup table instead of a Python loop per token (the loop was 30 % of `predict_batch` on 8192 lines)."""
+        tk = self.tokenizer
+        lut = getattr(self, "_id2char_lut", None)
+        if lut is None:
+            lut = np.array([tk.idx2char.get(i, "") for i in range(max(len(tk), 128))], dtype=object)
+            lut[tk.sos_idx] = ""
+            lut[tk.pad_idx] = ""
+            self._id2char_lut = lut
+        out = []
+        for i in range(tokens.shape[0]):
+            row = tokens[i, :lengths[i]]
+            stop = np.nonzero(row == tk.eos_idx)[0]
+            if stop.size:
+                row = row[:stop[0]]
+            out.append("".join(lut[np.clip(row, 0, lut.shape[0] - 1)].tolist()))
+        return out
 
     def _recognize_gray(self, grays):
         """Greedy recognition of grey uint8 lines through the pipeline: batches within the handles' capacity (sorted by
