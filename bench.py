@@ -530,6 +530,12 @@ def main():
         api = {"value": len(imgs) / dt, "unit": "lines/s", "lines": len(imgs), "seconds": dt,
                "call": "OCRPredictor.predict_batch(list of grey uint8 arrays, beam_width=1, batch_size=8) -> list[str]",
                "frac_of_e2e": (len(imgs) / dt) / e2e, "non_empty": int(sum(1 for t in texts if t))}
+        nb = min(len(imgs), 1024)
+        pred.predict_batch(imgs[:nb], beam_width=3)                          # (allocates the beam caches)
+        t0 = time.perf_counter()
+        pred.predict_batch(imgs[:nb], beam_width=3)
+        api["beam3"] = {"value": nb / (time.perf_counter() - t0), "unit": "lines/s", "lines": nb,
+                        "call": "OCRPredictor.predict_batch(..., beam_width=3): kocr_beam_search per batch of max_lines // 3 lines"}
         pred.close()
 
     if rank == 0:

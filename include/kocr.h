@@ -108,6 +108,14 @@ int kocr_beam_step(kocr_handle* h, int line, int n_rows, const int32_t* parents,
 int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, const int32_t* parents,
                          const int32_t* prefixes, int t, float* logits_out, void* stream);
 
+/* The whole of OCRPredictor._beam_search (predictor.py:101-136) for every line of the current batch (after kocr_gather_chunks /
+ * kocr_sevgg_encoder_forward / kocr_merge_bilstm_forward), in one call: KV-cached decoder positions for n_lines * beam_width
+ * hypothesis rows (<= max_lines), log-softmax + top-k on the device, the reference's bookkeeping (float64 score sums, stable
+ * sort, every <eos> candidate completed with score / len, first beam_width others survive) in the library.
+ * tokens_out: host int32 [n_lines, KOCR_TOKENS_LD] = the winning sequence as the reference hands it to Tokenizer.decode
+ * (<sos> ... and <eos> when a hypothesis completed); lengths_out: its length.  max_len <= decode_max_len (0 = decode_max_len). */
+int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* tokens_out, int32_t* lengths_out, void* stream);
+
 /* Teacher-forced batched forward - KhmerOCR.forward (recognition/model/se_model.py:240-289; vgg_model.py:214-246), the
  * training-time / evaluation-loop semantics: after kocr_gather_chunks + kocr_sevgg_encoder_forward on a batch of B
  * lines, every merged sequence is padded to Tmax = max T_i, global_pos is added to the pad rows too, the BiLSTM runs

@@ -15,7 +15,7 @@ EXPORTS = [
     "kocr_abi_version", "kocr_last_error", "kocr_create", "kocr_destroy", "kocr_workspace_bytes",
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
-    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines", "kocr_forward_teacher_forced",
+    "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines", "kocr_forward_teacher_forced", "kocr_beam_search",
 ]
 
 _lib = None
@@ -58,6 +58,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_beam_step.restype = i32
     lib.kocr_beam_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
     lib.kocr_beam_step_batch.restype = i32
+    lib.kocr_beam_search.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.kocr_beam_search.restype = i32
     lib.kocr_crop_lines.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.kocr_crop_lines.restype = i32
     lib.kocr_forward_teacher_forced.argtypes = [vp, vp, i32, vp, vp]
@@ -236,6 +238,13 @@ class Recognizer:
         logits = np.zeros((n_rows, 128), np.float32)
         check(self.lib.kocr_beam_step_batch(self._h, n_rows, _ptr(rl), _ptr(par), _ptr(prefixes), t, _ptr(logits), None))
         return logits[:, :124]
+
+    def beam_search(self, n_lines: int, beam_width: int, max_len: int = 0):
+        """`OCRPredictor._beam_search` for every line of the batch whose stages 1-5a have just run: (tokens [n, 257], lengths)."""
+        tokens = np.zeros((max(n_lines, 1), TOKENS_LD), np.int32)
+        lengths = np.zeros(max(n_lines, 1), np.int32)
+        check(self.lib.kocr_beam_search(self._h, int(beam_width), int(max_len), _ptr(tokens), _ptr(lengths), None))
+        return tokens[:n_lines], lengths[:n_lines]
 
     def crop_lines(self, page, boxes, pad_px: int, out_dev_ptr: int, out_offsets, page_dev_ptr=None, stream=None):
         """Cut `boxes` (int32 [n, 4] = x0, y0, x1, y1, clipped) out of `page` (uint8 (H, W) or (H, W, 3); pass

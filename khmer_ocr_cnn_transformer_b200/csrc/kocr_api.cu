@@ -123,6 +123,7 @@ struct kocr_handle {
     static const int BEAM_MAX = 8;
     Buf tf_x, tf_tab;             // kocr_forward_teacher_forced: padded memory operand, per-line tables
     Buf crop_page, crop_tab;      // kocr_crop_lines: device copy of a host page, boxes + offsets
+    Buf beam_scratch;            // kocr_beam_search: parents / tokens / top-k tables
     Buf beam_cache;              // [2 ping-pong][K,V][2 layers][max_lines][DEC_MAX][384] fp32, allocated on first use
     int beam_cur = 0;
     int dec_wide = 1;            // 1: decode GEMMs as 128x64 tiles + split-K over ~50-100 CTAs (lowest latency);
@@ -780,6 +781,7 @@ int kocr_destroy(kocr_handle* h) {
     if (h->mid_dev.p) cudaFree(h->mid_dev.p);
     if (h->trace.p) cudaFree(h->trace.p);
     if (h->beam_cache.p) cudaFree(h->beam_cache.p);
+    if (h->beam_scratch.p) cudaFree(h->beam_scratch.p);
     if (h->crop_page.p) cudaFree(h->crop_page.p);
     if (h->tf_x.p) cudaFree(h->tf_x.p);
     if (h->tf_tab.p) cudaFree(h->tf_tab.p);
@@ -1122,6 +1124,7 @@ __global__ void beam_reorder_kernel(const float* __restrict__ src, float* __rest
                                     int n_rows, int t, size_t layer_stride, size_t kv_stride) {
     // grid = (n_rows, 2 layers, 2 {K,V}); copies positions [0, t) of the parent's cache row
     const int r = blockIdx.x, layer = blockIdx.y, kv = blockIdx.z;
+    if (parents[r] < 0) return;                      // dead row (kocr_beam_search)
     const float4* s4 = reinterpret_cast<const float4*>(src + kv * kv_stride + layer * layer_stride + (size_t)parents[r] * DEC_MAX * D_MODEL);
     float4* d4 = reinterpret_cast<float4*>(dst + kv * kv_stride + layer * layer_stride + (size_t)r * DEC_MAX * D_MODEL);
     for (int i = threadIdx.x; i < t * (D_MODEL / 4); i += blockDim.x) d4[i] = s4[i];
@@ -1188,6 +1191,193 @@ int kocr_beam_step_batch(kocr_handle* h, int n_rows, const int32_t* row_line, co
     KOCR_CUDA(cudaMemcpy2DAsync(logits_out, VOCAB_PAD * 4, reinterpret_cast<float*>(h->trace.p) + (size_t)t * VOCAB_PAD,
                                 (size_t)DEC_MAX * VOCAB_PAD * 4, VOCAB_PAD * 4, n_rows, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(wait_stream(h, s));     // tab / prefixes are host memory of this call
+    return 0;
+}
+
+// ---- whole beam search in one call (OCRPredictor._beam_search, predictor.py:101-136, for every line of the batch) -------
+// The per-position host round trip of kocr_beam_step_batch (Python bookkeeping + torch log-softmax / top-k on the logits)
+// bounded beam search at ~0.6 k lines/s.  Here the loop lives in the library: hypotheses sit in fixed row slots (line l owns
+// rows [l * bw, (l + 1) * bw)), a device kernel turns the logits into log-softmax top-`bw` (value, index) pairs per row, the
+// host keeps the reference's bookkeeping in C++ (float64 score sums of the fp32 log-probabilities, hypothesis-major /
+// top-k-minor candidate order, STABLE descending sort, every <eos> candidate completed with score / len(seq), the first `bw`
+// others survive, best = first-appended among equal completed scores, else the first live hypothesis), and the next
+// position's prefixes / self-attention caches are re-ordered on the device from the parent indices.
+namespace {
+__global__ void __launch_bounds__(128) beam_topk_kernel(const float* __restrict__ trace, int t, int bw, int n_rows,
+                                                        float* __restrict__ vals, int* __restrict__ idxs) {
+    // warp per row: log_softmax over the 124 logits of position t (fp32, max-subtracted like torch), then `bw` rounds of
+    // warp arg-max (ties -> lowest index)
+    const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const float4 v4 = reinterpret_cast<const float4*>(trace + ((long)r * DEC_MAX + t) * VOCAB_PAD)[lane];
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (lane * 4 + j < VOCAB) mx = fmaxf(mx, v[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (lane * 4 + j < VOCAB) sum += expf(v[j] - mx);
+    sum = warp_sum(sum);
+    const float lse = logf(sum);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (lane * 4 + j < VOCAB) ? (v[j] - mx) - lse : -INFINITY;
+    for (int k = 0; k < bw; ++k) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (v[j] > best) { best = v[j]; bi = lane * 4 + j; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { vals[r * 8 + k] = best; idxs[r * 8 + k] = bi; }
+        if ((bi >> 2) == lane) v[bi & 3] = -INFINITY;           // remove the winner
+    }
+}
+
+// next position's row state from the parent indices: prefix tokens [0, t] of the parent + the chosen token at t + 1, and the
+// "dead row" flag the per-line kernels skip on.  grid = n_rows.
+__global__ void __launch_bounds__(64) beam_rows_kernel(const int* __restrict__ tok_old, int* __restrict__ tok_new,
+                                                       const int* __restrict__ parents, const int* __restrict__ new_tok,
+                                                       int* __restrict__ finished, int t) {
+    const int r = blockIdx.x, p = parents[r];
+    if (threadIdx.x == 0) finished[r] = p < 0 ? 1 : 0;
+    if (p < 0) return;
+    for (int i = threadIdx.x; i <= t; i += blockDim.x) tok_new[r * KOCR_TOKENS_LD + i] = tok_old[p * KOCR_TOKENS_LD + i];
+    if (threadIdx.x == 0) tok_new[r * KOCR_TOKENS_LD + t + 1] = new_tok[r];
+}
+}  // namespace
+
+int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* tokens_out, int32_t* lengths_out, void* stream) {
+    KOCR_CHECK(h != nullptr && tokens_out != nullptr && lengths_out != nullptr, "kocr_beam_search: null argument");
+    const int bw = beam_width, n_lines = h->n_lines, R = n_lines * bw;
+    KOCR_CHECK(bw >= 1 && bw <= kocr_handle::BEAM_MAX, "kocr_beam_search: beam width %d outside [1, %d]", bw, kocr_handle::BEAM_MAX);
+    KOCR_CHECK(n_lines > 0 && h->n_tok > 0, "kocr_beam_search: run kocr_gather_chunks + kocr_sevgg_encoder_forward + kocr_merge_bilstm_forward on a batch first");
+    KOCR_CHECK(R <= h->max_lines, "kocr_beam_search: %d lines x beam %d exceed the handle's %d decode rows", n_lines, bw, h->max_lines);
+    if (max_len <= 0 || max_len > h->dec_max_len) max_len = h->dec_max_len;
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    const int ML = h->max_lines;
+    const size_t row = (size_t)DEC_MAX * D_MODEL, layer_stride = (size_t)ML * row, kv_stride = 2 * layer_stride, buf_stride = 2 * kv_stride;
+    KOCR_TRY(ensure(h->beam_cache, 2 * buf_stride * sizeof(float)));
+    KOCR_TRY(ensure(h->trace, (size_t)ML * DEC_MAX * VOCAB_PAD * 4));
+    // device scratch: [0,R) parents | [R,2R) new tokens | [2R,3R) tok_off | [3R,4R) T | top-k vals [R*8] | top-k idx [R*8] | token table B
+    KOCR_TRY(ensure(h->beam_scratch, (size_t)(4 * ML + 16 * ML) * 4 + (size_t)ML * KOCR_TOKENS_LD * 4));
+    int* d_par = reinterpret_cast<int*>(h->beam_scratch.p);
+    int* d_newtok = d_par + ML;
+    int* d_tokoff = d_par + 2 * ML;
+    int* d_T = d_par + 3 * ML;
+    float* d_vals = reinterpret_cast<float*>(d_par + 4 * ML);
+    int* d_idx = d_par + 12 * ML;
+    int* d_tokB = d_par + 20 * ML;
+    int* tokens = buf<int>(h, "tokens");
+    float* base = reinterpret_cast<float*>(h->beam_cache.p);
+    h->have_forced = false;
+    const int sv_force = h->force_tokens, sv_fused = h->dec_fused;
+    h->force_tokens = 0; h->dec_fused = 0;        // the beam step wants the plain logits of every live row (trace), no greedy bookkeeping
+    struct Restore { kocr_handle* h; int f, d; ~Restore() { h->force_tokens = f; h->dec_fused = d; } } restore{h, sv_force, sv_fused};
+
+    std::vector<int32_t> tab((size_t)4 * ML, 0);
+    int max_T = 0;
+    for (int l = 0; l < n_lines; ++l)
+        for (int i = 0; i < bw; ++i) {
+            const int r = l * bw + i;
+            tab[r] = i == 0 ? 0 : -1;                      // position 0: one live hypothesis per line (<sos>)
+            tab[(size_t)2 * ML + r] = h->line_first_chunk[l] * TOK_PER_CHUNK;
+            tab[(size_t)3 * ML + r] = h->line_T[l];
+            max_T = std::max(max_T, h->line_T[l]);
+        }
+    max_T = (max_T + 127) / 128 * 128;
+    KOCR_CUDA(cudaMemcpyAsync(d_par, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
+    {   // token table: <sos> at position 0 of every row; dead rows flagged
+        std::vector<int32_t> init((size_t)R * KOCR_TOKENS_LD, 0);
+        for (int r = 0; r < R; ++r) init[(size_t)r * KOCR_TOKENS_LD] = 2;
+        KOCR_CUDA(cudaMemcpyAsync(tokens, init.data(), init.size() * 4, cudaMemcpyHostToDevice, s));
+        std::vector<int32_t> fin((size_t)R);
+        for (int r = 0; r < R; ++r) fin[r] = (r % bw) == 0 ? 0 : 1;
+        KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "finished"), fin.data(), fin.size() * 4, cudaMemcpyHostToDevice, s));
+        KOCR_CUDA(cudaMemsetAsync(buf<int>(h, "step_base"), 0, 64, s));
+        KOCR_CUDA(wait_stream(h, s));
+    }
+    // host state (reference: `beams` = list of (score, seq), `completed`)
+    struct Hyp { double score; std::vector<int32_t> seq; };
+    std::vector<std::vector<Hyp>> beams(n_lines);
+    std::vector<double> best_score(n_lines, -INFINITY);
+    std::vector<std::vector<int32_t>> best_seq(n_lines);
+    for (int l = 0; l < n_lines; ++l) beams[l].push_back(Hyp{0.0, std::vector<int32_t>{2}});
+    std::vector<float> hv((size_t)R * 8);
+    std::vector<int32_t> hi((size_t)R * 8), par((size_t)2 * ML);
+    int cur = 0;
+    DecRows rows;
+    rows.n_rows = R; rows.layer_stride = layer_stride; rows.tok_off = d_tokoff; rows.T = d_T;
+    struct Cand { double s; int hyp; int tok; };
+    std::vector<Cand> cand;
+    for (int t = 0; t < max_len; ++t) {
+        rows.kcache = base + cur * buf_stride;
+        rows.vcache = rows.kcache + kv_stride;
+        KOCR_TRY(decode_step(h, 0, max_T, s, &rows));
+        beam_topk_kernel<<<(R + 3) / 4, 128, 0, s>>>(reinterpret_cast<const float*>(h->trace.p), t, bw, R, d_vals, d_idx);
+        KOCR_CUDA(cudaGetLastError());
+        ++g_launches;
+        KOCR_CUDA(cudaMemcpyAsync(hv.data(), d_vals, (size_t)R * 8 * 4, cudaMemcpyDeviceToHost, s));
+        KOCR_CUDA(cudaMemcpyAsync(hi.data(), d_idx, (size_t)R * 8 * 4, cudaMemcpyDeviceToHost, s));
+        KOCR_CUDA(wait_stream(h, s));
+        bool any_live = false;
+        for (int l = 0; l < n_lines; ++l) {
+            std::vector<Hyp>& B = beams[l];
+            for (int i = 0; i < bw; ++i) { par[l * bw + i] = -1; par[(size_t)ML + l * bw + i] = 0; }
+            if (B.empty()) continue;
+            cand.clear();
+            for (int i = 0; i < (int)B.size(); ++i)
+                for (int k = 0; k < bw; ++k)
+                    cand.push_back(Cand{B[i].score + (double)hv[(size_t)(l * bw + i) * 8 + k], i, hi[(size_t)(l * bw + i) * 8 + k]});
+            std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.s > b.s; });   // list.sort(reverse=True)
+            std::vector<Hyp> next;
+            for (const Cand& c : cand) {
+                if (c.tok == 3) {                                   // <eos>: completed with score / len(seq)
+                    const double sc = c.s / (double)(B[c.hyp].seq.size() + 1);
+                    if (sc > best_score[l]) {                       // sorted(completed, reverse=True)[0]: first among equals
+                        best_score[l] = sc;
+                        best_seq[l] = B[c.hyp].seq;
+                        best_seq[l].push_back(3);
+                    }
+                } else if ((int)next.size() < bw) {
+                    par[l * bw + (int)next.size()] = l * bw + c.hyp;
+                    par[(size_t)ML + l * bw + (int)next.size()] = c.tok;
+                    Hyp nh{c.s, B[c.hyp].seq};
+                    nh.seq.push_back(c.tok);
+                    next.push_back(std::move(nh));
+                }
+            }
+            B.swap(next);
+            any_live = any_live || !B.empty();
+        }
+        if (!any_live || t + 1 >= max_len) break;
+        // device state of position t + 1: caches and prefixes follow their parents
+        KOCR_CUDA(cudaMemcpyAsync(d_par, par.data(), (size_t)2 * ML * 4, cudaMemcpyHostToDevice, s));
+        beam_rows_kernel<<<R, 64, 0, s>>>(tokens, d_tokB, d_par, d_newtok, buf<int>(h, "finished"), t);
+        KOCR_CUDA(cudaGetLastError());
+        KOCR_CUDA(cudaMemcpyAsync(tokens, d_tokB, (size_t)R * KOCR_TOKENS_LD * 4, cudaMemcpyDeviceToDevice, s));
+        const int nxt = cur ^ 1;
+        // (dead rows carry parent -1: clamp to their own row, the copy is harmless)
+        beam_reorder_kernel<<<dim3(R, 2, 2), 256, 0, s>>>(base + cur * buf_stride, base + nxt * buf_stride, d_par, R, t + 1, layer_stride, kv_stride);
+        KOCR_CUDA(cudaGetLastError());
+        g_launches += 2;
+        cur = nxt;
+        KOCR_TRY(launch_dec_bump(buf<int>(h, "step_base"), 1, s)); ++g_launches;
+    }
+    for (int l = 0; l < n_lines; ++l) {
+        // best completed hypothesis, else the first live one (predictor.py:135); `beams` is never empty in that case: a line
+        // without live beams has completed at least one
+        const std::vector<int32_t>& seq = !best_seq[l].empty() ? best_seq[l] : beams[l].front().seq;
+        const int n = std::min((int)seq.size(), KOCR_TOKENS_LD);
+        memset(tokens_out + (size_t)l * KOCR_TOKENS_LD, 0, KOCR_TOKENS_LD * 4);
+        memcpy(tokens_out + (size_t)l * KOCR_TOKENS_LD, seq.data(), (size_t)n * 4);
+        lengths_out[l] = n;
+    }
     return 0;
 }
 

@@ -173,6 +173,36 @@ class LinePipeline:
         if errors:
             raise errors[0]
 
+    def map_batches(self, batches, fn):
+        """Run `fn(recogniser, batch)` for every element of `batches`, up to `in_flight` at a time, each call on its own
+        recogniser and host thread (beam search, or any other multi-call sequence that must stay on one handle)."""
+        q: queue.Queue = queue.Queue()
+        for b in batches:
+            q.put(b)
+        n_threads = max(1, min(self.in_flight, len(batches)))
+        self._ensure(n_threads)
+        self._set_mode(n_threads > 1)
+        errors: list = []
+
+        def worker(rec):
+            try:
+                while True:
+                    try:
+                        b = q.get_nowait()
+                    except queue.Empty:
+                        return
+                    fn(rec, b)
+            except Exception as e:
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(self.recs[k],)) for k in range(n_threads)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
     def recognize(self, grays, max_steps: int = 0):
         """Greedy recognition of grey uint8 line images -> (tokens int32 [n, 257], lengths int32 [n]) in input order."""
         n = len(grays)

@@ -111,10 +111,33 @@ class OCRPredictor:
         return [self.tokenizer.decode(seq) for seq in beam.results()]
 
     def _beam_gray(self, grays, beam_width: int):
+        """Beam search for a list of grey lines: stages 1-5a per batch, then `kocr_beam_search` - the whole of
+        `OCRPredictor._beam_search` (reference predictor.py:101-136) for every line of the batch inside the library
+        (device log-softmax + top-k, the reference's bookkeeping in C++), several batches in flight on their own handles.
+        `_beam_search_batch` (the same bookkeeping in numpy over `kocr_beam_step_batch`) is kept as the cross-check."""
         if beam_width > 8:
             raise ValueError("beam_width > 8 is not supported by the CUDA path")
         results = [None] * len(grays)
         # every hypothesis is a row of the decode workspace: at most max_lines // beam_width lines per pass
+        lines_per_pass = max(1, self._max_lines // max(beam_width, 1))
+        batches = plan_batches([g.shape for g in grays], lines_per_pass, self._max_chunks, self.cfg.max_seq_len)
+
+        def run(rec, idxs):
+            rec.gather_chunks(LineBatch([grays[i] for i in idxs]))
+            rec.sevgg_encoder_forward()
+            rec.merge_bilstm_forward()
+            tokens, lengths = rec.beam_search(len(idxs), beam_width, self.cfg.decode_max_len)
+            for i, text in zip(idxs, self._decode_ids(tokens, lengths)):
+                results[i] = text
+
+        self._pipe.map_batches(batches, run)
+        return results
+
+    def _beam_gray_host(self, grays, beam_width: int):
+        """The round-1 path: one device pass per decoder position, bookkeeping in numpy (`beam.BatchedBeam`)."""
+        if beam_width > 8:
+            raise ValueError("beam_width > 8 is not supported by the CUDA path")
+        results = [None] * len(grays)
         lines_per_pass = max(1, self._max_lines // max(beam_width, 1))
         for idxs in plan_batches([g.shape for g in grays], lines_per_pass, self._max_chunks, self.cfg.max_seq_len):
             self.model.gather_chunks(LineBatch([grays[i] for i in idxs]))
