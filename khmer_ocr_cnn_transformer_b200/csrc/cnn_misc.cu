@@ -247,15 +247,20 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
                                                                   const float* __restrict__ b0p,
                                                                   const act16_t* __restrict__ w2p /*[C][128]*/,
                                                                   const float* __restrict__ b2,
-                                                                  act16_t* __restrict__ pooled, act16_t* __restrict__ out) {
+                                                                  act16_t* __restrict__ pooled, act16_t* __restrict__ out,
+                                                                  int n_chunks) {
     using S = SeSmem<C>;
     constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8;
     extern __shared__ __align__(16) uint8_t se_smem[];
     act16_t* sZ = reinterpret_cast<act16_t*>(se_smem);
     act16_t* sA = reinterpret_cast<act16_t*>(se_smem + S::Z_BYTES);
     float* sG = reinterpret_cast<float*>(se_smem + S::Z_BYTES);          // aliases sA (see SeSmem)
-    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // PERSISTENT over chunks (grid = 2 CTAs per SM): the 2 x 32 KB of FC weights a CTA reads through __ldg stay in ITS L1
+    // from the second chunk on - with one CTA per chunk every CTA paid their L2 latency inside two dependent MMA chains
+    // (ncu, round 2: 17 % SM busy, long-scoreboard stalls).
+#pragma unroll 1
+    for (int n = blockIdx.x; n < n_chunks; n += gridDim.x) {
     // ---- the chunk's pooled block (ROWS * 25 * C 16-bit values, contiguous) starts streaming into REGISTERS now: its HBM
     //      latency is hidden behind the two small contractions below instead of following them ----
     constexpr int TOTAL = SE_W * ROWS * CG;                 // 16-byte pieces of the block
@@ -393,6 +398,8 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
                                   pack_a16(acc[4] * inv, acc[5] * inv), pack_a16(acc[6] * inv, acc[7] * inv));
         }
     }
+    __syncthreads();        // shared memory is reused by the next chunk
+    }   // chunk loop
 }
 
 template <int C, int ROWS, bool FINAL>
@@ -401,7 +408,11 @@ static int launch_se_excite_impl(const act16_t* means, const SEWeights& w, act16
     const size_t smem = SeSmem<C>::BYTES + (FINAL ? SeSmem<C>::BINS_BYTES : 0);
     static PerDeviceOnce attr_once;
     KOCR_CUDA(opt_in_dynamic_smem(attr_once, se_excite_kernel<C, ROWS, FINAL>, (int)smem));
-    se_excite_kernel<C, ROWS, FINAL><<<n_chunks, SE_THREADS, smem, stream>>>(means, w.w0p, w.b0p, w.w2p, w.b2, pooled, out);
+    int dev = 0, sms = 148;
+    KOCR_CUDA(cudaGetDevice(&dev));
+    KOCR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = n_chunks < 2 * sms ? n_chunks : 2 * sms;
+    se_excite_kernel<C, ROWS, FINAL><<<grid, SE_THREADS, smem, stream>>>(means, w.w0p, w.b0p, w.w2p, w.b2, pooled, out, n_chunks);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }

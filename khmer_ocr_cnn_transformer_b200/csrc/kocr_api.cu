@@ -1310,7 +1310,7 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
     for (int l = 0; l < n_lines; ++l) beams[l].push_back(Hyp{0.0, std::vector<int32_t>{2}});
     std::vector<float> hv((size_t)R * 8);
     std::vector<int32_t> hi((size_t)R * 8), par((size_t)2 * ML);
-    int cur = 0;
+    int cur = 0, steps_run = 0;
     DecRows rows;
     rows.n_rows = R; rows.layer_stride = layer_stride; rows.tok_off = d_tokoff; rows.T = d_T;
     struct Cand { double s; int hyp; int tok; };
@@ -1355,7 +1355,13 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
             B.swap(next);
             any_live = any_live || !B.empty();
         }
-        if (!any_live || t + 1 >= max_len) break;
+        steps_run = t + 1;
+        int live_lines = 0;
+        for (int l = 0; l < n_lines; ++l) live_lines += beams[l].empty() ? 0 : 1;
+        // long tail (option "straggler_threshold", like kocr_decode_greedy): alternatives that never emit <eos> ramble on to
+        // max_len and hold the whole pass; stop once only a few lines still have live hypotheses - the caller re-submits
+        // those lines (kocr_read_unfinished; the search is deterministic)
+        if (!any_live || live_lines <= h->straggler_threshold || t + 1 >= max_len) break;
         // device state of position t + 1: caches and prefixes follow their parents
         KOCR_CUDA(cudaMemcpyAsync(d_par, par.data(), (size_t)2 * ML * 4, cudaMemcpyHostToDevice, s));
         beam_rows_kernel<<<R, 64, 0, s>>>(tokens, d_tokB, d_par, d_newtok, buf<int>(h, "finished"), t);
@@ -1377,7 +1383,9 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
         memset(tokens_out + (size_t)l * KOCR_TOKENS_LD, 0, KOCR_TOKENS_LD * 4);
         memcpy(tokens_out + (size_t)l * KOCR_TOKENS_LD, seq.data(), (size_t)n * 4);
         lengths_out[l] = n;
+        h->fin_host[l] = beams[l].empty() ? 1 : 0;          // live hypotheses left: unfinished unless the position budget ran out
     }
+    h->last_steps = steps_run; h->last_max_steps = max_len;
     return 0;
 }
 

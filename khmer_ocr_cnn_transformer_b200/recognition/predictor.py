@@ -120,17 +120,39 @@ class OCRPredictor:
         results = [None] * len(grays)
         # every hypothesis is a row of the decode workspace: at most max_lines // beam_width lines per pass
         lines_per_pass = max(1, self._max_lines // max(beam_width, 1))
-        batches = plan_batches([g.shape for g in grays], lines_per_pass, self._max_chunks, self.cfg.max_seq_len)
+        import threading
+        left, lock = [], threading.Lock()
 
-        def run(rec, idxs):
-            rec.gather_chunks(LineBatch([grays[i] for i in idxs]))
-            rec.sevgg_encoder_forward()
-            rec.merge_bilstm_forward()
-            tokens, lengths = rec.beam_search(len(idxs), beam_width, self.cfg.decode_max_len)
-            for i, text in zip(idxs, self._decode_ids(tokens, lengths)):
-                results[i] = text
+        def make_run(tail_div):
+            def run(rec, idxs):
+                # long tail: low-probability alternatives that never emit <eos> ramble on to decode_max_len and would hold the
+                # whole pass; a pass stops once <= 1/tail_div of its lines still have live hypotheses, those are searched
+                # again together afterwards (deterministic: same result)
+                rec.set_option("straggler_threshold", len(idxs) // tail_div if tail_div else 0)
+                rec.gather_chunks(LineBatch([grays[i] for i in idxs]))
+                rec.sevgg_encoder_forward()
+                rec.merge_bilstm_forward()
+                tokens, lengths = rec.beam_search(len(idxs), beam_width, self.cfg.decode_max_len)
+                todo = rec.unfinished(len(idxs)) if tail_div else np.zeros(len(idxs), np.int32)
+                texts = self._decode_ids(tokens, lengths)
+                with lock:
+                    for j, i in enumerate(idxs):
+                        if todo[j]:
+                            left.append(i)
+                        else:
+                            results[i] = texts[j]
+            return run
 
-        self._pipe.map_batches(batches, run)
+        def plan(ids):
+            return [[ids[j] for j in b] for b in plan_batches([grays[i].shape for i in ids], lines_per_pass, self._max_chunks,
+                                                              self.cfg.max_seq_len)]
+
+        self._pipe.map_batches(plan(list(range(len(grays)))), make_run(8))
+        if left:
+            again, left[:] = sorted(left), []
+            self._pipe.map_batches(plan(again), make_run(0))
+        for r in self._pipe.recs:
+            r.set_option("straggler_threshold", 0)
         return results
 
     def _beam_gray_host(self, grays, beam_width: int):
