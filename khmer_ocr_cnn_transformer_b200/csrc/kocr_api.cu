@@ -1353,6 +1353,17 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
                 }
             }
             B.swap(next);
+            // Exact early stop.  The reference never leaves its loop before decode_max_len positions (every live hypothesis
+            // contributes non-<eos> candidates, so `beams` is never empty) - it keeps extending low-probability alternatives
+            // long after the answer is known.  Log-probabilities are <= 0, so a hypothesis with score s can at best complete
+            // with a normalised score of s / (max_len + 1) (its sum can only fall, its length is at most max_len + 1); once
+            // that bound is below the best completed score for EVERY live hypothesis of the line, nothing the reference
+            // would still compute can change its answer (ties go to the earlier completion), and the line stops here.
+            if (best_score[l] > -INFINITY) {
+                bool can_win = false;
+                for (const Hyp& hy : B) can_win = can_win || (hy.score / (double)(max_len + 1) >= best_score[l]);
+                if (!can_win) B.clear();
+            }
             any_live = any_live || !B.empty();
         }
         steps_run = t + 1;
@@ -1383,7 +1394,7 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
         memset(tokens_out + (size_t)l * KOCR_TOKENS_LD, 0, KOCR_TOKENS_LD * 4);
         memcpy(tokens_out + (size_t)l * KOCR_TOKENS_LD, seq.data(), (size_t)n * 4);
         lengths_out[l] = n;
-        h->fin_host[l] = beams[l].empty() ? 1 : 0;          // live hypotheses left: unfinished unless the position budget ran out
+        h->fin_host[l] = beams[l].empty() ? 1 : 0;   // live hypotheses left: unfinished unless the position budget ran out
     }
     h->last_steps = steps_run; h->last_max_steps = max_len;
     return 0;
