@@ -9,7 +9,8 @@
  * a non-zero status on failure; kocr_last_error() then returns a thread-local message.  Nothing
  * throws across the boundary.  A handle owns its device weights and workspace, is bound to one
  * GPU, and must be used from one host thread at a time.  `stream` is a cudaStream_t passed as
- * void* (NULL = a stream owned by the handle).  There is NO CPU fallback: without a CUDA device every
+ * void* (NULL = a non-blocking stream owned by the handle; device buffers passed in are then ordered after the work the
+ * caller has enqueued on the default stream, and every call that returns data to the host synchronises before returning).  There is NO CPU fallback: without a CUDA device every
  * compute entry fails with an error.
  */
 #ifndef KOCR_H_

@@ -104,8 +104,12 @@ struct kocr_handle {
     // options
     int trace_logits = 0, force_tokens = 0;
     bool have_forced = false;
-    cudaStream_t own_stream = nullptr;       // used when the caller passes stream == NULL (blocking stream:
-                                             // implicitly ordered with the legacy default stream)
+    cudaStream_t own_stream = nullptr;       // used when the caller passes stream == NULL.  NON-blocking: a blocking stream that is
+                                             // capturing a CUDA graph makes every legacy-stream operation of any other host
+                                             // thread fail (cudaErrorStreamCaptureImplicit - seen with 8 ranks x 12 passes while
+                                             // another thread used torch's default stream); device inputs produced on the default
+                                             // stream are ordered explicitly instead (order_after_default_stream)
+    cudaEvent_t order_event = nullptr;
     struct DecGraph { cudaGraphExec_t exec = nullptr; size_t nodes = 0; };
     std::map<std::tuple<int, int, int, int>, DecGraph> dec_graphs;   // (n_lines, max_T bucket, trace, force)
     bool decode_warmed = false;
@@ -277,6 +281,15 @@ cudaError_t wait_stream(kocr_handle* h, cudaStream_t s) {
     return cudaEventSynchronize(h->sync_event);
 }
 
+// The caller handed us DEVICE memory and no stream: whatever it enqueued on the default (legacy) stream to produce that memory
+// must complete before our own (non-blocking) stream touches it.
+int order_after_default_stream(kocr_handle* h, cudaStream_t s) {
+    if (s != h->own_stream) return 0;           // the caller's own stream: the caller orders its work
+    KOCR_CUDA(cudaEventRecord(h->order_event, cudaStreamLegacy));
+    KOCR_CUDA(cudaStreamWaitEvent(s, h->order_event, 0));
+    return 0;
+}
+
 int carve_workspace(kocr_handle* h) {
     const size_t NC = h->max_chunks, L = h->max_lines, M = NC * TOK_PER_CHUNK;
     const size_t D = D_MODEL;
@@ -327,7 +340,8 @@ int carve_workspace(kocr_handle* h) {
     KOCR_CUDA(cudaEventCreateWithFlags(&h->staging_done, cudaEventDisableTiming | cudaEventBlockingSync));
     KOCR_CUDA(cudaEventCreateWithFlags(&h->sync_event, cudaEventDisableTiming | cudaEventBlockingSync));
     for (int i = 0; i < 2; ++i) KOCR_CUDA(cudaEventCreateWithFlags(&h->flag_event[i], cudaEventDisableTiming | cudaEventBlockingSync));
-    KOCR_CUDA(cudaStreamCreate(&h->own_stream));
+    KOCR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    KOCR_CUDA(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming));
     // input staging sized for the handle's capacity up front (4x the bytes of the height-48 chunks: source lines are
     // rarely more than 2x oversampled): a cudaMalloc in the middle of a run would synchronise every in-flight batch
     KOCR_TRY(ensure(h->pixels_dev, (size_t)h->max_chunks * CHUNK_STRIDE * IMG_H * 4));
@@ -767,6 +781,7 @@ int kocr_create(const void* weight_blob, size_t blob_bytes, int device, int max_
     if (rc) return fail(rc);
     rc = carve_workspace(h);
     if (rc) return fail(rc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("kocr_create: device synchronisation failed"); return fail(1); }   // weight upload / workspace memset ran on the default stream; ours is non-blocking
     *out = h;
     return 0;
 }
@@ -797,6 +812,7 @@ int kocr_destroy(kocr_handle* h) {
     for (int i = 0; i < 2; ++i) if (h->flag_event[i]) cudaEventDestroy(h->flag_event[i]);
     for (auto& g : h->dec_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->order_event) cudaEventDestroy(h->order_event);
     for (auto& p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     delete h;
@@ -902,6 +918,7 @@ int kocr_gather_chunks(kocr_handle* h, const uint8_t* pixels, size_t pixel_bytes
     KOCR_CUDA(cudaEventRecord(h->staging_done, s));
 
     const uint8_t* d_pix = pixels;
+    if (pixels_on_device) KOCR_TRY(order_after_default_stream(h, s));
     if (!pixels_on_device) {
         KOCR_TRY(ensure(h->pixels_dev, pixel_bytes));
         KOCR_CUDA(cudaMemcpyAsync(h->pixels_dev.p, pixels, pixel_bytes, cudaMemcpyHostToDevice, s));
@@ -1490,6 +1507,7 @@ int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w,
     KOCR_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
     const uint8_t* d_page = page;
+    KOCR_TRY(order_after_default_stream(h, s));       // out_pixels_dev (and a device page) belong to the caller
     if (!page_on_device) {
         const size_t bytes = (size_t)page_h * page_w * channels;
         KOCR_TRY(ensure(h->crop_page, bytes));

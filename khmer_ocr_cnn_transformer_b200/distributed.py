@@ -10,6 +10,17 @@ from .scheduling import shard_lines
 TOKENS_LD = 257
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device):
+    import torch
+    key = str(torch.device(device))
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def gather_ids(tok_local, len_local, shards, rank: int, world: int, group=None, device=None):
     """The one collective of a request: every rank contributes the ids of ITS shard (tok_local int32 [len(shards[rank]), 257],
     len_local int32 [...]), padded to the largest shard, in one `gather` to rank 0, which puts them back into input order.
@@ -25,11 +36,22 @@ def gather_ids(tok_local, len_local, shards, rank: int, world: int, group=None, 
         arrs = [send]
     else:
         t = torch.from_numpy(send)
-        if device is not None:
-            t = t.to(device, non_blocking=True)
-        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, parts, dst=0, group=group)
-        arrs = [p.cpu().numpy() for p in parts] if rank == 0 else None
+        if device is not None and torch.device(device).type == "cuda":
+            # on a side stream: the default (legacy) stream must stay out of it while other host threads of the process
+            # may be capturing CUDA graphs (libkocr's decode loop)
+            side = _side_stream(device)
+            with torch.cuda.stream(side):
+                t = t.to(device, non_blocking=True)
+                parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+                dist.gather(t, parts, dst=0, group=group)
+                arrs = [p.cpu().numpy() for p in parts] if rank == 0 else None
+                side.synchronize()
+        else:
+            if device is not None:
+                t = t.to(device)
+            parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+            dist.gather(t, parts, dst=0, group=group)
+            arrs = [p.cpu().numpy() for p in parts] if rank == 0 else None
     if rank != 0:
         return None
     n = sum(len(s) for s in shards)
