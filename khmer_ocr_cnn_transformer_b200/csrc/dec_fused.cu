@@ -1,7 +1,7 @@
 // Fused kernels of the greedy decode loop (TransformerDecoderWrapper.forward + OCRPredictor._greedy_decode,
 // se_model.py:182-208, predictor.py:85-99).  A generated position used to be 25 launches; every launch boundary costs
 // a few microseconds of dependent-chain latency per batch and, with a dozen batches in flight, a measurable share of the
-// whole GPU's time (profiles/r02/decode_attribution.md).  Two fusions take the count to 17:
+// whole GPU's time (profiles/r02/decode_attribution.md).  Two fusions take the count to 18:
 //
 //   dec_gemm_ln_kernel        out-projection (self-attention / cross-attention) or FFN2  +  bias + residual + LayerNorm
 //                             = post-norm sub-layer tail  x <- LN(x + W a + b)   (replaces: split-K GEMM, LayerNorm kernel).
@@ -9,8 +9,8 @@
 //                             for all 384 columns was tried first: a single SM cannot stream the weights fast enough);
 //                             the row statistics are combined through distributed shared memory.
 //   dec_out_argmax_kernel     output projection (384 -> 124)  +  argmax  +  greedy bookkeeping (stop BEFORE <eos>)
-//                             +  token + positional embedding of the NEXT position
-//                             (replaces: split-K GEMM, dec_argmax_kernel, dec_embed_kernel)
+//                             (replaces: split-K GEMM, dec_argmax_kernel; a first version also embedded the next position,
+//                             one row at a time per warp - a serial chain of L2 latencies, slower than the 3 us kernel it replaced)
 //
 // Both are single-tile tcgen05 GEMMs (TF32 operands, fp32 accumulation in TMEM, operands staged by TMA) whose epilogue
 // threads own one accumulator row each (tcgen05.ld 32x32b: lane = row), which is exactly the access pattern a row-wise
@@ -43,7 +43,8 @@ struct DfCommon {          // producer / MMA halves shared by the two kernels
 };
 
 // Sets up barriers + TMEM and runs the TMA producer (warp 0) and the MMA issuer (warp 1) for ONE 128 x N tile starting at
-// row m0; returns in the epilogue warps with the accumulator complete (tmem_full waited).  N is a multiple of 128: the B
+// row m0; returns true in the epilogue warps right away (they overlap their own prefetches with the main loop and then
+// call df_wait_accumulator), false in the producer / MMA warps once those are done.  N is a multiple of 128: the B
 // tile is loaded and multiplied as N / 128 slabs of 128 weight rows (TMA boxes hold at most 256 rows).
 template <int N>
 __device__ __forceinline__ bool df_mainloop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int m0, int b_row0, int num_kb,
@@ -108,9 +109,12 @@ __device__ __forceinline__ bool df_mainloop(const CUtensorMap& tmap_a, const CUt
         }
         return false;
     }
+    return true;              // epilogue warps: the caller prefetches what it needs, then df_wait_accumulator()
+}
+
+__device__ __forceinline__ void df_wait_accumulator(const DfCommon& c) {
     mbar_wait(c.tmem_full, 0);
     tc_fence_after();
-    return true;
 }
 
 template <int N>
@@ -127,8 +131,10 @@ __device__ __forceinline__ void df_finish(const DfCommon& c) {
 // grid = (3, m tiles), cluster (3,1,1): CTA `slab` computes output columns [slab*128, +128) of a 128-row tile.
 // ------------------------------------------------------------------------------------------
 static constexpr int LN_SLABS = D_MODEL / 128;     // 3
+static constexpr int LN_RES_PITCH = 528;           // bytes per row of the shared-memory residual slab (512 + 16)
+static constexpr int LN_SMEM_BYTES = DfCfg<128>::SMEM_BYTES + DF_BM * LN_RES_PITCH;
 
-__global__ void __cluster_dims__(LN_SLABS, 1, 1) __launch_bounds__(DF_THREADS, 2)
+__global__ void __cluster_dims__(LN_SLABS, 1, 1) __launch_bounds__(DF_THREADS, 1)
 dec_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int L, int num_kb,
                    const float* __restrict__ bias, const float* resid, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* out_x, float* out_xt) {
@@ -145,9 +151,21 @@ dec_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const long row = (long)m0 + r;
     const bool valid = row < L;
     const uint32_t t_row = c.tmem_base + (uint32_t(quad * 32) << 16);
+    // residual slab [128 rows][128 floats] of this CTA in shared memory, row pitch 528 B (row-per-thread float4 reads are then
+    // bank-conflict free).  The epilogue warps are idle while the MMAs run: they stream it in with coalesced cp.async.
+    const uint32_t s_res = smem_u32(c.smem + DF_STAGES * DfCfg<128>::STAGE_BYTES + 256);
     uint32_t v[32];
-    if (epi) {      // pass 1: v = acc + bias + residual, written back to TMEM; partial row sum of this slab
-        const float* rrow = resid + (valid ? row : 0) * D_MODEL + col0;
+    if (epi) {
+        const int te = threadIdx.x - 64;            // 0..127
+        for (int idx = te; idx < DF_BM * 32; idx += 128) {
+            const int rr = idx >> 5, c4 = idx & 31;
+            if ((long)m0 + rr < L) cp_async_16(s_res + rr * LN_RES_PITCH + c4 * 16, resid + ((long)m0 + rr) * D_MODEL + col0 + c4 * 4);
+        }
+        cp_async_commit();
+        df_wait_accumulator(c);
+        cp_async_wait<0>();
+        named_bar_sync(1, 128);                     // every epilogue thread's part of the slab has landed
+        // pass 1: v = acc + bias + residual, written back to TMEM; partial row sum of this slab
         float sum = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
@@ -156,7 +174,7 @@ dec_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + ch * 32 + j));
-                const float4 rr = __ldcg(reinterpret_cast<const float4*>(rrow + ch * 32 + j));    // written by a predecessor under PDL
+                const float4 rr = valid ? ld_shared_v4(s_res + r * LN_RES_PITCH + (ch * 32 + j) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float f0 = __uint_as_float(v[j]) + b.x + rr.x, f1 = __uint_as_float(v[j + 1]) + b.y + rr.y;
                 const float f2 = __uint_as_float(v[j + 2]) + b.z + rr.z, f3 = __uint_as_float(v[j + 3]) + b.w + rr.w;
                 sum += (f0 + f1) + (f2 + f3);
@@ -222,27 +240,26 @@ int launch_dec_gemm_ln(const float* a, int L, int K, const float* w, const float
     KOCR_TRY(make_tmap_2d(&ta, a, (uint64_t)L, (uint64_t)K, DF_BM, 4));
     KOCR_TRY(make_tmap_2d(&tb, w, (uint64_t)D_MODEL, (uint64_t)K, 128, 4));
     static PerDeviceOnce attr_once;
-    KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_gemm_ln_kernel, DfCfg<128>::SMEM_BYTES));
-    KOCR_CUDA(launch_kernel(dec_gemm_ln_kernel, dim3(LN_SLABS, (L + DF_BM - 1) / DF_BM), dim3(DF_THREADS), DfCfg<128>::SMEM_BYTES,
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_gemm_ln_kernel, LN_SMEM_BYTES));
+    KOCR_CUDA(launch_kernel(dec_gemm_ln_kernel, dim3(LN_SLABS, (L + DF_BM - 1) / DF_BM), dim3(DF_THREADS), LN_SMEM_BYTES,
                             stream, ta, tb, L, K / DF_KE, bias, resid, gamma, beta, out_x, out_xt));
     gemm_tc_count_launch();
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// logits = x W_out^T + b (384 -> 124, padded to 128), argmax (ties -> lowest index, like torch.argmax), the greedy
-// bookkeeping of predictor.py:90-97 (stop BEFORE appending <eos>), and the embedding of the next position
-// (se_model.py:184-186: tok_emb[token] + pos_emb[t + 1]) for the lines that go on.
+// logits = x W_out^T + b (384 -> 124, padded to 128), argmax (ties -> lowest index, like torch.argmax) and the greedy
+// bookkeeping of predictor.py:90-97 (stop BEFORE appending <eos>).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DF_THREADS, 2)
 dec_out_argmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int L, int num_kb,
                       const float* __restrict__ bias, int* tokens, int* lengths, int* finished, int* n_active,
-                      const int* __restrict__ step_base, int step_off, const int* __restrict__ forced, float* trace,
-                      const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, float* x_next, float* xt_next) {
+                      const int* __restrict__ step_base, int step_off, const int* __restrict__ forced, float* trace) {
     extern __shared__ uint8_t df_smem[];
     DfCommon c;
     const int m0 = blockIdx.x * DF_BM;
     if (df_mainloop<VOCAB_PAD>(tmap_a, tmap_b, m0, 0, num_kb, df_smem, c)) {
+        df_wait_accumulator(c);
         const int quad = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
         const int l = m0 + quad * 32 + lane;
         const int t = __ldcg(step_base) + step_off;
@@ -271,34 +288,16 @@ dec_out_argmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int j = 0; j < 32; ++j)
                 if (ch * 32 + j < VOCAB && f[j] > best) { best = f[j]; bi = ch * 32 + j; }      // ascending scan, strict >: lowest index wins ties
         }
-        int next = -1;              // token this line feeds to position t + 1 (-1: the line stops here)
         if (live) {
             if (forced) {
-                next = forced[l * TOK_LD + t + 1];
-                tokens[l * TOK_LD + t + 1] = next;
+                tokens[l * TOK_LD + t + 1] = forced[l * TOK_LD + t + 1];
                 lengths[l] = t + 2;
             } else if (bi == 3 || bi < 0) {         // <eos> (or no finite logit at all): finished, nothing appended
                 finished[l] = 1;
             } else {
                 tokens[l * TOK_LD + t + 1] = bi;
                 lengths[l] = t + 2;
-                if (t + 1 >= DEC_MAX) finished[l] = 1; else { atomicAdd(n_active + t, 1); next = bi; }
-            }
-            if (t + 1 >= DEC_MAX) next = -1;
-        }
-        // embedding of position t + 1: the warp copies one row at a time (32 lanes x 3 float4 = 384 floats)
-        const float4* pos = reinterpret_cast<const float4*>(pos_emb + (long)min(t + 1, DEC_MAX - 1) * D_MODEL);
-        for (int r = 0; r < 32; ++r) {
-            const int tk = __shfl_sync(0xffffffffu, next, r);
-            if (tk < 0) continue;
-            const long orow = (long)(m0 + quad * 32 + r) * (D_MODEL / 4);
-            const float4* e = reinterpret_cast<const float4*>(tok_emb + (long)tk * D_MODEL);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float4 a = __ldg(e + j * 32 + lane), p = __ldg(pos + j * 32 + lane);
-                const float4 s = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
-                reinterpret_cast<float4*>(x_next)[orow + j * 32 + lane] = s;
-                reinterpret_cast<float4*>(xt_next)[orow + j * 32 + lane] = make_float4(rna_tf32(s.x), rna_tf32(s.y), rna_tf32(s.z), rna_tf32(s.w));
+                if (t + 1 >= DEC_MAX) finished[l] = 1; else atomicAdd(n_active + t, 1);
             }
         }
     }
@@ -307,7 +306,7 @@ dec_out_argmax_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
 int launch_dec_out_argmax(const float* a, int L, const float* w /*[128][384]*/, const float* bias, int* tokens, int* lengths,
                           int* finished, int* n_active, const int* step_base, int step_off, const int* forced, float* trace,
-                          const float* tok_emb, const float* pos_emb, float* x_next, float* xt_next, cudaStream_t stream) {
+                          cudaStream_t stream) {
     KOCR_CHECK(L > 0, "dec_out_argmax: empty batch");
     CUtensorMap ta, tb;
     KOCR_TRY(make_tmap_2d(&ta, a, (uint64_t)L, (uint64_t)D_MODEL, DF_BM, 4));
@@ -316,7 +315,7 @@ int launch_dec_out_argmax(const float* a, int L, const float* w /*[128][384]*/, 
     KOCR_CUDA(opt_in_dynamic_smem(attr_once, dec_out_argmax_kernel, DfCfg<VOCAB_PAD>::SMEM_BYTES));
     KOCR_CUDA(launch_kernel(dec_out_argmax_kernel, dim3((L + DF_BM - 1) / DF_BM), dim3(DF_THREADS), DfCfg<VOCAB_PAD>::SMEM_BYTES,
                             stream, ta, tb, L, D_MODEL / DF_KE, bias, tokens, lengths, finished, n_active, step_base, step_off,
-                            forced, trace, tok_emb, pos_emb, x_next, xt_next));
+                            forced, trace));
     gemm_tc_count_launch();
     return 0;
 }

@@ -107,10 +107,10 @@ int launch_dec_bump(int* step_base, int n, cudaStream_t stream);
 // a row each (a: [L][K] fp32, w: [384][K]); writes the exact row (out_x, may alias resid) and its TF32-rounded copy (out_xt).
 int launch_dec_gemm_ln(const float* a, int L, int K, const float* w, const float* bias, const float* resid,
                        const float* gamma, const float* beta, float* out_x, float* out_xt, cudaStream_t stream);
-// Output projection + argmax + greedy bookkeeping + embedding of the next position (x_next / xt_next rows of the lines that go on).
+// Output projection + argmax + greedy bookkeeping.
 int launch_dec_out_argmax(const float* a, int L, const float* w /*[128][384]*/, const float* bias, int* tokens, int* lengths,
                           int* finished, int* n_active, const int* step_base, int step_off, const int* forced, float* trace,
-                          const float* tok_emb, const float* pos_emb, float* x_next, float* xt_next, cudaStream_t stream);
+                          cudaStream_t stream);
 // row compaction of the greedy loop: pairs = int2 (src row in the tail, dst row in the head), see seq.cu
 int launch_decode_compact(const int* pairs, int n_pairs, int t, float* kcache, float* vcache, size_t layer_stride, int* tokens,
                           int* lengths, int* finished, int* tok_off, int* line_T, cudaStream_t stream);

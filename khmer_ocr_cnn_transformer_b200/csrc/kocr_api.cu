@@ -134,8 +134,7 @@ struct kocr_handle {
                                  // 0: 128x128 tiles, no split (fewest CTAs: leaves the SMs to other in-flight batches)
     int debug_stop = 0;          // >0 (tests/diagnosis): a decode step launches only its first n kernels
     int dec_lookahead = 0;       // 1: enqueue decode group g+1 before polling the outcome of group g
-    int dec_fused = 0;           // 1: GEMM+LayerNorm and out_proj+argmax+embed kernels of dec_fused.cu (17 launches per position); 0: 25 launches
-                                 // (measured, 12 passes in flight: the fused kernels' thread-per-row epilogues are latency-bound - decode 5.8 vs 4.3 ms)
+    int dec_fused = 0;           // 1: GEMM+LayerNorm and out_proj+argmax kernels of dec_fused.cu (18 launches per position); 0: 25 launches
     int pool2_fused = 0;         // 1: the 2x2 max-pool after conv2 runs in conv2's epilogue (4 whole columns = 96 of 128 MMA rows per tile:
                                  // measured 5 % SLOWER than conv2 + pool2x2_kernel, profiles/r02); 0 (default): separate kernel
     int dec_skip = 0;            // diagnosis (tools/inflight_probe.py): bit mask of kernel classes a decode step does NOT launch
@@ -623,8 +622,8 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     float* dh = buf<float>(h, "dh");
     const int S2 = h->dec_wide ? 2 : 1, S8 = h->dec_wide ? 8 : 1;   // K = 384 -> 2 slices of 6 k-blocks; K = 1536 -> 8
     const bool fused = h->dec_fused != 0;
-    // fused path: the embedding of this position was written by the previous position's out_proj + argmax kernel
-    if (!fused || embed_first) DSKIP(16, DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches);
+    (void)embed_first;
+    DSKIP(16, DSTEP(launch_dec_embed(tokens, sb, off, h->dec_tok_emb, h->dec_pos, dx, dxt, nullptr, nullptr, L, s)); ++g_launches);
     for (int l = 0; l < 2; ++l) {
         const DecLayerW& w = h->dec[l];
         float* kc = rows ? rows->kcache + l * rows->layer_stride : buf<float>(h, "kcache") + (size_t)l * h->max_lines * DEC_MAX * D;
@@ -662,7 +661,7 @@ int decode_step(kocr_handle* h, int off, int max_T, cudaStream_t s, const DecRow
     float* trace = (h->trace_logits || rows) ? reinterpret_cast<float*>(h->trace.p) : nullptr;
     if (fused) {
         DSKIP(8, DSTEP(launch_dec_out_argmax(dxt, L, h->dec_out_w, h->dec_out_b, tokens, buf<int>(h, "lengths"), buf<int>(h, "finished"),
-                                             buf<int>(h, "n_active"), sb, off, forced, trace, h->dec_tok_emb, h->dec_pos, dx, dxt, s)));
+                                             buf<int>(h, "n_active"), sb, off, forced, trace, s)));
         return 0;
     }
     DSKIP(8, DSTEP(gemm_dec(h, dxt, L, h->dec_out_w, VOCAB_PAD, D, S2, parts, s)));
@@ -966,15 +965,10 @@ int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32
         KOCR_CUDA(cudaMemsetAsync(h->trace.p, 0, (size_t)L * DEC_MAX * VOCAB_PAD * 4, s));
     }
     const bool forcing = h->force_tokens && h->have_forced;
-    if (h->dec_fused) {     // position 0 (<sos>); every later position is embedded by the previous position's argmax kernel
-        KOCR_TRY(launch_dec_embed(tokens, buf<int>(h, "step_base"), 0, h->dec_tok_emb, h->dec_pos, buf<float>(h, "dx"), buf<float>(h, "dq"),
-                                  nullptr, nullptr, L, s));
-        ++g_launches;
-    }
     const int max_T = (h->max_T + 127) / 128 * 128;      // bucketed: only sizes the cross-attention scratch
     // Row compaction (see decode_compact_kernel): plain greedy decoding only - the logits trace and forced tokens are
     // indexed by the caller's line numbers
-    const bool may_compact = h->compact_rows && !forcing && !h->trace_logits && !h->dec_fused;   // (the fused path keeps the next position's embedding per row)
+    const bool may_compact = h->compact_rows && !forcing && !h->trace_logits;
     h->dec_rows = L;
     h->row_orig.resize(L);
     for (int i = 0; i < L; ++i) h->row_orig[i] = i;
