@@ -496,7 +496,7 @@ def main():
                 for s in kt}
 
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
         run, kind, note = reference_runner(sd, cfg["variant"])
         imgs = wl.images
         run(imgs[:2])
