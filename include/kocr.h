@@ -128,6 +128,23 @@ int kocr_beam_search(kocr_handle* h, int beam_width, int max_len, int32_t* token
  * with the training-time memory); the next kocr_gather_chunks resets it. */
 int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L, float* logits_out, void* stream);
 
+/* The reference's MODEL protocol - what its OCRPredictor calls on `self.model` (predictor.py:53-78,166-192; modules at
+ * model/se_model.py:35-79 cnn, :81-117 patch, :119-126 enc, :228-234 context_bilstm, :162-208 dec) - as stage-level entry
+ * points on HOST tensors in the reference's own layouts (fp32, C-contiguous).  They reuse the handle's batch state: do not
+ * interleave them with a kocr_gather_chunks ... kocr_decode_greedy sequence on the same handle.
+ *   cnn:    chunks (n, 1, 48, 100)        -> f (n, 512, 2, 32)
+ *   patch:  f (n, 512, 2, 32)             -> x (n, 32, 384)            (+ bias + local positions; the reference also returns N = 32)
+ *   enc:    p seq-first (32, n, 384)      -> (32, n, 384)
+ *   bilstm: merged (B, T, 384)            -> (B, T, 384)               (zero initial state; SE-VGG family only)
+ *   dec:    tgt int32 (B, t), memory (B, T, 384), pad_mask uint8 (B, T) (1 = padded, a suffix per line; may be NULL)
+ *                                         -> logits (B, t, vocab = 124)  (causal self-attention, <pad> target keys masked) */
+int kocr_model_cnn(kocr_handle* h, const float* chunks, int n, float* f_out, void* stream);
+int kocr_model_patch(kocr_handle* h, const float* f, int n, float* x_out, void* stream);
+int kocr_model_enc(kocr_handle* h, const float* p, int n, float* out, void* stream);
+int kocr_model_bilstm(kocr_handle* h, const float* merged, int B, int T, float* out, void* stream);
+int kocr_model_dec(kocr_handle* h, const int32_t* tgt, int B, int t, const float* memory, int T, const uint8_t* pad_mask,
+                   float* logits_out, void* stream);
+
 /* Input side - extract_textline_crops (netra_ocr/textline_detection.py:7-53) and the custom-detector crop of
  * OCREngine (netra_ocr/ocr_engine.py:72-76), followed by the `convert('L')` of ImagePreprocessor.process
  * (recognition/preprocessor.py:39-41).  page = uint8 [page_h][page_w][channels] (3 = RGB, 1 = L), host or device.

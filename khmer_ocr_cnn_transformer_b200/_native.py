@@ -16,6 +16,7 @@ EXPORTS = [
     "kocr_model_info", "kocr_gather_chunks", "kocr_sevgg_encoder_forward", "kocr_merge_bilstm_forward",
     "kocr_decode_greedy", "kocr_recognize_lines", "kocr_set_option", "kocr_set_forced_tokens",
     "kocr_debug_read", "kocr_launch_count", "kocr_test_gemm", "kocr_read_kernel_timing", "kocr_read_unfinished", "kocr_beam_step", "kocr_beam_step_batch", "kocr_crop_lines", "kocr_forward_teacher_forced", "kocr_beam_search",
+    "kocr_model_cnn", "kocr_model_patch", "kocr_model_enc", "kocr_model_bilstm", "kocr_model_dec",
 ]
 
 _lib = None
@@ -58,6 +59,13 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.kocr_beam_step.restype = i32
     lib.kocr_beam_step_batch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
     lib.kocr_beam_step_batch.restype = i32
+    for f in ("kocr_model_cnn", "kocr_model_patch", "kocr_model_enc"):
+        getattr(lib, f).argtypes = [vp, vp, i32, vp, vp]
+        getattr(lib, f).restype = i32
+    lib.kocr_model_bilstm.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.kocr_model_bilstm.restype = i32
+    lib.kocr_model_dec.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp]
+    lib.kocr_model_dec.restype = i32
     lib.kocr_beam_search.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.kocr_beam_search.restype = i32
     lib.kocr_crop_lines.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]
@@ -245,6 +253,48 @@ class Recognizer:
         lengths = np.zeros(max(n_lines, 1), np.int32)
         check(self.lib.kocr_beam_search(self._h, int(beam_width), int(max_len), _ptr(tokens), _ptr(lengths), None))
         return tokens[:n_lines], lengths[:n_lines]
+
+    # ---- the reference's model protocol (predictor.py:53-78,166-192), numpy in / numpy out ------------------------------
+    def model_cnn(self, chunks: np.ndarray) -> np.ndarray:
+        """`model.cnn`: chunks fp32 (n, 1, 48, 100) -> features fp32 (n, 512, 2, 32)."""
+        x = np.ascontiguousarray(chunks, np.float32).reshape(-1, 1, 48, 100)
+        out = np.empty((x.shape[0], 512, 2, 32), np.float32)
+        check(self.lib.kocr_model_cnn(self._h, _ptr(x), x.shape[0], _ptr(out), None))
+        return out
+
+    def model_patch(self, f: np.ndarray) -> np.ndarray:
+        """`model.patch`: features (n, 512, 2, 32) -> patch embeddings + local positions (n, 32, 384)."""
+        x = np.ascontiguousarray(f, np.float32).reshape(-1, 512, 2, 32)
+        out = np.empty((x.shape[0], 32, self.emb_dim), np.float32)
+        check(self.lib.kocr_model_patch(self._h, _ptr(x), x.shape[0], _ptr(out), None))
+        return out
+
+    def model_enc(self, p: np.ndarray) -> np.ndarray:
+        """`model.enc`: seq-first (32, n, 384) -> (32, n, 384)."""
+        x = np.ascontiguousarray(p, np.float32)
+        assert x.ndim == 3 and x.shape[0] == 32 and x.shape[2] == self.emb_dim
+        out = np.empty_like(x)
+        check(self.lib.kocr_model_enc(self._h, _ptr(x), x.shape[1], _ptr(out), None))
+        return out
+
+    def model_bilstm(self, merged: np.ndarray) -> np.ndarray:
+        """`model.context_bilstm` (zero initial state): (B, T, 384) -> (B, T, 384)."""
+        x = np.ascontiguousarray(merged, np.float32)
+        assert x.ndim == 3 and x.shape[2] == self.emb_dim
+        out = np.empty_like(x)
+        check(self.lib.kocr_model_bilstm(self._h, _ptr(x), x.shape[0], x.shape[1], _ptr(out), None))
+        return out
+
+    def model_dec(self, tgt: np.ndarray, memory: np.ndarray, pad_mask=None) -> np.ndarray:
+        """`model.dec(tgt, memory, memory_key_padding_mask)`: tgt int (B, t), memory (B, T, 384), mask bool (B, T) with True =
+        padded (a suffix per line) or None -> logits fp32 (B, t, vocab)."""
+        tg = np.ascontiguousarray(tgt, np.int32)
+        mem = np.ascontiguousarray(memory, np.float32)
+        assert tg.ndim == 2 and mem.ndim == 3 and mem.shape[0] == tg.shape[0] and mem.shape[2] == self.emb_dim
+        mk = np.ascontiguousarray(pad_mask, np.uint8) if pad_mask is not None else None
+        out = np.empty((tg.shape[0], tg.shape[1], self.vocab_size), np.float32)
+        check(self.lib.kocr_model_dec(self._h, _ptr(tg), tg.shape[0], tg.shape[1], _ptr(mem), mem.shape[1], _ptr(mk), _ptr(out), None))
+        return out
 
     def crop_lines(self, page, boxes, pad_px: int, out_dev_ptr: int, out_offsets, page_dev_ptr=None, stream=None):
         """Cut `boxes` (int32 [n, 4] = x0, y0, x1, y1, clipped) out of `page` (uint8 (H, W) or (H, W, 3); pass

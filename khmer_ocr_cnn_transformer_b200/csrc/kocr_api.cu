@@ -57,6 +57,9 @@ struct Buf {
 
 using namespace kocr;
 
+struct kocr_handle;
+extern "C" int kocr_decode_greedy(kocr_handle* h, int max_steps, int32_t* tokens_out, int32_t* lengths_out, void* stream);
+
 struct kocr_handle {
     int device = 0;
     int num_sms = 148;
@@ -473,14 +476,17 @@ int stage_resnet_backbone(kocr_handle* h, cudaStream_t s) {
     return 0;
 }
 
-int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
+// parts: 1 = backbone (chunks -> patch_in), 2 = patch projection (patch_in -> x), 4 = encoder layers (x -> x); the whole
+// path runs all three with the merge's global_pos added by the last LayerNorm (the model-protocol entry points run one part)
+int stage_cnn_encoder(kocr_handle* h, cudaStream_t s, int parts = 7, bool add_global_pos = true) {
     const int NC = h->n_chunks;
     if (NC == 0) return 0;
     const bool se = h->variant == 0;
     auto B = [&](const char* n) { return buf<act16_t>(h, n); };
     const double nc = NC;
     auto cf = [&](int H, int W, int ci, int co) { return 2.0 * nc * H * W * 9.0 * ci * co; };   // algorithmic conv FLOPs
-    if (h->variant == 2) {
+    if (!(parts & 1)) {
+    } else if (h->variant == 2) {
         KOCR_TRY(stage_resnet_backbone(h, s));
     } else {
     // SE-VGG (se_model.py:63-79) / VGG baseline (vgg_model.py:50-59).  conv4 / conv6 / conv7 never store their un-pooled
@@ -512,13 +518,13 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
     const long M = (long)NC * TOK_PER_CHUNK;
     float* x = buf<float>(h, "x"); float* y = buf<float>(h, "y");
     act16_t* xb = B("xb");
-    {   // patch projection + bias + local positional encoding (se_model.py:108-115)
+    if (parts & 2) {   // patch projection + bias + local positional encoding (se_model.py:108-115)
         GemmEpilogue e = ep_none();
         e.bias = h->patch_b; e.addend = h->patch_pos; e.ld_add = D_MODEL; e.add_period = TOK_PER_CHUNK;
         e.out_f32 = x; e.ld_f32 = D_MODEL; e.out_a16 = xb; e.ld_a16 = D_MODEL;
         TIMED("patch_proj", 2.0 * M * 1024 * D_MODEL, gemm_linear(h, B("patch_in"), M, h->patch_w, D_MODEL, 1024, e, s));
     }
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < 2 && (parts & 4); ++l) {
         const EncLayerW& w = h->enc[l];
         GemmEpilogue e = ep_none();
         e.bias = w.in_b; e.out_a16 = B("qkv"); e.ld_a16 = 3 * D_MODEL;
@@ -535,7 +541,7 @@ int stage_cnn_encoder(kocr_handle* h, cudaStream_t s) {
         e.bias = w.l2_b; e.addend = x; e.ld_add = D_MODEL; e.out_f32 = y; e.ld_f32 = D_MODEL;
         TIMED("enc_ffn2", 2.0 * M * D_MODEL * 1024, gemm_linear(h, B("hff"), M, w.l2_w, D_MODEL, 1024, e, s));
         // last layer: fuse the merge's "+ global_pos[t]" (predictor.py:178-183) into the LayerNorm
-        const bool last = l == 1;
+        const bool last = l == 1 && add_global_pos;
         TIMED("enc_layernorm", 0, launch_layernorm(y, w.n2_g, w.n2_b, last ? h->global_pos : nullptr, last ? h->d_row_pos : nullptr, x,
                                   xb, nullptr, (int)M, s)); ++g_launches;
     }
@@ -557,11 +563,12 @@ int project_cross_kv(kocr_handle* h, long rows, const float* mem_f32, const act1
     return 0;
 }
 
-int stage_memory(kocr_handle* h, cudaStream_t s) {
+int stage_memory(kocr_handle* h, cudaStream_t s, int parts = 3) {
     const long M = h->n_tok;
     if (M == 0) return 0;
     const act16_t* memb = buf<act16_t>(h, "xb");
-    if (h->variant == 0) {
+    if (h->variant == 0 && !(parts & 1)) memb = buf<act16_t>(h, "memb");
+    if (h->variant == 0 && (parts & 1)) {
         GemmEpilogue e = ep_none();
         e.bias = h->lstm_b; e.out_f32 = buf<float>(h, "gin"); e.ld_f32 = 8 * LSTM_H;
         if (h->lstm_split) {        // split-precision input projection: fp32 merged sequence as [hi | lo | hi] rows (see project_cross_kv)
@@ -579,6 +586,7 @@ int stage_memory(kocr_handle* h, cudaStream_t s) {
         ++g_launches;
         memb = buf<act16_t>(h, "memb");
     }
+    if (!(parts & 2)) return 0;
     return project_cross_kv(h, M, buf<float>(h, h->variant == 0 ? "mem" : "x"), memb, s);
 }
 
@@ -716,6 +724,106 @@ int decode_group_graph(kocr_handle* h, int max_T, cudaStream_t s) {
     return 0;
 }
 
+
+// ---- tables of a batch given as token counts (model-protocol entry points; kocr_gather_chunks derives them from images) --
+// Line i owns rows [off_i, off_i + T_i) of the token-major buffers, off_i = sum of the previous lines' T rounded up to 32.
+int set_token_tables(kocr_handle* h, int n_lines, const int* T, cudaStream_t s) {
+    KOCR_CHECK(n_lines > 0 && n_lines <= h->max_lines, "model call: %d lines exceed the handle's capacity %d", n_lines, h->max_lines);
+    KOCR_CUDA(cudaEventSynchronize(h->staging_done));
+    uint8_t* sp = h->staging_host;
+    LineDesc* lines = reinterpret_cast<LineDesc*>(sp); sp += (size_t)h->max_lines * sizeof(LineDesc);
+    int* chunk_line = reinterpret_cast<int*>(sp); sp += (size_t)h->max_chunks * 4;
+    int* row_pos = reinterpret_cast<int*>(sp); sp += (size_t)h->max_chunks * TOK_PER_CHUNK * 4;
+    int* tok_off = reinterpret_cast<int*>(sp); sp += (size_t)h->max_lines * 4;
+    int* lineT = reinterpret_cast<int*>(sp); sp += (size_t)h->max_lines * 4;
+    sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
+    LstmGroup* groups = reinterpret_cast<LstmGroup*>(sp);
+    auto dev_of = [&](void* hp) { return h->staging_dev + (reinterpret_cast<uint8_t*>(hp) - h->staging_host); };
+    h->d_lines = reinterpret_cast<LineDesc*>(dev_of(lines));
+    h->d_chunk_line = reinterpret_cast<int*>(dev_of(chunk_line));
+    h->d_row_pos = reinterpret_cast<int*>(dev_of(row_pos));
+    h->d_line_tok_off = reinterpret_cast<int*>(dev_of(tok_off));
+    h->d_line_T = reinterpret_cast<int*>(dev_of(lineT));
+    h->d_groups = reinterpret_cast<LstmGroup*>(dev_of(groups));
+    h->n_lines = n_lines; h->max_T = 0; h->max_new_w = 0;
+    h->line_T.assign(n_lines, 0); h->line_first_chunk.assign(n_lines, 0); h->line_n_chunks.assign(n_lines, 0);
+    int nc = 0;
+    for (int i = 0; i < n_lines; ++i) {
+        KOCR_CHECK(T[i] > 0 && T[i] <= h->max_seq_len, "model call: line %d has %d tokens (1..%d supported)", i, T[i], h->max_seq_len);
+        const int n = (T[i] + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
+        KOCR_CHECK(nc + n <= h->max_chunks, "model call: batch needs more than %d x 32 token rows", h->max_chunks);
+        memset(&lines[i], 0, sizeof(LineDesc));
+        lines[i].first_chunk = nc; lines[i].n_chunks = n;
+        for (int k = 0; k < n; ++k) chunk_line[nc + k] = i;
+        for (int r = 0; r < n * TOK_PER_CHUNK; ++r) row_pos[(size_t)nc * TOK_PER_CHUNK + r] = std::min(r, h->max_seq_len - 1);
+        tok_off[i] = nc * TOK_PER_CHUNK; lineT[i] = T[i];
+        h->line_T[i] = T[i]; h->line_first_chunk[i] = nc; h->line_n_chunks[i] = n;
+        h->max_T = std::max(h->max_T, T[i]);
+        nc += n;
+    }
+    h->n_chunks = nc; h->n_tok = nc * TOK_PER_CHUNK;
+    std::vector<int> order(n_lines);
+    for (int i = 0; i < n_lines; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->line_T[a] > h->line_T[b]; });
+    h->n_groups = (n_lines + 7) / 8;
+    for (int g = 0; g < h->n_groups; ++g)
+        for (int j = 0; j < 8; ++j) groups[g].line[j] = (g * 8 + j < n_lines) ? order[g * 8 + j] : -1;
+    LstmGroup16* groups16 = reinterpret_cast<LstmGroup16*>(groups + h->n_groups);
+    h->d_groups16 = reinterpret_cast<LstmGroup16*>(dev_of(groups16));
+    h->n_groups16 = (n_lines + 15) / 16;
+    for (int g = 0; g < h->n_groups16; ++g)
+        for (int j = 0; j < 16; ++j) groups16[g].line[j] = (g * 16 + j < n_lines) ? order[g * 16 + j] : -1;
+    const size_t used = reinterpret_cast<uint8_t*>(groups16 + h->n_groups16) - h->staging_host;
+    KOCR_CHECK(used <= h->staging_bytes, "internal: staging overflow");
+    KOCR_CUDA(cudaMemcpyAsync(h->staging_dev, h->staging_host, used, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaEventRecord(h->staging_done, s));
+    return 0;
+}
+
+// host fp32 -> the library's 16-bit format (round to nearest even, saturating like pack_a16)
+inline act16_t host_a16(float x) {
+#ifdef KOCR_A16_BF16
+    return __float2bfloat16_rn(x);
+#else
+    if (x > 65504.f) x = 65504.f;
+    if (x < -65504.f) x = -65504.f;
+    return __float2half_rn(x);
+#endif
+}
+inline float host_f32(act16_t x) {
+#ifdef KOCR_A16_BF16
+    return __bfloat162float(x);
+#else
+    return __half2float(x);
+#endif
+}
+
+// forced-token decode of the current batch (memory + cross K/V in place): logits of positions 0 .. L-1 -> host [B][L][ld_out]
+int run_forced_decode(kocr_handle* h, const int32_t* tgt, int B, int L, float* logits_out, int n_valid, void* stream, cudaStream_t s) {
+    std::vector<int32_t> forced((size_t)B * KOCR_TOKENS_LD, 0);
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < L; ++t) forced[(size_t)b * KOCR_TOKENS_LD + t] = tgt[(size_t)b * L + t];
+    KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "forced"), forced.data(), forced.size() * 4, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(wait_stream(h, s));              // `forced` is a host vector of this call
+    const int sv_force = h->force_tokens, sv_trace = h->trace_logits, sv_thr = h->straggler_threshold;
+    const bool sv_have = h->have_forced;
+    h->force_tokens = 1; h->trace_logits = 1; h->have_forced = true; h->straggler_threshold = 0;
+    const int rc = kocr_decode_greedy(h, L, nullptr, nullptr, stream);
+    h->force_tokens = sv_force; h->trace_logits = sv_trace; h->have_forced = sv_have; h->straggler_threshold = sv_thr;
+    if (rc) return rc;
+    if (n_valid == VOCAB_PAD) {
+        KOCR_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)L * VOCAB_PAD * 4, h->trace.p, (size_t)DEC_MAX * VOCAB_PAD * 4,
+                                    (size_t)L * VOCAB_PAD * 4, B, cudaMemcpyDeviceToHost, s));
+        KOCR_CUDA(wait_stream(h, s));
+    } else {        // compact rows of `n_valid` logits
+        std::vector<float> tmp((size_t)B * L * VOCAB_PAD);
+        KOCR_CUDA(cudaMemcpy2DAsync(tmp.data(), (size_t)L * VOCAB_PAD * 4, h->trace.p, (size_t)DEC_MAX * VOCAB_PAD * 4,
+                                    (size_t)L * VOCAB_PAD * 4, B, cudaMemcpyDeviceToHost, s));
+        KOCR_CUDA(wait_stream(h, s));
+        for (size_t r = 0; r < (size_t)B * L; ++r) memcpy(logits_out + r * n_valid, tmp.data() + r * VOCAB_PAD, (size_t)n_valid * 4);
+    }
+    return 0;
+}
 }  // namespace
 
 // ===========================================================================================
@@ -1467,21 +1575,145 @@ int kocr_forward_teacher_forced(kocr_handle* h, const int32_t* tgt_tokens, int L
     // ... and in the host copy of the table, which kocr_decode_greedy restores from after a row compaction
     memcpy(h->staging_host + (reinterpret_cast<uint8_t*>(h->d_line_tok_off) - h->staging_dev), tab.data(), (size_t)B * 4);
     for (int b = 0; b < B; ++b) h->line_first_chunk[b] = b * Tmax / TOK_PER_CHUNK;
-    std::vector<int32_t> forced((size_t)B * KOCR_TOKENS_LD, 0);
-    for (int b = 0; b < B; ++b)
-        for (int t = 0; t < L; ++t) forced[(size_t)b * KOCR_TOKENS_LD + t] = tgt_tokens[(size_t)b * L + t];
-    KOCR_CUDA(cudaMemcpyAsync(buf<int>(h, "forced"), forced.data(), forced.size() * 4, cudaMemcpyHostToDevice, s));
-    KOCR_CUDA(wait_stream(h, s));              // `tab` / `forced` are host vectors of this call
-    const int sv_force = h->force_tokens, sv_trace = h->trace_logits, sv_thr = h->straggler_threshold;
-    const bool sv_have = h->have_forced;
-    h->force_tokens = 1; h->trace_logits = 1; h->have_forced = true; h->straggler_threshold = 0;
-    const int rc = kocr_decode_greedy(h, L, nullptr, nullptr, stream);
-    h->force_tokens = sv_force; h->trace_logits = sv_trace; h->have_forced = sv_have; h->straggler_threshold = sv_thr;
-    if (rc) return rc;
-    KOCR_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)L * VOCAB_PAD * 4, h->trace.p, (size_t)DEC_MAX * VOCAB_PAD * 4,
-                                (size_t)L * VOCAB_PAD * 4, B, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(wait_stream(h, s));              // `tab` is a host vector of this call
+    return run_forced_decode(h, tgt_tokens, B, L, logits_out, VOCAB_PAD, stream, s);
+}
+
+// ---- the reference's MODEL protocol (predictor.py:53-78,166-192) on host tensors in the reference's layouts ----------------
+namespace {
+// tables for a chunk-level stage call: the n chunks are independent there, so they are booked as lines of up to
+// max_seq_len / 32 chunks (any n <= max_chunks fits, whatever max_lines is)
+int set_chunk_tables(kocr_handle* h, int n, cudaStream_t s) {
+    const int per_line = std::max(1, h->max_seq_len / TOK_PER_CHUNK);
+    std::vector<int> T;
+    for (int left = n; left > 0; left -= per_line) T.push_back(std::min(left, per_line) * TOK_PER_CHUNK);
+    return set_token_tables(h, (int)T.size(), T.data(), s);
+}
+}  // namespace
+
+int kocr_model_cnn(kocr_handle* h, const float* chunks, int n, float* f_out, void* stream) {
+    KOCR_CHECK(h != nullptr && chunks != nullptr && f_out != nullptr, "kocr_model_cnn: null argument");
+    KOCR_CHECK(n > 0 && n <= h->max_chunks, "kocr_model_cnn: %d chunks exceed the handle's capacity", n);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    KOCR_TRY(set_chunk_tables(h, n, s));                 // every chunk is its own 32-token "line"
+    KOCR_CUDA(cudaMemcpyAsync(buf<float>(h, "chunks"), chunks, (size_t)n * IMG_H * CHUNK_W * 4, cudaMemcpyHostToDevice, s));
+    KOCR_TRY(stage_cnn_encoder(h, s, 1));
+    std::vector<act16_t> pin((size_t)n * TOK_PER_CHUNK * 1024);
+    KOCR_CUDA(cudaMemcpyAsync(pin.data(), buf<act16_t>(h, "patch_in"), pin.size() * 2, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(wait_stream(h, s));
+    for (int i = 0; i < n; ++i)                                     // patch_in [n*32 + k][kh*512 + c] -> f (n, 512, 2, 32)
+        for (int k = 0; k < TOK_PER_CHUNK; ++k)
+            for (int kh = 0; kh < 2; ++kh)
+                for (int c = 0; c < 512; ++c)
+                    f_out[(((size_t)i * 512 + c) * 2 + kh) * TOK_PER_CHUNK + k] = host_f32(pin[((size_t)i * TOK_PER_CHUNK + k) * 1024 + kh * 512 + c]);
+    return 0;
+}
+
+int kocr_model_patch(kocr_handle* h, const float* f, int n, float* x_out, void* stream) {
+    KOCR_CHECK(h != nullptr && f != nullptr && x_out != nullptr, "kocr_model_patch: null argument");
+    KOCR_CHECK(n > 0 && n <= h->max_chunks, "kocr_model_patch: %d chunks exceed the handle's capacity", n);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    KOCR_TRY(set_chunk_tables(h, n, s));
+    std::vector<act16_t> pin((size_t)n * TOK_PER_CHUNK * 1024);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < TOK_PER_CHUNK; ++k)
+            for (int kh = 0; kh < 2; ++kh)
+                for (int c = 0; c < 512; ++c)
+                    pin[((size_t)i * TOK_PER_CHUNK + k) * 1024 + kh * 512 + c] = host_a16(f[(((size_t)i * 512 + c) * 2 + kh) * TOK_PER_CHUNK + k]);
+    KOCR_CUDA(cudaMemcpyAsync(buf<act16_t>(h, "patch_in"), pin.data(), pin.size() * 2, cudaMemcpyHostToDevice, s));
+    KOCR_TRY(stage_cnn_encoder(h, s, 2));
+    KOCR_CUDA(cudaMemcpyAsync(x_out, buf<float>(h, "x"), (size_t)n * TOK_PER_CHUNK * D_MODEL * 4, cudaMemcpyDeviceToHost, s));
     KOCR_CUDA(wait_stream(h, s));
     return 0;
+}
+
+int kocr_model_enc(kocr_handle* h, const float* p, int n, float* out, void* stream) {
+    KOCR_CHECK(h != nullptr && p != nullptr && out != nullptr, "kocr_model_enc: null argument");
+    KOCR_CHECK(n > 0 && n <= h->max_chunks, "kocr_model_enc: %d chunks exceed the handle's capacity", n);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    KOCR_TRY(set_chunk_tables(h, n, s));
+    const size_t rows = (size_t)n * TOK_PER_CHUNK;
+    std::vector<float> x(rows * D_MODEL);
+    std::vector<act16_t> xb(rows * D_MODEL);
+    for (int tok = 0; tok < TOK_PER_CHUNK; ++tok)                   // seq-first (32, n, 384) -> chunk-major rows
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d < D_MODEL; ++d) {
+                const float v = p[((size_t)tok * n + i) * D_MODEL + d];
+                x[((size_t)i * TOK_PER_CHUNK + tok) * D_MODEL + d] = v;
+                xb[((size_t)i * TOK_PER_CHUNK + tok) * D_MODEL + d] = host_a16(v);
+            }
+    KOCR_CUDA(cudaMemcpyAsync(buf<float>(h, "x"), x.data(), x.size() * 4, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaMemcpyAsync(buf<act16_t>(h, "xb"), xb.data(), xb.size() * 2, cudaMemcpyHostToDevice, s));
+    KOCR_TRY(stage_cnn_encoder(h, s, 4, /*add_global_pos=*/false));
+    KOCR_CUDA(cudaMemcpyAsync(x.data(), buf<float>(h, "x"), x.size() * 4, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(wait_stream(h, s));
+    for (int tok = 0; tok < TOK_PER_CHUNK; ++tok)
+        for (int i = 0; i < n; ++i)
+            memcpy(out + ((size_t)tok * n + i) * D_MODEL, x.data() + ((size_t)i * TOK_PER_CHUNK + tok) * D_MODEL, D_MODEL * 4);
+    return 0;
+}
+
+namespace {
+// uploads B sequences of (at most) T rows each into the token-major fp32 buffer `name` (+ its 16-bit twin) at the padded offsets
+int upload_sequences(kocr_handle* h, const char* name, const char* name16, const float* src, int B, int T, const int* Ti, cudaStream_t s) {
+    std::vector<float> x((size_t)h->n_tok * D_MODEL, 0.f);
+    std::vector<act16_t> xb((size_t)h->n_tok * D_MODEL, host_a16(0.f));
+    for (int b = 0; b < B; ++b) {
+        const size_t off = (size_t)h->line_first_chunk[b] * TOK_PER_CHUNK;
+        for (int t = 0; t < Ti[b]; ++t)
+            for (int d = 0; d < D_MODEL; ++d) {
+                const float v = src[((size_t)b * T + t) * D_MODEL + d];
+                x[(off + t) * D_MODEL + d] = v;
+                xb[(off + t) * D_MODEL + d] = host_a16(v);
+            }
+    }
+    KOCR_CUDA(cudaMemcpyAsync(buf<float>(h, name), x.data(), x.size() * 4, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(cudaMemcpyAsync(buf<act16_t>(h, name16), xb.data(), xb.size() * 2, cudaMemcpyHostToDevice, s));
+    KOCR_CUDA(wait_stream(h, s));              // host vectors of this call
+    return 0;
+}
+}  // namespace
+
+int kocr_model_bilstm(kocr_handle* h, const float* merged, int B, int T, float* out, void* stream) {
+    KOCR_CHECK(h != nullptr && merged != nullptr && out != nullptr, "kocr_model_bilstm: null argument");
+    KOCR_CHECK(h->variant == 0, "kocr_model_bilstm: this checkpoint family has no context_bilstm");
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    std::vector<int> Ti((size_t)B, T);
+    KOCR_TRY(set_token_tables(h, B, Ti.data(), s));
+    KOCR_TRY(upload_sequences(h, "x", "xb", merged, B, T, Ti.data(), s));
+    KOCR_TRY(stage_memory(h, s, 1));
+    std::vector<float> mem((size_t)h->n_tok * D_MODEL);
+    KOCR_CUDA(cudaMemcpyAsync(mem.data(), buf<float>(h, "mem"), mem.size() * 4, cudaMemcpyDeviceToHost, s));
+    KOCR_CUDA(wait_stream(h, s));
+    for (int b = 0; b < B; ++b)
+        memcpy(out + (size_t)b * T * D_MODEL, mem.data() + (size_t)h->line_first_chunk[b] * TOK_PER_CHUNK * D_MODEL, (size_t)T * D_MODEL * 4);
+    return 0;
+}
+
+int kocr_model_dec(kocr_handle* h, const int32_t* tgt, int B, int t, const float* memory, int T, const uint8_t* pad_mask,
+                   float* logits_out, void* stream) {
+    KOCR_CHECK(h != nullptr && tgt != nullptr && memory != nullptr && logits_out != nullptr, "kocr_model_dec: null argument");
+    KOCR_CHECK(t >= 1 && t <= h->dec_max_len, "kocr_model_dec: target length %d outside [1, %d]", t, h->dec_max_len);
+    KOCR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->own_stream;
+    std::vector<int> Ti((size_t)B, T);
+    for (int b = 0; b < B && pad_mask; ++b) {          // memory_key_padding_mask: a suffix of padded positions per line
+        int n = T;
+        while (n > 0 && pad_mask[(size_t)b * T + n - 1]) --n;
+        for (int j = 0; j < n; ++j)
+            KOCR_CHECK(!pad_mask[(size_t)b * T + j], "kocr_model_dec: memory_key_padding_mask of line %d is not a suffix mask", b);
+        KOCR_CHECK(n > 0, "kocr_model_dec: line %d has every memory position masked", b);
+        Ti[b] = n;
+    }
+    KOCR_TRY(set_token_tables(h, B, Ti.data(), s));
+    const bool lstm = h->variant == 0;
+    KOCR_TRY(upload_sequences(h, lstm ? "mem" : "x", lstm ? "memb" : "xb", memory, B, T, Ti.data(), s));
+    KOCR_TRY(stage_memory(h, s, 2));                   // cross-attention K/V of the given memory
+    return run_forced_decode(h, tgt, B, t, logits_out, VOCAB, stream, s);
 }
 
 int kocr_crop_lines(kocr_handle* h, const uint8_t* page, int page_h, int page_w, int channels, int page_on_device,

@@ -23,6 +23,38 @@ plan_batches = _core.scheduling.plan_batches
 logger = logging.getLogger(__name__)
 
 
+def _attach_model_protocol(rec, sd, variant):
+    """The attributes the reference's predictor uses on `self.model` (predictor.py:26-31,53-78,166-192): `cnn(chunks)`,
+    `patch(f) -> (x, N)`, `enc(p)` seq-first, `global_pos`, `context_bilstm(merged) -> (out, state)` (SE-VGG family only: the
+    reference probes it with hasattr) and `dec(tgt, memory, mask)`, on torch tensors, backed by the kocr_model_* entry points.
+    With them the reference's own OCRPredictor code runs unchanged on this object (tests/test_gpu_model_protocol.py)."""
+    import torch
+
+    def f32(t):
+        return t.detach().cpu().float().numpy() if hasattr(t, "detach") else np.asarray(t, np.float32)
+
+    rec.global_pos = torch.from_numpy(np.array(sd["global_pos"], np.float32))
+    rec.cnn = lambda chunks: torch.from_numpy(rec.model_cnn(f32(chunks)))
+    rec.patch = lambda f: (torch.from_numpy(rec.model_patch(f32(f))), 32)
+    rec.enc = lambda p: torch.from_numpy(rec.model_enc(f32(p)))
+    if variant == "se":
+        class _ContextBiLSTM:
+            def __call__(self, merged):
+                return torch.from_numpy(rec.model_bilstm(f32(merged))), None
+
+            def flatten_parameters(self):           # (predictor.py:75 calls it on the nn.LSTM)
+                pass
+        rec.context_bilstm = _ContextBiLSTM()
+
+    def dec(tgt, memory, mask=None):
+        tg = tgt.detach().cpu().numpy() if hasattr(tgt, "detach") else np.asarray(tgt)
+        mk = None if mask is None else (mask.detach().cpu().numpy() if hasattr(mask, "detach") else np.asarray(mask))
+        return torch.from_numpy(rec.model_dec(tg.astype(np.int32), f32(memory), None if mk is None else mk.astype(np.uint8)))
+    rec.dec = dec
+    rec.eval = lambda: rec                      # (nn.Module no-ops the reference calls on its model)
+    rec.to = lambda *a, **k: rec
+
+
 class OCRPredictor:
     def __init__(self, model_path, tokenizer: Tokenizer, config: OCRConfig, model_class,
                  max_lines: int = 256, max_chunks: int = 2816, in_flight: int = 6):
@@ -57,6 +89,7 @@ class OCRPredictor:
         self._pipe = _core.pipeline().LinePipeline(pack_blob(sd), device=index, in_flight=self._in_flight,
                                                    max_lines=self._max_lines, max_chunks=self._max_chunks)
         self.model = self._pipe.recs[0]
+        _attach_model_protocol(self.model, sd, variant)
 
     def close(self):
         """Release every device handle of the predictor (weights, workspaces, streams)."""
@@ -85,10 +118,24 @@ class OCRPredictor:
     def _recognize_gray(self, grays):
         """Greedy recognition of grey uint8 lines through the pipeline: batches within the handles' capacity (sorted by
         length, results in input order), several passes in flight, the long tail of every pass pooled and decoded
-        together (pipeline.py).  Greedy decoding is deterministic and lines are independent: results do not depend on
-        the batching."""
-        tokens, lengths = self._pipe.recognize(grays, max_steps=self.cfg.decode_max_len)
-        return self._decode_ids(tokens, lengths)
+        together (pipeline.py); every batch is detokenised by its worker thread as soon as its last line is final, while
+        the other passes are still on the GPU.  Greedy decoding is deterministic and lines are independent: results do
+        not depend on the batching."""
+        n = len(grays)
+        texts = [None] * n
+        if n == 0:
+            return texts
+        Job = _core.pipeline().Job
+        tokens = np.zeros((n, _core.native.TOKENS_LD), np.int32)
+        lengths = np.zeros(n, np.int32)
+        jobs = [Job(ids, images=[grays[i] for i in ids]) for ids in self._pipe.plan([g.shape for g in grays])]
+
+        def on_done(job):
+            for i, text in zip(job.ids, self._decode_ids(tokens[job.ids], lengths[job.ids])):
+                texts[i] = text
+
+        self._pipe.run_jobs(jobs, tokens, lengths, max_steps=self.cfg.decode_max_len, image_of=lambda i: grays[i], on_done=on_done)
+        return texts
 
     # ------------------------------------------------------------------------------------
     def _beam_search_batch(self, n_lines: int, beam_width: int) -> list:
