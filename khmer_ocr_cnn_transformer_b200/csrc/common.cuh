@@ -101,18 +101,6 @@ inline cudaError_t opt_in_dynamic_smem(PerDeviceOnce& st, K kernel, int bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Geometry of a "padded-linear" NHWC activation:
-// per chunk (H+1) rows of pitch P = W+1 positions; position (h, w) with h == H or w == W is a
-// zero pad, shared by the neighbouring row / chunk, so that a 3x3 tap is a pure row shift.
-// ------------------------------------------------------------------------------------------
-struct PLGeom {
-    int H, W, P, S;     // P = W + 1, S = (H + 1) * P rows per chunk
-};
-__host__ __device__ inline PLGeom make_pl(int H, int W) {
-    PLGeom g; g.H = H; g.W = W; g.P = W + 1; g.S = (H + 1) * (W + 1); return g;
-}
-
-// ------------------------------------------------------------------------------------------
 // Device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

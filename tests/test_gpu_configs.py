@@ -140,3 +140,34 @@ def test_c5_vgg_trained_fixture_tokens_batch_1024():
             assert np.array_equal(t2[j, :l2[j]], z[f"tokens{i}"])
     finally:
         rec.close()
+
+
+def test_handles_on_two_devices_in_one_process():
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a handle created on cuda:1 AFTER one on cuda:0 in the
+    same process must work and decode the same ids, also through the model-level pipeline object.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from khmer_ocr_cnn_transformer_b200 import _native, weights
+    from khmer_ocr_cnn_transformer_b200.checkpoint import load_checkpoint
+    from khmer_ocr_cnn_transformer_b200.pipeline import LinePipeline
+    z = np.load(GOLDEN / "golden_se.npz")
+    blob = weights.pack_blob(load_checkpoint(GOLDEN / "fixture_se_ckpt.npz"))
+    imgs = [z[f"img{i}"] for i in range(int(z["n_lines"]))]
+    recs = [_native.Recognizer(blob, device=d, max_lines=16, max_chunks=256) for d in (0, 1)]
+    try:
+        outs = [r.recognize_lines(_native.LineBatch(imgs)) for r in recs]
+        outs.append(recs[0].recognize_lines(_native.LineBatch(imgs)))        # back on device 0 after device 1 was current
+        for tok, ln in outs:
+            for i in range(len(imgs)):
+                assert np.array_equal(tok[i, :ln[i]], z[f"tokens{i}"]), i
+    finally:
+        for r in recs:
+            r.close()
+    pipe = LinePipeline(blob, device=1, in_flight=2, max_lines=4, max_chunks=64)
+    try:
+        tok, ln = pipe.recognize(imgs)
+        for i in range(len(imgs)):
+            assert np.array_equal(tok[i, :ln[i]], z[f"tokens{i}"]), i
+    finally:
+        pipe.close()
