@@ -3,8 +3,9 @@ signatures (reference: netra_ocr/recognition/predictor.py:12-199), running on li
 
 Differences that do not change results: chunks of many lines are batched on the GPU regardless of
 `batch_size` (lines are independent, predictor.py:150-193), BiLSTM/decoding are batched across lines
-with a KV cache instead of one line and one full-prefix pass per token.  Beam search (beam_width > 1) keeps the
-reference's bookkeeping on the host and runs each decoder position for all hypotheses on the GPU.
+with a KV cache instead of one line and one full-prefix pass per token.  Beam search (beam_width > 1) runs inside the
+library for all lines of a batch (kocr_beam_search: the reference's bookkeeping, KV-cached positions).  `self.model` is the
+device handle and carries the reference's model protocol (cnn / patch / enc / global_pos / context_bilstm / dec).
 There is no CPU path."""
 import logging
 from pathlib import Path
