@@ -225,13 +225,16 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 
 static constexpr int SE_W = 25;            // columns of every SE stage (100 / 4)
 static constexpr int SE_THREADS = 256;
 
-template <int C> struct SeSmem {
+template <int C, bool FRAG> struct SeSmem {
     static constexpr int R = C / 16;                       // reduced width (se_model.py:9,13)
     static constexpr int LDA = C + 8;                      // a16 elements per row of the means (conflict-free frags)
     static constexpr int LDZ = R + 8;
+    // gate row stride in floats: + 8 spreads the 8 accumulator rows of an FC2 store over the banks (2 wavefronts per
+    // float2 store instead of 8 - ncu, round 2: 45 % of the kernel's shared-memory wavefronts were bank conflicts)
+    static constexpr int LDG = FRAG ? C + 8 : C;
     static constexpr size_t A_BYTES = 32 * LDA * 2;
     static constexpr size_t Z_BYTES = 32 * LDZ * 2;
-    static constexpr size_t G_BYTES = (size_t)SE_W * C * 4;
+    static constexpr size_t G_BYTES = (size_t)SE_W * LDG * 4;
     // the gate (written by FC2) re-uses the storage of the column means (dead once FC1 is done); the final-pool variant
     // adds room for the chunk's 25 x 2 row-bin sums
     static constexpr size_t AG_BYTES = A_BYTES > G_BYTES ? A_BYTES : G_BYTES;
@@ -241,16 +244,22 @@ template <int C> struct SeSmem {
 
 // ROWS = pooled rows per column (H/2) - or 2 row-bin sums when FINAL.  FINAL = false: pooled is scaled in place;
 // FINAL = true: pooled = bins [col][2][C], out = patch operand [n*32 + k][kh*C + c].
-template <int C, int ROWS, bool FINAL>
-__global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t* __restrict__ means /*[n*25 + w][C]*/,
+// PREFETCH = true: the pooled block is loaded into registers before the contractions (76 registers: 2 CTAs per SM);
+// PREFETCH = false (not FINAL): the block is streamed load -> scale -> store after them (<= 64 registers: 4 CTAs per SM).
+// FRAG = true: the FC weights are read in mma-fragment order (w0f / w2f, weights.se_fragments): one coalesced 16-byte load
+// per lane covers two k-steps, where the row-major layout (w0p / w2p) costs 8 L1 wavefronts per 4-byte fragment load - the
+// L1/TEX pipe was the busiest unit of this kernel (ncu: 61-71 %).
+template <int C, int ROWS, bool FINAL, bool PREFETCH, bool FRAG>
+__global__ void __launch_bounds__(SE_THREADS, PREFETCH ? 2 : 4) se_excite_kernel(const act16_t* __restrict__ means /*[n*25 + w][C]*/,
                                                                   const act16_t* __restrict__ w0p /*[128][C]*/,
                                                                   const float* __restrict__ b0p,
                                                                   const act16_t* __restrict__ w2p /*[C][128]*/,
                                                                   const float* __restrict__ b2,
+                                                                  const act16_t* __restrict__ w0f, const act16_t* __restrict__ w2f,
                                                                   act16_t* __restrict__ pooled, act16_t* __restrict__ out,
                                                                   int n_chunks) {
-    using S = SeSmem<C>;
-    constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8;
+    using S = SeSmem<C, FRAG>;
+    constexpr int R = S::R, LDA = S::LDA, LDZ = S::LDZ, CG = C / 8, LDG = S::LDG;
     extern __shared__ __align__(16) uint8_t se_smem[];
     act16_t* sZ = reinterpret_cast<act16_t*>(se_smem);
     act16_t* sA = reinterpret_cast<act16_t*>(se_smem + S::Z_BYTES);
@@ -266,11 +275,13 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
     constexpr int TOTAL = SE_W * ROWS * CG;                 // 16-byte pieces of the block
     constexpr int PER_THREAD = (TOTAL + SE_THREADS - 1) / SE_THREADS;
     const uint4* blk_in = reinterpret_cast<const uint4*>(pooled + (long)n * SE_W * ROWS * C);
-    uint4 pre[PER_THREAD];
+    uint4 pre[PREFETCH ? PER_THREAD : 1];
+    if (PREFETCH) {
 #pragma unroll
-    for (int i = 0; i < PER_THREAD; ++i) {
-        const int idx = tid + i * SE_THREADS;
-        pre[i] = idx < TOTAL ? __ldg(blk_in + idx) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < PER_THREAD; ++i) {
+            const int idx = tid + i * SE_THREADS;
+            pre[i] = idx < TOTAL ? __ldg(blk_in + idx) : make_uint4(0, 0, 0, 0);
+        }
     }
     // ---- column means (16-bit, written by the conv epilogue from its fp32 accumulators) -> A operand [32][C] (rows 25..31 zero) ----
     {
@@ -289,17 +300,33 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
             const int mt = warp / NT, nt = warp % NT;
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             const act16_t* arow0 = sA + (mt * 16 + g) * LDA + 2 * t;
-            const act16_t* wrow = w0p + (long)(nt * 8 + g) * C + 2 * t;
-#pragma unroll 8
-            for (int k = 0; k < C; k += 16) {
-                uint32_t a[4];
+            auto a_frag = [&](int k, uint32_t (&a)[4]) {
                 a[0] = *reinterpret_cast<const uint32_t*>(arow0 + k);
                 a[1] = *reinterpret_cast<const uint32_t*>(arow0 + 8 * LDA + k);
                 a[2] = *reinterpret_cast<const uint32_t*>(arow0 + k + 8);
                 a[3] = *reinterpret_cast<const uint32_t*>(arow0 + 8 * LDA + k + 8);
-                const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k));
-                const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8));
-                mma_a16_16816(d, a, b0, b1);
+            };
+            if (FRAG) {
+                const uint4* wf = reinterpret_cast<const uint4*>(w0f) + (long)nt * (C / 32) * 32 + lane;
+#pragma unroll 4
+                for (int kp = 0; kp < C / 32; ++kp) {
+                    const uint4 b = __ldg(wf + kp * 32);
+                    uint32_t a[4];
+                    a_frag(kp * 32, a);
+                    mma_a16_16816(d, a, b.x, b.y);
+                    a_frag(kp * 32 + 16, a);
+                    mma_a16_16816(d, a, b.z, b.w);
+                }
+            } else {
+                const act16_t* wrow = w0p + (long)(nt * 8 + g) * C + 2 * t;
+#pragma unroll 8
+                for (int k = 0; k < C; k += 16) {
+                    uint32_t a[4];
+                    a_frag(k, a);
+                    const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k));
+                    const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8));
+                    mma_a16_16816(d, a, b0, b1);
+                }
             }
             const int col = nt * 8 + 2 * t;
             const float bb0 = __ldg(b0p + col), bb1 = __ldg(b0p + col + 1);
@@ -326,12 +353,23 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
 #pragma unroll 4
         for (int i = 0; i < NT_PER_WARP; ++i) {
             const int c0 = (warp * NT_PER_WARP + i) * 8;
-            const act16_t* wrow = w2p + (long)(c0 + g) * 128 + 2 * t;
             uint32_t b[KS][2];
+            if (FRAG) {
+                const int ntile = warp * NT_PER_WARP + i;
+                if (KS == 2) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(w2f) + ntile * 32 + lane);
+                    b[0][0] = v.x; b[0][1] = v.y; b[KS - 1][0] = v.z; b[KS - 1][1] = v.w;
+                } else {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(w2f) + ntile * 32 + lane);
+                    b[0][0] = v.x; b[0][1] = v.y;
+                }
+            } else {
+                const act16_t* wrow = w2p + (long)(c0 + g) * 128 + 2 * t;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                b[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16));
-                b[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8));
+                for (int ks = 0; ks < KS; ++ks) {
+                    b[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16));
+                    b[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8));
+                }
             }
             const int col = c0 + 2 * t;
             const float bb0 = __ldg(b2 + col), bb1 = __ldg(b2 + col + 1);
@@ -342,10 +380,10 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
                 for (int ks = 0; ks < KS; ++ks) mma_a16_16816(d, a[mt][ks], b[ks][0], b[ks][1]);
                 const int r0 = mt * 16 + g, r1 = r0 + 8;
                 if (r0 < SE_W)
-                    *reinterpret_cast<float2*>(sG + r0 * C + col) =
+                    *reinterpret_cast<float2*>(sG + r0 * LDG + col) =
                         make_float2(fast_sigmoid(d[0] + bb0), fast_sigmoid(d[1] + bb1));
                 if (r1 < SE_W)
-                    *reinterpret_cast<float2*>(sG + r1 * C + col) =
+                    *reinterpret_cast<float2*>(sG + r1 * LDG + col) =
                         make_float2(fast_sigmoid(d[2] + bb0), fast_sigmoid(d[3] + bb1));
             }
         }
@@ -354,18 +392,36 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
     // ---- excite ----
     if (!FINAL) {
         uint4* blk = reinterpret_cast<uint4*>(pooled + (long)n * SE_W * ROWS * C);    // scaled in place
+        auto scale = [&](int idx, const uint4 o) {
+            const int cg = idx % CG, w = idx / (ROWS * CG);
+            const float4 ga = *reinterpret_cast<const float4*>(sG + w * LDG + cg * 8);
+            const float4 gb = *reinterpret_cast<const float4*>(sG + w * LDG + cg * 8 + 4);
+            blk[idx] = make_uint4(pack_a16(a16_lo(o.x) * ga.x, a16_hi(o.x) * ga.y),
+                                  pack_a16(a16_lo(o.y) * ga.z, a16_hi(o.y) * ga.w),
+                                  pack_a16(a16_lo(o.z) * gb.x, a16_hi(o.z) * gb.y),
+                                  pack_a16(a16_lo(o.w) * gb.z, a16_hi(o.w) * gb.w));
+        };
+        if (PREFETCH) {
 #pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            const int idx = tid + i * SE_THREADS;
-            if (idx < TOTAL) {
-                const int cg = idx % CG, w = idx / (ROWS * CG);
-                const uint4 o = pre[i];
-                const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
-                const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
-                blk[idx] = make_uint4(pack_a16(a16_lo(o.x) * ga.x, a16_hi(o.x) * ga.y),
-                                      pack_a16(a16_lo(o.y) * ga.z, a16_hi(o.y) * ga.w),
-                                      pack_a16(a16_lo(o.z) * gb.x, a16_hi(o.z) * gb.y),
-                                      pack_a16(a16_lo(o.w) * gb.z, a16_hi(o.w) * gb.w));
+            for (int i = 0; i < PER_THREAD; ++i) {
+                const int idx = tid + i * SE_THREADS;
+                if (idx < TOTAL) scale(idx, pre[i]);
+            }
+        } else {
+            // streamed: 4 loads in flight per thread, 32 warps per SM
+            constexpr int FULL = TOTAL / SE_THREADS / 4 * 4;
+#pragma unroll 1
+            for (int i0 = 0; i0 < FULL; i0 += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __ldg(blk_in + tid + (i0 + j) * SE_THREADS);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) scale(tid + (i0 + j) * SE_THREADS, v[j]);
+            }
+#pragma unroll
+            for (int i = FULL; i < PER_THREAD; ++i) {
+                const int idx = tid + i * SE_THREADS;
+                if (idx < TOTAL) scale(idx, __ldg(blk_in + idx));
             }
         }
     } else {
@@ -385,8 +441,8 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
             const int w0 = (k * SE_W) / TOK_PER_CHUNK, w1 = ((k + 1) * SE_W + TOK_PER_CHUNK - 1) / TOK_PER_CHUNK;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int w = w0; w < w1; ++w) {
-                const float4 ga = *reinterpret_cast<const float4*>(sG + w * C + cg * 8);
-                const float4 gb = *reinterpret_cast<const float4*>(sG + w * C + cg * 8 + 4);
+                const float4 ga = *reinterpret_cast<const float4*>(sG + w * LDG + cg * 8);
+                const float4 gb = *reinterpret_cast<const float4*>(sG + w * LDG + cg * 8 + 4);
                 const uint4 a = bins[(w * 2 + kh) * CG + cg];
                 acc[0] += a16_lo(a.x) * ga.x; acc[1] += a16_hi(a.x) * ga.y;
                 acc[2] += a16_lo(a.y) * ga.z; acc[3] += a16_hi(a.y) * ga.w;
@@ -402,17 +458,23 @@ __global__ void __launch_bounds__(SE_THREADS, 2) se_excite_kernel(const act16_t*
     }   // chunk loop
 }
 
-template <int C, int ROWS, bool FINAL>
+static int g_se_stream_variant = 4;
+void set_se_excite_variant(int v) { g_se_stream_variant = v; }
+
+template <int C, int ROWS, bool FINAL, bool PREFETCH, bool FRAG>
 static int launch_se_excite_impl(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks,
                                  cudaStream_t stream) {
-    const size_t smem = SeSmem<C>::BYTES + (FINAL ? SeSmem<C>::BINS_BYTES : 0);
+    size_t smem = SeSmem<C, FRAG>::BYTES + (FINAL ? SeSmem<C, FRAG>::BINS_BYTES : 0);
+    int per_sm = PREFETCH ? 2 : 4;
+    if (!PREFETCH && g_se_stream_variant % 100 == 3) { per_sm = 3; if (smem < 72 * 1024) smem = 72 * 1024; }   // (probe: 3 CTAs per SM)
     static PerDeviceOnce attr_once;
-    KOCR_CUDA(opt_in_dynamic_smem(attr_once, se_excite_kernel<C, ROWS, FINAL>, (int)smem));
+    KOCR_CUDA(opt_in_dynamic_smem(attr_once, se_excite_kernel<C, ROWS, FINAL, PREFETCH, FRAG>, 72 * 1024 > (int)smem ? 72 * 1024 : (int)smem));
     int dev = 0, sms = 148;
     KOCR_CUDA(cudaGetDevice(&dev));
     KOCR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = n_chunks < 2 * sms ? n_chunks : 2 * sms;
-    se_excite_kernel<C, ROWS, FINAL><<<grid, SE_THREADS, smem, stream>>>(means, w.w0p, w.b0p, w.w2p, w.b2, pooled, out, n_chunks);
+    const int grid = n_chunks < per_sm * sms ? n_chunks : per_sm * sms;
+    se_excite_kernel<C, ROWS, FINAL, PREFETCH, FRAG><<<grid, SE_THREADS, smem, stream>>>(means, w.w0p, w.b0p, w.w2p, w.b2, w.w0f, w.w2f, pooled, out,
+                                                                                       n_chunks);
     KOCR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -421,9 +483,21 @@ static int launch_se_excite_impl(const act16_t* means, const SEWeights& w, act16
 int launch_se_excite(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
                      int C, bool final_pool, cudaStream_t stream) {
     if (n_chunks == 0) return 0;
-    if (W == SE_W && C == 256 && rows == 6 && !final_pool) return launch_se_excite_impl<256, 6, false>(means, w, pooled, out, n_chunks, stream);
-    if (W == SE_W && C == 512 && rows == 3 && !final_pool) return launch_se_excite_impl<512, 3, false>(means, w, pooled, out, n_chunks, stream);
-    if (W == SE_W && C == 512 && rows == 2 && final_pool) return launch_se_excite_impl<512, 2, true>(means, w, pooled, out, n_chunks, stream);
+    // g_se_stream_variant (option "se_variant", probes only): 4 (default) / 3 = fragment-order weights, pooled block streamed
+    // after the gate with 4 / 3 CTAs per SM; 0 = fragment-order weights + register prefetch (2 CTAs per SM); 100 + v = the
+    // same with the row-major weights (the kernel of the first half of round 2).  Measured (tools/se_probe.py, 2039 chunks,
+    // se3 + se4 + se5): 100: 0.418 ms, 104: 0.400, 0: 0.334, 4: 0.301 - all bit-identical.
+    const bool frag = g_se_stream_variant < 100;
+    const bool streamed = g_se_stream_variant % 100 != 0;
+#define KOCR_SE(CC, RR, FF)                                                                                                      \
+    if (frag) return streamed && !FF ? launch_se_excite_impl<CC, RR, FF, FF, true>(means, w, pooled, out, n_chunks, stream)      \
+                                     : launch_se_excite_impl<CC, RR, FF, true, true>(means, w, pooled, out, n_chunks, stream);   \
+    return streamed && !FF ? launch_se_excite_impl<CC, RR, FF, FF, false>(means, w, pooled, out, n_chunks, stream)               \
+                           : launch_se_excite_impl<CC, RR, FF, true, false>(means, w, pooled, out, n_chunks, stream);
+    if (W == SE_W && C == 256 && rows == 6 && !final_pool) { KOCR_SE(256, 6, false) }
+    if (W == SE_W && C == 512 && rows == 3 && !final_pool) { KOCR_SE(512, 3, false) }
+    if (W == SE_W && C == 512 && rows == 2 && final_pool) { KOCR_SE(512, 2, true) }
+#undef KOCR_SE
     KOCR_CHECK(false, "se_excite: unsupported geometry rows=%d W=%d C=%d final=%d", rows, W, C, (int)final_pool);
     return 2;
 }

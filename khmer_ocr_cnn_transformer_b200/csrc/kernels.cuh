@@ -49,7 +49,9 @@ int launch_pool_h2(const act16_t* in, act16_t* out, int n_chunks, int H, int W, 
 int launch_finalpool(const act16_t* in, int rows_in, act16_t* out, int n_chunks, int W, int C, cudaStream_t stream);
 // 1D-SE excitation on the 16-bit column means [n*W + w][C] written by the conv epilogue: gate = sigmoid(FC2(relu(FC1(mean))));
 // pooled [col][rows][C] *= gate in place, or (final_pool) gate * row-bin sums -> AdaptiveAvgPool2d((2,32)) -> out.
-struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; const float* b2; };
+struct SEWeights { const act16_t* w0p; const float* b0p; const act16_t* w2p; const float* b2;
+                   const act16_t* w0f; const act16_t* w2f; };   // w0f / w2f: the same weights in mma fragment order (weights.se_fragments)
+void set_se_excite_variant(int v);   // probe hook, see launch_se_excite (cnn_misc.cu)
 int launch_se_excite(const act16_t* means, const SEWeights& w, act16_t* pooled, act16_t* out, int n_chunks, int rows, int W,
                      int C, bool final_pool, cudaStream_t stream);
 

@@ -208,6 +208,8 @@ int resolve_weights(kocr_handle* h) {
             snprintf(nm, sizeof nm, "se%d.b0p", i + 3); W_F32(h->se[i].b0p, nm, 128);
             snprintf(nm, sizeof nm, "se%d.w2p", i + 3); W_A16(h->se[i].w2p, nm, C * 128);
             snprintf(nm, sizeof nm, "se%d.b2", i + 3); W_F32(h->se[i].b2, nm, C);
+            snprintf(nm, sizeof nm, "se%d.w0f", i + 3); W_A16(h->se[i].w0f, nm, C / 16 * C);
+            snprintf(nm, sizeof nm, "se%d.w2f", i + 3); W_A16(h->se[i].w2f, nm, C * (C / 16));
         }
         W_A16(h->lstm_w_ih, "lstm.w_ih", 8 * LSTM_H * D);
         W_A16(h->lstm_w_ih3, "lstm.w_ih3", 8 * LSTM_H * 3 * D);
@@ -1206,6 +1208,7 @@ int kocr_set_option(kocr_handle* h, const char* name, int value) {
     if (strcmp(name, "lstm_split") == 0) { h->lstm_split = value; return 0; }
     if (strcmp(name, "compact_rows") == 0) { h->compact_rows = value; return 0; }
     if (strcmp(name, "dec_cross_impl") == 0) { set_dec_cross_attention_impl(value); return 0; }          // process-wide
+    if (strcmp(name, "se_variant") == 0) { set_se_excite_variant(value); return 0; }                      // process-wide
     if (strcmp(name, "gemm_bn192") == 0) { set_gemm_bn192(value); return 0; }                             // process-wide
     if (strcmp(name, "chunk_attn_impl") == 0) { set_chunk_attention_impl(value); return 0; }   // process-wide
     if (strcmp(name, "debug_stop") == 0) { h->debug_stop = value; return 0; }

@@ -179,6 +179,8 @@ def pack_tensors(sd: dict) -> dict:
             bf16(f"se{k}.w0p", w0p)
             f32(f"se{k}.b0p", b0p)
             bf16(f"se{k}.w2p", w2p)
+            bf16(f"se{k}.w0f", se_fragments(w0))                  # the same weights in mma.sync B-fragment order
+            bf16(f"se{k}.w2f", se_fragments(w2))
             f32(f"se{k}.b2", sd[f"cnn.se{k}.fc.2.bias"])
     if not resnet:
         bf16("conv7.w", conv_to_kmajor(w7))
@@ -232,6 +234,26 @@ def pack_tensors(sd: dict) -> dict:
     tf32("dec.out_w", ow)
     f32("dec.out_b", ob)
     return t
+
+
+def se_fragments(w: np.ndarray) -> np.ndarray:
+    """w [N][K] (out, in) -> the B operand of `mma.sync.m16n8k16` (B[k][n] = w[n][k]) in FRAGMENT order: for every n-tile of 8
+    outputs and every k-step of 16, lane (g = lane >> 2, t = lane & 3) holds {w[n0+g][k0+2t], w[n0+g][k0+2t+1]} (b0) and
+    {w[n0+g][k0+8+2t], w[n0+g][k0+9+2t]} (b1); laid out [n-tile][k-step PAIR][lane][8 values] (K = 16: [n-tile][lane][4]), so a
+    warp reads its fragments of two k-steps with ONE coalesced 16-byte load per lane (se_excite_kernel, csrc/cnn_misc.cu)."""
+    N, K = w.shape
+    assert N % 8 == 0 and K % 16 == 0
+    lane = np.arange(32)
+    g, t = lane >> 2, lane & 3
+    koff = np.stack([2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9], axis=1)              # [32][4] within a k-step
+    ks = np.arange(K // 16)
+    n_idx = (np.arange(N // 8)[:, None, None, None] * 8 + g[None, None, :, None])   # [NT][1][32][1]
+    k_idx = ks[None, :, None, None] * 16 + koff[None, None, :, :]                   # [1][KS][32][4]
+    frag = w[n_idx, k_idx]                                                          # [NT][KS][32][4]
+    if K // 16 >= 2:
+        assert (K // 16) % 2 == 0
+        frag = frag.reshape(N // 8, K // 32, 2, 32, 4).transpose(0, 1, 3, 2, 4)     # [NT][KP][32][2][4]
+    return np.ascontiguousarray(frag, np.float32).reshape(-1)
 
 
 def pack_blob(sd: dict) -> bytes:
