@@ -212,8 +212,9 @@ int launch_finalpool(const act16_t* in, int rows_in, act16_t* out, int n_chunks,
 //     gate[25][C] = sigmoid(W2 relu(W0 mean + b0) + b2)            two [25 -> 32] x C x C/16 contractions
 //     pooled[w][r][c] *= gate[w][c]                                 (gate > 0: max-pool and gate commute exactly)
 // or, for the last block, gate * row-bin sums -> AdaptiveAvgPool2d((2,32)) -> patch operand.
-// ONE CTA per chunk; the contractions are far below a tcgen05 tile, so they run on mma.sync.m16n8k16 (a16, fp32
-// accumulate) with the means / hidden vector as A operands in shared memory and the weights read from L2 as B fragments.
+// Persistent CTAs, one chunk per iteration; the contractions are far below a tcgen05 tile, so they run on
+// mma.sync.m16n8k16 (a16, fp32 accumulate) with the means / hidden vector as A operands in shared memory and the weights
+// read through L1 as B fragments (fragment order: one coalesced 16-byte load per lane per two k-steps).
 // HBM traffic per chunk: 25*C*2 B of means + one read and one write of the POOLED tensor (the r01 kernel read the
 // un-pooled conv output twice).
 // ------------------------------------------------------------------------------------------
