@@ -309,3 +309,25 @@ def test_build_skips_missing_dependencies(monkeypatch, tmp_path):
     real = B.PKG.parent / "include" / "kocr.h"
     assert real.exists()
     assert isinstance(B.needs_build(), bool)
+
+
+def test_se_fragments_layout():
+    """weights.se_fragments: B operand of mma.sync.m16n8k16 in fragment order (lane (g, t) of n-tile nt, k-step ks holds
+    w[nt*8+g][ks*16 + 2t, +1] and [ks*16 + 8 + 2t, +1]; k-steps interleaved in pairs per lane)."""
+    from khmer_ocr_cnn_transformer_b200.weights import se_fragments
+    rng = np.random.default_rng(1)
+    for N, K in ((32, 512), (16, 256), (512, 32), (256, 16)):
+        w = rng.standard_normal((N, K)).astype(np.float32)
+        f = se_fragments(w)
+        assert f.shape == (N * K,) and np.array_equal(np.sort(f), np.sort(w.reshape(-1)))      # a permutation
+        pair = K // 16 >= 2
+        f = f.reshape(N // 8, K // 32, 32, 2, 4) if pair else f.reshape(N // 8, 1, 32, 1, 4)
+        for nt in (0, N // 8 - 1):
+            for lane in (0, 7, 18, 31):
+                g, t = lane >> 2, lane & 3
+                for ks in range(K // 16):
+                    got = f[nt, ks // 2, lane, ks % 2] if pair else f[nt, 0, lane, 0]
+                    k0 = ks * 16
+                    want = [w[nt * 8 + g, k0 + 2 * t], w[nt * 8 + g, k0 + 2 * t + 1], w[nt * 8 + g, k0 + 8 + 2 * t],
+                            w[nt * 8 + g, k0 + 9 + 2 * t]]
+                    assert np.array_equal(got, want)
