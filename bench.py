@@ -322,6 +322,7 @@ def main():
     max_chunks = args.max_chunks or (4096 if args.config == "c5" else 2816)
     pipe = LinePipeline(blob, device=local_rank, in_flight=S, max_lines=max_lines, max_chunks=max_chunks,
                         straggler_per_256=args.straggler_threshold)
+    pipe._ensure(S)      # every handle (weights + workspace) exists before anything is timed, also when a warm-up has fewer jobs than S
 
     def barrier():
         torch.cuda.synchronize()
