@@ -23,9 +23,7 @@ for margin in (12.0, 16.0, 20.0):
         chunks = O.preprocess_gray(img)[1]
         enc = O.encoder_forward(sd, O.patch_forward(sd, O.cnn_forward(sd, chunks, "se")))
         mem = O.memory_for_line(sd, enc, "se")
-        toks = [O.SOS] + [int(t) for t in O.greedy_decode(sd, mem)[0]] if isinstance(O.greedy_decode(sd, mem), tuple) else None
-        if toks is None:
-            toks = [O.SOS] + [int(t) for t in O.greedy_decode(sd, mem)]
+        toks = [int(t) for t in O.greedy_decode(sd, mem)]          # <sos> + decoded ids
         t = len(toks)
         tok = np.asarray(toks, np.int64)
         x = (sd["dec.tok_emb.weight"][tok] + sd["dec.pos_emb"][:t]).astype(np.float32)
